@@ -1,0 +1,211 @@
+/*
+ * grmonty_b200.h -- C ABI of the B200-native superphoton transport path.
+ *
+ * This is the drop-in boundary.  The reference has no plugin/FFI interface; its only
+ * seam is the `#ifdef CUDA` block of HARMModel::run_simulation (reference cuda_grmonty/harm_model.cpp:345-362)
+ * that calls three C++ free functions declared in cuda_grmonty/super_photon.cuh:29-61:
+ *
+ *     cuda_super_photon::alloc_memory(header, data, units, hotcross_table, f, k2)     -> grmonty_b200_create
+ *     cuda_super_photon::track_super_photons(bias_norm, max_tau_scatt, photon_queue,
+ *                                            stop_sem, spectrum, n_recorded, n_scatt) -> grmonty_b200_run
+ *                                                                                       + grmonty_b200_result
+ *     cuda_super_photon::free_memory()                                                -> grmonty_b200_destroy
+ *
+ * Differences by design: photon generation (reference harm_model.cpp:673-811, host threads feeding a queue
+ * in the reference GPU build, :842-892) happens on the device, so there is no photon queue/semaphore in the
+ * interface; errors are returned as codes (the reference's gpuErrchk calls exit(), utils.cuh:33-40); a context
+ * object replaces the reference's file-scope statics (super_photon.cu:36-71), so several contexts (one per
+ * GPU) can live in one process.
+ *
+ * Conventions: plain C structs and pointers, no C++ or torch types.  The caller owns every input buffer and
+ * may free it as soon as grmonty_b200_create returns (inputs are copied to the device).  Outputs are
+ * caller-allocated.  All functions return 0 on success or a negative GRMONTY_B200_E* code and never throw or
+ * exit.  A context is bound to one CUDA device and must be used by one host thread at a time.
+ * There is NO CPU fallback: without a CUDA device grmonty_b200_create fails with GRMONTY_B200_ECUDA.
+ */
+#ifndef GRMONTY_B200_H
+#define GRMONTY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRMONTY_B200_ABI_VERSION 1
+
+#define GRMONTY_B200_N_TH_BINS 6     /* reference consts.hpp:26 */
+#define GRMONTY_B200_N_E_BINS 200    /* reference consts.hpp:25 */
+#define GRMONTY_B200_SPEC_FIELDS 13  /* reference harm_data.hpp:129-143, same field order */
+#define GRMONTY_B200_HOTCROSS_N (221 * 81)
+#define GRMONTY_B200_TABLE_N 201
+#define GRMONTY_B200_NINT_N 20001
+#define GRMONTY_B200_PHOTON_FLAT 25  /* test exports: reference photon.hpp:19-36 order, n_scatt last */
+
+enum {
+    GRMONTY_B200_OK = 0,
+    GRMONTY_B200_EINVAL = -1,   /* bad argument / config */
+    GRMONTY_B200_ECUDA = -2,    /* CUDA runtime error (message in last_error) */
+    GRMONTY_B200_EQUEUE = -3,   /* device photon queue overflowed: raise queue_capacity or lower gen_cap */
+    GRMONTY_B200_ENCCL = -4,    /* NCCL not loadable / collective failed */
+    GRMONTY_B200_ESTATE = -5    /* call order violation */
+};
+
+typedef struct grmonty_b200_ctx grmonty_b200_ctx;
+
+/* Everything the transport path reads; mirrors what HARMModel holds after read_file() + init(). */
+typedef struct grmonty_b200_config {
+    uint32_t abi_version; /* GRMONTY_B200_ABI_VERSION */
+    uint32_t struct_size; /* sizeof(grmonty_b200_config) */
+
+    /* harm::Header subset, reference harm_data.hpp:19-44 */
+    int32_t n0, n1;
+    double x_start1, x_start2; /* x_start[1..2] */
+    double dx1, dx2, dx3;      /* dx[1..3] */
+    double x_stop1, x_stop2;   /* x_stop[1..2] */
+    double a, h_slope, r_0;
+
+    /* harm::Units, reference harm_data.hpp:63-72 */
+    double mass_unit, l_unit, t_unit, rho_unit, u_unit, b_unit, theta_e_unit, n_e_unit;
+
+    /* harm::Data, reference harm_data.hpp:49-58: eight row-major [n0][n1] host arrays */
+    const double *k_rho, *u, *u_1, *u_2, *u_3, *b_1, *b_2, *b_3;
+    /* geometry_.det, reference harm_model.cpp:261: sqrt|det g_cov| at zone centres, row-major [n0][n1] */
+    const double *geom_det;
+
+    /* tables, reference harm_model.hpp:159-195 */
+    const double *hotcross;   /* [221][81] log10 of the hot cross-section, hotcross.cpp:60-79 */
+    const double *f;          /* [201] ln F(K), jnu_mixed.cpp:57-65 */
+    const double *k2;         /* [201] ln K2(1/theta_e), jnu_mixed.cpp:67-70 */
+    const double *weight;     /* [201] ln weight, harm_model.cpp:268-306 */
+    const double *nint;       /* [20001] ln nint, harm_model.cpp:308-338 */
+    const double *dndlnu_max; /* [20001] ln dndlnu_max */
+
+    /* scalars, reference harm_model.hpp:104-125 */
+    double photon_n;       /* estimate of photon number (CLI -photon_n) */
+    double bias_norm;      /* harm_model.cpp:206,219 */
+    double max_tau_scatt0; /* initial max_tau_scatt, harm_model.cpp:72 */
+    uint64_t seed;         /* Philox key; the reference seeds mt19937 with 123 (main.cpp:49) */
+
+    /* sharding: this context tracks the primaries whose global index i satisfies i % world == rank */
+    int32_t rank, world;
+    int32_t device; /* CUDA device ordinal */
+
+    /* tuning, 0 = default */
+    int32_t threads_per_block;
+    int32_t blocks_per_sm;
+    int64_t queue_capacity; /* photon slots in the device queue */
+    int64_t gen0;           /* primaries (global) in the first generation; doubles each generation ... */
+    int64_t gen_cap;        /* ... up to this cap.  Bias statistics are frozen within a generation. */
+} grmonty_b200_config;
+
+/* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */
+typedef struct grmonty_b200_stats {
+    uint64_t n_tracked;        /* photons tracked (primaries + scattered children) */
+    uint64_t n_steps;          /* accepted geodesic steps */
+    uint64_t n_push_attempts;  /* push_photon attempts incl. halved sub-steps and scatter back-ups */
+    uint64_t n_interactions;   /* in-fluid interaction evaluations (reference harm_model.cpp:937 gate) */
+    uint64_t n_scatter_events; /* scatter_super_photon calls */
+    uint64_t n_generations;
+    uint64_t n_kernel_launches;
+    uint64_t queue_high_water;
+    double kernel_ms;          /* device time of all kernels of the last run (CUDA events) */
+    double transport_ms;       /* of which: the persistent transport kernel */
+} grmonty_b200_stats;
+
+/* ---- product entry points ---------------------------------------------------------------------------- */
+
+/* Allocate device state, copy the model to the device, build per-zone emission data (init_zone / tetrads,
+ * reference harm_model.cpp:1337-1389, :717-731) and the zone -> primary-index prefix table. */
+int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg);
+
+/* Total number of primary superphotons of the whole job (all ranks), = sum of the per-zone counts of
+ * reference harm_model.cpp:673-704. */
+int grmonty_b200_total_primaries(grmonty_b200_ctx *ctx, int64_t *total);
+
+/* Generate, transport and record this rank's share of primaries [first, last) of the global sequence
+ * (last < 0: to the end).  Blocking.  Replaces the CPU loop at reference harm_model.cpp:366-404. */
+int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last);
+/* = run_range(ctx, 0, -1) */
+int grmonty_b200_run(grmonty_b200_ctx *ctx);
+
+/* Sum the spectrum and counters (and max the scattering depth) over the ranks of `nccl_comm`
+ * (an ncclComm_t passed as void*).  NCCL is resolved at run time (dlopen); world == 1: no-op. */
+int grmonty_b200_allreduce(grmonty_b200_ctx *ctx, void *nccl_comm, void *cuda_stream);
+
+/* Device pointers of the accumulators, for hosts that do the reduction with their own collective library
+ * (e.g. torch.distributed):  spectrum: double[6*200*13]; counters: uint64[3] = created, scattered, recorded;
+ * max_tau_scatt: double[1]. */
+int grmonty_b200_device_accumulators(grmonty_b200_ctx *ctx, void **spectrum, void **counters, void **max_tau_scatt);
+
+/* Copy results to the host.  spectrum: [6][200][13] doubles in harm::Spectrum field order;
+ * counts: created, scattered (sum of n_scatt over recorded photons), recorded -- the three counters the
+ * reference logs (harm_model.cpp:409-413).  Any pointer may be NULL. */
+int grmonty_b200_result(grmonty_b200_ctx *ctx, double *spectrum, uint64_t counts[3], double *max_tau_scatt,
+                        grmonty_b200_stats *stats);
+
+/* Zero the accumulators and counters so the same context can run again. */
+int grmonty_b200_reset(grmonty_b200_ctx *ctx);
+
+void grmonty_b200_destroy(grmonty_b200_ctx *ctx);
+
+/* Message of the last error on this context (ctx == NULL: of the last failed create on this thread). */
+const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx);
+
+/* FP64 FMA throughput micro-benchmark on the context's device (TFLOP/s, FMA = 2 flop); the roofline
+ * denominator of this path (MEASURED_PEAKS.json has no FP64 entry). */
+int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops);
+
+/* ---- test-only batch exports (host arrays in / out), used by the parity tests --------------------------- */
+
+/* x: [n][4] -> gcov [n][16], gcon [n][16], conn [n][64] (full symmetric); any output may be NULL */
+int grmonty_b200_test_geometry(grmonty_b200_ctx *ctx, int64_t n, const double *x, double *gcov, double *gcon,
+                               double *conn);
+/* x,k: [n][4] -> dkdlam [n][4] (init_dkdlam), step [n] (step_size) */
+int grmonty_b200_test_dkdlam_step(grmonty_b200_ctx *ctx, int64_t n, const double *x, const double *k,
+                                  double *dkdlam, double *step);
+/* photons: [n][25] in/out, dl: [n]; one full push_photon (with halving) per photon; attempts [n] may be NULL */
+int grmonty_b200_test_push_photon(grmonty_b200_ctx *ctx, int64_t n, double *photons, const double *dl,
+                                  int32_t *attempts);
+/* photons: [n][25] in/out; nsteps x (step_size + push_photon) or until the photon leaves [r_h, 100];
+ * every `stride` steps x[4] k[4] e_0_s are written to trace [n][nsteps/stride][9] (NaN where not reached) */
+int grmonty_b200_test_trajectory(grmonty_b200_ctx *ctx, int64_t n, double *photons, int32_t nsteps,
+                                 int32_t stride, double *trace);
+/* x: [n][4] -> out [n][19]: n_e theta_e b u_con[4] u_cov[4] b_con[4] b_cov[4] (zeros if outside the grid) */
+int grmonty_b200_test_fluid_params(grmonty_b200_ctx *ctx, int64_t n, const double *x, double *out);
+/* args: [n][5] = nu theta_e n_e b theta -> out [n][5] = alpha_inv_scatt alpha_inv_abs synch k2_eval f_eval */
+int grmonty_b200_test_radiation(grmonty_b200_ctx *ctx, int64_t n, const double *args, double *out);
+/* args: [n][2] = w theta_e -> sigma [n] (total_compton_cross_lkup) */
+int grmonty_b200_test_hotcross(grmonty_b200_ctx *ctx, int64_t n, const double *args, double *sigma);
+/* k: [n][4], fluid: [n][19] (layout of test_fluid_params) -> theta [n], nu [n] */
+int grmonty_b200_test_angles(grmonty_b200_ctx *ctx, int64_t n, const double *k, const double *fluid, double *theta,
+                             double *nu);
+/* in: [n][24] = gcov[16] u_con[4] trial[4] -> e_con [n][16], e_cov [n][16] */
+int grmonty_b200_test_tetrad(grmonty_b200_ctx *ctx, int64_t n, const double *in, double *e_con, double *e_cov);
+/* per-zone emission data computed at create: nz [n0*n1] (may be NULL), dn_max, num_to_gen */
+int grmonty_b200_test_zones(grmonty_b200_ctx *ctx, double *nz, double *dn_max, int64_t *num_to_gen);
+/* bias_func(theta_e, w) with the given frozen statistics; args [n][2] */
+int grmonty_b200_test_bias(grmonty_b200_ctx *ctx, int64_t n, const double *args, double max_tau_scatt,
+                           double n_scatt, double n_recorded, double *out);
+/* birth state of primaries idx[n] -> photons [n][25] (dkdlam zero), rng [n][4] = id0 id1 id2 ctr */
+int grmonty_b200_test_make_primaries(grmonty_b200_ctx *ctx, int64_t n, const int64_t *idx, double *photons,
+                                     uint32_t *rng);
+/* Track n given photons (and all their descendants) to completion with frozen bias statistics, recording into
+ * the context's accumulators.  photons [n][25] in -> end state of each given photon out;
+ * rng [n][4] = id0 id1 id2 ctr in/out; status [n]: bit0 recorded, bit1 scattered at least once, bit2 absorbed
+ * or dropped. */
+int grmonty_b200_test_track(grmonty_b200_ctx *ctx, int64_t n, double *photons, uint32_t *rng,
+                            double max_tau_scatt, double n_scatt, double n_recorded, int32_t *status);
+/* which: 0 uniform, 3..6 chi_sq(dof), 10 sample_y(p0), 11 sample_mu(p0), 12 klein_nishina(p0), 13 thomson,
+ * 20 electron gamma, 21 electron mu (p0 = k0, p1 = theta_e), 22 scattered energy ratio, 23 scattered cosine.
+ * Stream of sample i: primary stream `first_stream + i`. */
+int grmonty_b200_test_samplers(grmonty_b200_ctx *ctx, int32_t which, double p0, double p1, int64_t first_stream,
+                               int64_t n, double *out);
+/* raw Philox4x32-10 blocks: ctr [n][4], key [n][2] -> out [n][4] */
+int grmonty_b200_test_philox(grmonty_b200_ctx *ctx, int64_t n, const uint32_t *ctr, const uint32_t *key,
+                             uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRMONTY_B200_H */

@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference CPU build (oracle/_ref, `make -C oracle ref`).
+
+Runs only in the build container (needs /root/reference to have been compiled into oracle/_ref/).  The
+fixtures it writes are committed; tests never read /root/reference.
+
+  python oracle/make_golden.py functions     # function-level vectors on a 48x48 synthetic dump
+  python oracle/make_golden.py samplers      # empirical quantiles of the reference's samplers
+  python oracle/make_golden.py spectrum      # 8-seed reference spectra on the 192x192 dump (minutes)
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refharness as rh  # noqa: E402
+from tools import make_harm_dump  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SMALL = dict(n0=48, n1=48, photon_n=2000, mass_unit=4e19)
+
+
+def small_dump(path):
+    header, table = make_harm_dump.make_dump(n0=SMALL["n0"], n1=SMALL["n1"])
+    make_harm_dump.write_dump(path, header, table)
+
+
+def null_k(R, rng, x):
+    """random future-directed null wave-vector at x (k.k = 0 in the reference's own metric)"""
+    g = R.gcov(x)
+    ksp = rng.normal(size=3) * np.array([1.0, 0.3, 0.3])
+    # solve g00 k0^2 + 2 g0i k0 ki + gij ki kj = 0 for k0
+    a = g[0, 0]
+    b = 2.0 * (g[0, 1:] @ ksp)
+    c = ksp @ g[1:, 1:] @ ksp
+    disc = b * b - 4 * a * c
+    k0 = (-b - np.sqrt(disc)) / (2 * a) if a < 0 else (-c / b)
+    k = np.array([k0, *ksp])
+    if k0 < 0:
+        k = -k
+    return k * 10 ** rng.uniform(-9, -3)
+
+
+def gen_functions():
+    rng = np.random.default_rng(20261018)
+    tmp = tempfile.mkdtemp()
+    dump = os.path.join(tmp, "dump48.txt")
+    small_dump(dump)
+    R = rh.Ref(dump, SMALL["photon_n"], SMALL["mass_unit"], seed=123)
+    d = R.model_dict()
+    out = {("model_" + k): np.asarray(v) for k, v in d.items()}
+    x1lo, x1hi = d["x_start1"], np.log(100.0)
+
+    # ---- geometry ----
+    n = 256
+    X = np.zeros((n, 4))
+    X[:, 1] = rng.uniform(x1lo - 0.05, x1hi, n)
+    X[:, 2] = rng.uniform(1e-3, 1 - 1e-3, n)
+    X[:8, 2] = [1e-6, 1e-4, 0.5, 0.999999, 0.25, 0.75, 0.01, 0.99]
+    X[:, 3] = rng.uniform(0, 2 * np.pi, n)
+    out["geom_x"] = X
+    out["geom_gcov"] = np.array([R.gcov(x) for x in X])
+    out["geom_gcon"] = np.array([R.gcon(x) for x in X])
+    out["geom_conn"] = np.array([R.connection(x) for x in X])
+    K = np.array([null_k(R, rng, x) for x in X])
+    out["geom_k"] = K
+    out["geom_dkdlam"] = np.array([R.init_dkdlam(x, k) for x, k in zip(X, K)])
+    out["geom_step"] = np.array([R.step_size(x, k) for x, k in zip(X, K)])
+
+    # ---- single push_photon calls ----
+    P0 = np.zeros((n, 25))
+    P1 = np.zeros((n, 25))
+    DL = np.zeros(n)
+    for t in range(n):
+        x, k = X[t], K[t]
+        g = R.gcov(x)
+        f = np.zeros(25)
+        f[0:4], f[4:8] = x, k
+        f[8:12] = R.init_dkdlam(x, k)
+        f[12] = 1e40
+        f[23] = -(k @ g[0])  # e_0_s
+        f[13] = f[23]
+        scale = 1.0 if t % 4 else 6.0  # every 4th: oversized step to force the halving branch
+        DL[t] = R.step_size(x, k) * scale
+        P0[t] = f
+        P1[t] = R.push_photon(f, DL[t])
+    out["push_in"], out["push_dl"], out["push_out"] = P0, DL, P1
+
+    # ---- vacuum trajectories: step_size + push_photon until stop or 400 steps ----
+    ntraj, nsteps, stride = 24, 400, 20
+    T0 = np.zeros((ntraj, 25))
+    TR = np.full((ntraj, nsteps // stride, 9), np.nan)  # x[4] k[4] e_0_s every `stride` steps
+    for t in range(ntraj):
+        x = np.array([0.0, rng.uniform(np.log(2.0), np.log(30.0)), rng.uniform(0.1, 0.9), 0.0])
+        k = null_k(R, rng, x)
+        g = R.gcov(x)
+        f = np.zeros(25)
+        f[0:4], f[4:8] = x, k
+        f[8:12] = R.init_dkdlam(x, k)
+        f[12] = 1e40
+        f[23] = f[13] = -(k @ g[0])
+        T0[t] = f
+        for s in range(nsteps):
+            if f[1] < d["x1_min"] or f[1] > x1hi:
+                break
+            dl = R.step_size(f[0:4], f[4:8])
+            f = R.push_photon(f, dl)
+            if (s + 1) % stride == 0:
+                TR[t, s // stride, 0:4] = f[0:4]
+                TR[t, s // stride, 4:8] = f[4:8]
+                TR[t, s // stride, 8] = f[23]
+    out["traj_in"], out["traj_out"] = T0, TR
+    out["traj_meta"] = np.array([nsteps, stride])
+
+    # ---- fluid ----
+    nf = 400
+    XF = np.zeros((nf, 4))
+    XF[:, 1] = rng.uniform(x1lo - 0.02, d["x_stop1"] + 0.05, nf)
+    XF[:, 2] = rng.uniform(-0.01, 1.01, nf)
+    XF[:6, 1] = [x1lo + 1e-9, x1lo + 0.4 * d["dx1"], d["x_stop1"] - 1e-9, d["x_stop1"] - 0.3 * d["dx1"],
+                 0.5 * (x1lo + d["x_stop1"]), x1lo + 3.5 * d["dx1"]]
+    XF[:6, 2] = [0.5, 0.2 * d["dx2"], 1 - 0.2 * d["dx2"], 0.5, 1e-9, 1 - 1e-9]
+    out["fluid_x"] = XF
+    out["fluid_params"] = np.array([R.fluid_params(x) for x in XF])
+    zi, zj = np.meshgrid(np.arange(0, 48, 5), np.arange(0, 48, 3), indexing="ij")
+    zij = np.stack([zi.ravel(), zj.ravel()], 1)
+    out["zone_ij"] = zij
+    out["zone_fluid"] = np.array([R.fluid_zone(int(i), int(j)) for i, j in zij])
+    out["zone_init_all"] = np.array([[R.init_zone(i, j) for j in range(48)] for i in range(48)])
+
+    # ---- radiation ----
+    nr = 400
+    nu = 10 ** rng.uniform(8, 22, nr)
+    te = 10 ** rng.uniform(-1.0, 3.0, nr)
+    te[:20] = 10 ** rng.uniform(-5, -0.6, 20)  # below theta_e_min / hotcross min_t branches
+    ne = 10 ** rng.uniform(2, 9, nr)
+    bb = 10 ** rng.uniform(-2, 4, nr)
+    th = rng.uniform(0.01, np.pi - 0.01, nr)
+    out["rad_args"] = np.stack([nu, te, ne, bb, th], 1)
+    L = R.L
+    out["rad_alpha_scatt"] = np.array([L.ref_alpha_inv_scatt(a, b, c) for a, b, c in zip(nu, te, ne)])
+    out["rad_alpha_abs"] = np.array([L.ref_alpha_inv_abs(a, b, c, e, f) for a, b, c, e, f in zip(nu, te, ne, bb, th)])
+    out["rad_synch"] = np.array([L.ref_synch(a, c, b, e, f) for a, b, c, e, f in zip(nu, te, ne, bb, th)])
+    out["rad_k2"] = np.array([L.ref_k2_eval(b) for b in te])
+    out["rad_f"] = np.array([L.ref_f_eval(b, e, a) for a, b, e in zip(nu, te, bb)])
+    w = 10 ** rng.uniform(-11.5, 5.5, nr)
+    tt = 10 ** rng.uniform(-4.5, 3.9, nr)
+    out["hc_args"] = np.stack([w, tt], 1)
+    out["hc_lkup"] = np.array([L.ref_hotcross_lkup(a, b) for a, b in zip(w, tt)])
+    # angles / frequencies with real fluid states
+    inside = out["fluid_params"][:, 0] > 0
+    XA = XF[inside][:128]
+    FP = out["fluid_params"][inside][:128]
+    KA = np.array([null_k(R, rng, x) for x in XA])
+    out["ang_x"], out["ang_k"], out["ang_fluid"] = XA, KA, FP
+    out["ang_theta"] = np.array([R.bk_angle(x, k, fp[7:11], fp[15:19], fp[2]) for x, k, fp in zip(XA, KA, FP)])
+    out["ang_nu"] = np.array([R.fluid_nu(x, k, fp[7:11]) for x, k, fp in zip(XA, KA, FP)])
+
+    # ---- bias ----
+    R.L.ref_set_bias_stats(3.3e-3, 777, 1000)
+    tb = 10 ** rng.uniform(-1, 2.5, 64)
+    wb = 10 ** rng.uniform(30, 40, 64)
+    out["bias_stats"] = np.array([3.3e-3, 777, 1000])
+    out["bias_args"] = np.stack([tb, wb], 1)
+    out["bias_out"] = np.array([L.ref_bias_func(a, b) for a, b in zip(tb, wb)])
+
+    # ---- tetrads ----
+    ET = []
+    for x, fp in zip(XA[:64], FP[:64]):
+        g = R.gcov(x)
+        bhat = fp[11:15] / (fp[2] / d["b_unit"])
+        ec, ev = R.make_tetrad(fp[3:7], bhat, g)
+        ET.append(np.concatenate([g.ravel(), fp[3:7], bhat, ec.ravel(), ev.ravel()]))
+    out["tetrad"] = np.array(ET)
+
+    # ---- whole-photon tracks that are RNG independent (no scattering, no roulette) ----
+    # bias statistics pinned so that bias = 1 (max_tau_scatt huge); photons whose result differs between two
+    # reference RNG seeds consumed a decision-relevant random number and are dropped.
+    R.L.ref_set_bias_stats(1e30, 0, 0)
+    zinit = out["zone_init_all"]
+    zones = [(i, j) for i in range(48) for j in range(48) if zinit[i, j, 0] > 0]
+    pick = rng.choice(len(zones), size=min(96, len(zones)), replace=False)
+    starts = []
+    R.L.ref_rng_init(1)
+    for zidx in pick:
+        i, j = zones[zidx]
+        ips = R.sample_zone_photons(i, j, zinit[i, j, 1], 3)
+        starts += [rh.init_to_flat(ip) for ip in ips]
+    starts = np.array(starts)
+    R.L.ref_rng_init(11)
+    endA = np.array([R.track(s) for s in starts])
+    R.L.ref_rng_init(12)
+    endB = np.array([R.track(s) for s in starts])
+    same = np.all((endA == endB) | (np.isnan(endA) & np.isnan(endB)), axis=1)
+    out["track_bias_stats"] = np.array([1e30, 0, 0])
+    out["track_in"], out["track_out"] = starts[same], endA[same]
+    print(f"track: kept {same.sum()} of {len(same)} RNG-independent photons", file=sys.stderr)
+    # record: spectrum produced by recording the kept end states that escaped
+    R.L.ref_clear_spectrum()
+    R.L.ref_set_bias_stats(1e30, 0, 0)
+    esc = out["track_out"][:, 1] > np.log(100.0)
+    for f in out["track_out"][esc]:
+        ff = np.ascontiguousarray(f)
+        R.L.ref_record_super_photon(ff.ctypes.data_as(rh.dp))
+    out["record_spectrum"] = R.spectrum()
+    out["record_counters"] = R.counters()
+
+    os.makedirs(GOLD, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLD, "functions_48.npz"), **out)
+    print("wrote functions_48.npz", {k: v.shape for k, v in out.items() if not k.startswith("model_")},
+          file=sys.stderr)
+
+
+def quantiles(v, nq=501):
+    return np.quantile(np.asarray(v), np.linspace(0, 1, nq))
+
+
+def gen_samplers():
+    tmp = tempfile.mkdtemp()
+    dump = os.path.join(tmp, "dump48.txt")
+    small_dump(dump)
+    R = rh.Ref(dump, SMALL["photon_n"], SMALL["mass_unit"], seed=4242)
+    L = R.L
+    N = 200000
+    out = {"n_samples": np.array(N)}
+    for dof in (3, 4, 5, 6):
+        out[f"chi_sq_{dof}"] = quantiles([L.ref_chi_sq(dof) for _ in range(N)])
+    for te in (0.5, 3.0, 30.0):
+        out[f"y_{te}"] = quantiles([L.ref_sample_y(te) for _ in range(N)])
+    for beta in (0.3, 0.9, 0.9999):
+        out[f"mu_{beta}"] = quantiles([L.ref_sample_mu(beta) for _ in range(N)])
+    for k0 in (0.01, 1.0, 30.0):
+        out[f"kn_{k0}"] = quantiles([L.ref_sample_kn(k0) for _ in range(N)])
+    out["thomson"] = quantiles([L.ref_sample_thomson() for _ in range(N)])
+    # electron sampling: gamma and cosine between p and k, for a soft and a hard photon
+    for k0, te in ((1e-6, 5.0), (2.0, 5.0), (1e-3, 50.0)):
+        k = np.array([k0, k0, 0.0, 0.0])
+        P = np.array([R.sample_electron(k, te) for _ in range(N // 4)])
+        out[f"el_gamma_{k0}_{te}"] = quantiles(P[:, 0])
+        out[f"el_mu_{k0}_{te}"] = quantiles(P[:, 1] / np.sqrt((P[:, 1:] ** 2).sum(1)))
+        # full scatter in the tetrad frame: energy ratio and deflection cosine
+        KP = np.array([R.sample_scattered_photon(k, p) for p in P])
+        out[f"sc_eratio_{k0}_{te}"] = quantiles(KP[:, 0] / k0)
+        out[f"sc_cos_{k0}_{te}"] = quantiles(KP[:, 1] / KP[:, 0])
+    np.savez_compressed(os.path.join(GOLD, "samplers.npz"), **out)
+    print("wrote samplers.npz", file=sys.stderr)
+
+
+def gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e19,)):
+    tmp = tempfile.mkdtemp()
+    dump = os.path.join(tmp, "dump192.txt")
+    header, table = make_harm_dump.make_dump()
+    make_harm_dump.write_dump(dump, header, table)
+    for mu in mass_units:
+        procs = []
+        for s in range(seeds):
+            sb = os.path.join(tmp, f"spec_{s}.bin")
+            cmd = [rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit", repr(mu),
+                   "--seed", str(123 + s), "--hotcross_cache", rh.HOTCROSS_CACHE, "--spectrum_bin", sb]
+            procs.append((subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True), sb))
+        specs, metas = [], []
+        for p, sb in procs:
+            o, _ = p.communicate()
+            metas.append(json.loads(o.strip().splitlines()[-1]))
+            specs.append(np.fromfile(sb).reshape(6, 200, 13))
+        specs = np.array(specs)
+        out = dict(photon_n=np.array(photon_n), mass_unit=np.array(mu), seeds=np.array(seeds),
+                   created=np.array([m["created"] for m in metas]),
+                   scattered=np.array([m["scattered"] for m in metas]),
+                   recorded=np.array([m["recorded"] for m in metas]),
+                   run_s=np.array([m["run_s"] for m in metas]),
+                   max_tau_scatt=np.array([m["max_tau_scatt"] for m in metas]),
+                   # per-seed: dn_dle, de_dle, nph, nscatt, tau_abs, tau_scatt (fields 0,1,2,3,7,8)
+                   spec=specs[:, :, :, [0, 1, 2, 3, 7, 8]].astype(np.float64))
+        name = f"spectrum_192_{mu:.0e}.npz".replace("+", "")
+        np.savez_compressed(os.path.join(GOLD, name), **out)
+        print("wrote", name, "rates", out["created"] / out["run_s"], file=sys.stderr)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "functions"
+    if what == "functions":
+        gen_functions()
+    elif what == "samplers":
+        gen_samplers()
+    elif what == "spectrum":
+        gen_spectrum()
+    else:
+        raise SystemExit(__doc__)
