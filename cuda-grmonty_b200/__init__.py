@@ -1,0 +1,355 @@
+"""cuda-grmonty_b200 -- B200-native superphoton transport (grmonty) behind the reference's host surface.
+
+This Python module is plumbing only: it builds the native artefacts in-tree and binds the C ABI
+(include/grmonty_b200.h) with ctypes so that tests/, bench.py and __graft_entry__.py can drive the CUDA
+path.  There is no Python or CPU implementation of the transport path here: if the CUDA library cannot be
+loaded or no CUDA device is present, every call fails loudly.
+
+Artefacts (all git-ignored, built by `build()`):
+    cuda-grmonty_b200/libgrmonty_b200.so        CUDA kernels + C ABI (csrc/)
+    cuda-grmonty_b200/libgrmonty_b200_host.so   C++20 host: HARM dump loader, table builders, spectrum writer
+    cuda-grmonty_b200/grmonty_b200              CLI with the reference's flags (host/main.cpp)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+HOST = os.path.join(PKG_DIR, "host")
+INCLUDE = os.path.join(ROOT, "include")
+LIB_CUDA = os.path.join(PKG_DIR, "libgrmonty_b200.so")
+LIB_HOST = os.path.join(PKG_DIR, "libgrmonty_b200_host.so")
+CLI = os.path.join(PKG_DIR, "grmonty_b200")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC"]
+
+N_TH, N_E, N_F = 6, 200, 13
+SPEC_FIELDS = ["dn_dle", "de_dle", "nph", "nscatt", "x1i_av", "x2i_sq", "x3f_sq", "tau_abs", "tau_scatt",
+               "ne_0", "theta_e_0", "b_0", "e_0"]
+dp = C.POINTER(C.c_double)
+
+
+def _stale(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def _sources(d: str, exts) -> list[str]:
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(tuple(exts)))
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a: cross-compiles without a GPU."""
+    srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".inc")) + [os.path.join(INCLUDE, "grmonty_b200.h")]
+    if force or _stale(LIB_CUDA, srcs):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB_CUDA, os.path.join(CSRC, "gm_api.cu"), "-ldl"]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return LIB_CUDA
+
+
+def build_host(force: bool = False) -> str:
+    srcs = _sources(HOST, (".cpp", ".hpp", ".h")) + [os.path.join(INCLUDE, "grmonty_b200.h")]
+    cpps = [s for s in srcs if s.endswith(".cpp") and not s.endswith("main.cpp")]
+    if not cpps:
+        return ""
+    if force or _stale(LIB_HOST, srcs):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-I" + INCLUDE, "-o", LIB_HOST, *cpps,
+                               "-lpthread", "-ldl"])
+    main = os.path.join(HOST, "main.cpp")
+    if os.path.exists(main) and (force or _stale(CLI, srcs)):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-I" + INCLUDE, "-o", CLI, main, *cpps, "-lpthread",
+                               "-ldl"])
+    return LIB_HOST
+
+
+def build(force: bool = False) -> None:
+    build_cuda(force)
+    build_host(force)
+
+
+# ---- C ABI structs (must mirror include/grmonty_b200.h) ------------------------------------------------------
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("struct_size", C.c_uint32),
+        ("n0", C.c_int32), ("n1", C.c_int32),
+        ("x_start1", C.c_double), ("x_start2", C.c_double),
+        ("dx1", C.c_double), ("dx2", C.c_double), ("dx3", C.c_double),
+        ("x_stop1", C.c_double), ("x_stop2", C.c_double),
+        ("a", C.c_double), ("h_slope", C.c_double), ("r_0", C.c_double),
+        ("mass_unit", C.c_double), ("l_unit", C.c_double), ("t_unit", C.c_double), ("rho_unit", C.c_double),
+        ("u_unit", C.c_double), ("b_unit", C.c_double), ("theta_e_unit", C.c_double), ("n_e_unit", C.c_double),
+        ("k_rho", dp), ("u", dp), ("u_1", dp), ("u_2", dp), ("u_3", dp), ("b_1", dp), ("b_2", dp), ("b_3", dp),
+        ("geom_det", dp),
+        ("hotcross", dp), ("f", dp), ("k2", dp), ("weight", dp), ("nint", dp), ("dndlnu_max", dp),
+        ("photon_n", C.c_double), ("bias_norm", C.c_double), ("max_tau_scatt0", C.c_double),
+        ("seed", C.c_uint64),
+        ("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32),
+        ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
+        ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_tracked", C.c_uint64), ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64),
+                ("n_interactions", C.c_uint64), ("n_scatter_events", C.c_uint64), ("n_generations", C.c_uint64),
+                ("n_kernel_launches", C.c_uint64), ("queue_high_water", C.c_uint64),
+                ("kernel_ms", C.c_double), ("transport_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+ABI_SYMBOLS = [
+    "grmonty_b200_create", "grmonty_b200_total_primaries", "grmonty_b200_run_range", "grmonty_b200_run",
+    "grmonty_b200_allreduce", "grmonty_b200_device_accumulators", "grmonty_b200_result", "grmonty_b200_reset",
+    "grmonty_b200_destroy", "grmonty_b200_last_error", "grmonty_b200_fp64_peak",
+    "grmonty_b200_test_geometry", "grmonty_b200_test_dkdlam_step", "grmonty_b200_test_push_photon",
+    "grmonty_b200_test_trajectory", "grmonty_b200_test_fluid_params", "grmonty_b200_test_radiation",
+    "grmonty_b200_test_hotcross", "grmonty_b200_test_angles", "grmonty_b200_test_tetrad",
+    "grmonty_b200_test_zones", "grmonty_b200_test_bias", "grmonty_b200_test_make_primaries",
+    "grmonty_b200_test_track", "grmonty_b200_test_samplers", "grmonty_b200_test_philox",
+]
+
+_lib = None
+
+
+class GrmontyError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library.  Raises if it is missing: there is no fallback implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_CUDA):
+            raise GrmontyError(f"{LIB_CUDA} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_CUDA)
+        L.grmonty_b200_last_error.restype = C.c_char_p
+        L.grmonty_b200_last_error.argtypes = [C.c_void_p]
+        L.grmonty_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
+        L.grmonty_b200_run_range.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.grmonty_b200_run.argtypes = [C.c_void_p]
+        L.grmonty_b200_reset.argtypes = [C.c_void_p]
+        L.grmonty_b200_destroy.argtypes = [C.c_void_p]
+        L.grmonty_b200_destroy.restype = None
+        L.grmonty_b200_total_primaries.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.grmonty_b200_result.argtypes = [C.c_void_p, dp, C.POINTER(C.c_uint64), dp, C.POINTER(Stats)]
+        L.grmonty_b200_device_accumulators.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3
+        L.grmonty_b200_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.grmonty_b200_fp64_peak.argtypes = [C.c_void_p, dp]
+        _lib = L
+    return _lib
+
+
+def _arr(a, dtype=np.float64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Context:
+    """One grmonty_b200 context = one GPU's share of a run.  `model` is a dict with the grids, tables and scalars
+    HARMModel holds after read_file() + init() (see host.HarmModel.model_dict / tests/golden)."""
+
+    GRIDS = ["k_rho", "u", "u_1", "u_2", "u_3", "b_1", "b_2", "b_3", "geom_det"]
+    TABLES = {"hotcross": 221 * 81, "f": 201, "k2": 201, "weight": 201, "nint": 20001, "dndlnu_max": 20001}
+    SCALARS = ["x_start1", "x_start2", "dx1", "dx2", "dx3", "x_stop1", "x_stop2", "a", "h_slope", "r_0",
+               "mass_unit", "l_unit", "t_unit", "rho_unit", "u_unit", "b_unit", "theta_e_unit", "n_e_unit",
+               "photon_n", "bias_norm", "max_tau_scatt0"]
+
+    def __init__(self, model: dict, seed: int = 123, rank: int = 0, world: int = 1, device: int = 0,
+                 threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
+                 gen_cap: int = 0):
+        self.L = lib()
+        cfg = Config()
+        cfg.abi_version = 1
+        cfg.struct_size = C.sizeof(Config)
+        cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
+        for k in self.SCALARS:
+            setattr(cfg, k, float(model[k]))
+        self._keep = {}
+        nz = cfg.n0 * cfg.n1
+        for k in self.GRIDS:
+            a = _arr(model[k]).reshape(-1)
+            assert a.size == nz, k
+            self._keep[k] = a
+            setattr(cfg, k, _ptr(a))
+        for k, n in self.TABLES.items():
+            a = _arr(model[k]).reshape(-1)
+            assert a.size == n, k
+            self._keep[k] = a
+            setattr(cfg, k, _ptr(a))
+        cfg.seed, cfg.rank, cfg.world, cfg.device = seed, rank, world, device
+        cfg.threads_per_block, cfg.blocks_per_sm = threads_per_block, blocks_per_sm
+        cfg.queue_capacity, cfg.gen0, cfg.gen_cap = queue_capacity, gen0, gen_cap
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))
+        if rc != 0:
+            raise GrmontyError(f"grmonty_b200_create failed ({rc}): "
+                               f"{self.L.grmonty_b200_last_error(None).decode()}")
+        self.n0, self.n1 = cfg.n0, cfg.n1
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GrmontyError(f"grmonty_b200 error {rc}: {self.L.grmonty_b200_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.L.grmonty_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- product API ----
+    def total_primaries(self) -> int:
+        t = C.c_int64()
+        self._ck(self.L.grmonty_b200_total_primaries(self.h, C.byref(t)))
+        return t.value
+
+    def run(self, first: int = 0, last: int = -1):
+        self._ck(self.L.grmonty_b200_run_range(self.h, first, last))
+
+    def reset(self):
+        self._ck(self.L.grmonty_b200_reset(self.h))
+
+    def result(self):
+        spec = np.zeros((N_TH, N_E, N_F))
+        counts = (C.c_uint64 * 3)()
+        mt = C.c_double()
+        st = Stats()
+        self._ck(self.L.grmonty_b200_result(self.h, _ptr(spec), counts, C.byref(mt), C.byref(st)))
+        return dict(spectrum=spec, created=counts[0], scattered=counts[1], recorded=counts[2],
+                    max_tau_scatt=mt.value, stats=st.as_dict())
+
+    def device_accumulators(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.grmonty_b200_device_accumulators(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def fp64_peak(self) -> float:
+        t = C.c_double()
+        self._ck(self.L.grmonty_b200_fp64_peak(self.h, C.byref(t)))
+        return t.value
+
+    # ---- test exports ----
+    def t_geometry(self, x):
+        x = _arr(x).reshape(-1, 4)
+        n = len(x)
+        gcov, gcon, conn = np.zeros((n, 4, 4)), np.zeros((n, 4, 4)), np.zeros((n, 4, 4, 4))
+        self._ck(self.L.grmonty_b200_test_geometry(self.h, C.c_int64(n), _ptr(x), _ptr(gcov), _ptr(gcon),
+                                                   _ptr(conn)))
+        return gcov, gcon, conn
+
+    def t_dkdlam_step(self, x, k):
+        x, k = _arr(x).reshape(-1, 4), _arr(k).reshape(-1, 4)
+        n = len(x)
+        dk, st = np.zeros((n, 4)), np.zeros(n)
+        self._ck(self.L.grmonty_b200_test_dkdlam_step(self.h, C.c_int64(n), _ptr(x), _ptr(k), _ptr(dk), _ptr(st)))
+        return dk, st
+
+    def t_push_photon(self, photons, dl):
+        p = _arr(photons).reshape(-1, 25).copy()
+        dl = _arr(dl).reshape(-1)
+        att = np.zeros(len(p), dtype=np.int32)
+        self._ck(self.L.grmonty_b200_test_push_photon(self.h, C.c_int64(len(p)), _ptr(p), _ptr(dl),
+                                                      _ptr(att, C.c_int32)))
+        return p, att
+
+    def t_trajectory(self, photons, nsteps, stride):
+        p = _arr(photons).reshape(-1, 25).copy()
+        tr = np.zeros((len(p), nsteps // stride, 9))
+        self._ck(self.L.grmonty_b200_test_trajectory(self.h, C.c_int64(len(p)), _ptr(p), nsteps, stride, _ptr(tr)))
+        return p, tr
+
+    def t_fluid_params(self, x):
+        x = _arr(x).reshape(-1, 4)
+        out = np.zeros((len(x), 19))
+        self._ck(self.L.grmonty_b200_test_fluid_params(self.h, C.c_int64(len(x)), _ptr(x), _ptr(out)))
+        return out
+
+    def t_radiation(self, args):
+        a = _arr(args).reshape(-1, 5)
+        out = np.zeros((len(a), 5))
+        self._ck(self.L.grmonty_b200_test_radiation(self.h, C.c_int64(len(a)), _ptr(a), _ptr(out)))
+        return out
+
+    def t_hotcross(self, args):
+        a = _arr(args).reshape(-1, 2)
+        out = np.zeros(len(a))
+        self._ck(self.L.grmonty_b200_test_hotcross(self.h, C.c_int64(len(a)), _ptr(a), _ptr(out)))
+        return out
+
+    def t_angles(self, k, fluid):
+        k, f = _arr(k).reshape(-1, 4), _arr(fluid).reshape(-1, 19)
+        th, nu = np.zeros(len(k)), np.zeros(len(k))
+        self._ck(self.L.grmonty_b200_test_angles(self.h, C.c_int64(len(k)), _ptr(k), _ptr(f), _ptr(th), _ptr(nu)))
+        return th, nu
+
+    def t_tetrad(self, rows24):
+        a = _arr(rows24).reshape(-1, 24)
+        ec, ev = np.zeros((len(a), 4, 4)), np.zeros((len(a), 4, 4))
+        self._ck(self.L.grmonty_b200_test_tetrad(self.h, C.c_int64(len(a)), _ptr(a), _ptr(ec), _ptr(ev)))
+        return ec, ev
+
+    def t_zones(self):
+        nz = self.n0 * self.n1
+        a, b, c = np.zeros(nz), np.zeros(nz), np.zeros(nz, dtype=np.int64)
+        self._ck(self.L.grmonty_b200_test_zones(self.h, _ptr(a), _ptr(b), _ptr(c, C.c_int64)))
+        return a.reshape(self.n0, self.n1), b.reshape(self.n0, self.n1), c.reshape(self.n0, self.n1)
+
+    def t_bias(self, args, max_tau, n_scatt, n_rec):
+        a = _arr(args).reshape(-1, 2)
+        out = np.zeros(len(a))
+        self._ck(self.L.grmonty_b200_test_bias(self.h, C.c_int64(len(a)), _ptr(a), C.c_double(max_tau),
+                                               C.c_double(n_scatt), C.c_double(n_rec), _ptr(out)))
+        return out
+
+    def t_make_primaries(self, idx):
+        idx = _arr(idx, np.int64).reshape(-1)
+        p = np.zeros((len(idx), 25))
+        r = np.zeros((len(idx), 4), dtype=np.uint32)
+        self._ck(self.L.grmonty_b200_test_make_primaries(self.h, C.c_int64(len(idx)), _ptr(idx, C.c_int64), _ptr(p),
+                                                         _ptr(r, C.c_uint32)))
+        return p, r
+
+    def t_track(self, photons, rng, max_tau, n_scatt, n_rec):
+        p = _arr(photons).reshape(-1, 25).copy()
+        r = _arr(rng, np.uint32).reshape(-1, 4).copy()
+        st = np.zeros(len(p), dtype=np.int32)
+        self._ck(self.L.grmonty_b200_test_track(self.h, C.c_int64(len(p)), _ptr(p), _ptr(r, C.c_uint32),
+                                                C.c_double(max_tau), C.c_double(n_scatt), C.c_double(n_rec),
+                                                _ptr(st, C.c_int32)))
+        return p, r, st
+
+    def t_samplers(self, which, p0, p1, first_stream, n):
+        out = np.zeros(n)
+        self._ck(self.L.grmonty_b200_test_samplers(self.h, which, C.c_double(p0), C.c_double(p1),
+                                                   C.c_int64(first_stream), C.c_int64(n), _ptr(out)))
+        return out
+
+    def t_philox(self, ctr, key):
+        c, k = _arr(ctr, np.uint32).reshape(-1, 4), _arr(key, np.uint32).reshape(-1, 2)
+        out = np.zeros((len(c), 4), dtype=np.uint32)
+        self._ck(self.L.grmonty_b200_test_philox(self.h, C.c_int64(len(c)), _ptr(c, C.c_uint32),
+                                                 _ptr(k, C.c_uint32), _ptr(out, C.c_uint32)))
+        return out

@@ -1,0 +1,613 @@
+/*
+ * gm_api.cu -- implementation of the C ABI declared in include/grmonty_b200.h.
+ *
+ * Replaces the seam cuda_super_photon::{alloc_memory, track_super_photons, free_memory}
+ * (reference cuda_grmonty/super_photon.cuh:29-61, super_photon.cu:447-1037) with a context object,
+ * on-device photon generation and one persistent kernel per generation.  No CPU fallback exists: every
+ * entry point needs a CUDA device and fails with GRMONTY_B200_ECUDA otherwise.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/grmonty_b200.h"
+#include "gm_kernels.cuh"
+
+using namespace gm;
+
+struct grmonty_b200_ctx {
+    grmonty_b200_config cfg;
+    GmParams P;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* device buffers */
+    double *d_grid = nullptr, *d_det = nullptr, *d_hotcross = nullptr, *d_f = nullptr, *d_k2 = nullptr;
+    double *d_weight = nullptr, *d_nint = nullptr, *d_dnmax = nullptr;
+    ZoneData *d_zones = nullptr;
+    long long *d_num = nullptr, *d_prefix = nullptr;
+    double *d_nz = nullptr;
+    PhotonQueue Q{};
+    unsigned long long *d_qctr = nullptr; /* head, tail, finished */
+    Accumulators A{};
+    double *d_spectrum = nullptr;
+    unsigned long long *d_counters = nullptr, *d_maxtau = nullptr, *d_work = nullptr;
+    unsigned int *d_error = nullptr;
+    /* host state */
+    std::vector<long long> prefix; /* [nzones+1] */
+    long long total = 0;
+    long long perm_mult = 1; /* Weyl multiplier of the processing order */
+    unsigned int gen_tag = 0;
+    int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
+    long long gen0 = 32, gen_cap = 1 << 22;
+    grmonty_b200_stats stats{};
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(grmonty_b200_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c)
+        c->err = buf;
+    else
+        g_create_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, GRMONTY_B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),      \
+                        __FILE__, __LINE__);                                                                  \
+    } while (0)
+
+template <typename T> static cudaError_t upload(T **dst, const T *src, size_t n) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), n * sizeof(T));
+    if (e != cudaSuccess)
+        return e;
+    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+/* ---- kernel dispatch over the compiled (block, min-blocks) variants ------------------------------------- */
+typedef void (*TransportFn)(const TransportArgs);
+struct Variant {
+    int block, min_blocks;
+    TransportFn fn;
+};
+static const Variant kVariants[] = {
+    {128, 2, transport_kernel<128, 2>}, {128, 3, transport_kernel<128, 3>}, {128, 4, transport_kernel<128, 4>},
+    {256, 1, transport_kernel<256, 1>}, {64, 4, transport_kernel<64, 4>},
+};
+static const Variant *find_variant(int block, int min_blocks) {
+    for (const Variant &v : kVariants)
+        if (v.block == block && v.min_blocks == min_blocks)
+            return &v;
+    return nullptr;
+}
+
+extern "C" {
+
+const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) {
+    grmonty_b200_ctx *ctx = nullptr;
+    if (!out || !cfg)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != GRMONTY_B200_ABI_VERSION || cfg->struct_size != sizeof(grmonty_b200_config))
+        return fail(nullptr, GRMONTY_B200_EINVAL, "ABI mismatch: version %u size %u (library: %u, %zu)",
+                    cfg->abi_version, cfg->struct_size, GRMONTY_B200_ABI_VERSION, sizeof(grmonty_b200_config));
+    if (cfg->n0 < 2 || cfg->n1 < 2 || cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "bad grid or sharding: n0=%d n1=%d rank=%d world=%d", cfg->n0,
+                    cfg->n1, cfg->rank, cfg->world);
+    const void *ptrs[] = {cfg->k_rho, cfg->u,  cfg->u_1, cfg->u_2,    cfg->u_3,  cfg->b_1,       cfg->b_2, cfg->b_3,
+                          cfg->geom_det, cfg->hotcross, cfg->f, cfg->k2, cfg->weight, cfg->nint, cfg->dndlnu_max};
+    for (const void *p : ptrs)
+        if (!p)
+            return fail(nullptr, GRMONTY_B200_EINVAL, "null input array");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, GRMONTY_B200_ECUDA, "no CUDA device: %s (there is no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+
+    ctx = new grmonty_b200_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    int rc = [&]() -> int {
+        CK(cudaSetDevice(ctx->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ctx->device));
+        ctx->sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ctx->ev0));
+        CK(cudaEventCreate(&ctx->ev1));
+
+        /* ---- parameter block ---- */
+        GmParams &P = ctx->P;
+        memset(&P, 0, sizeof(P));
+        P.n0 = cfg->n0;
+        P.n1 = cfg->n1;
+        P.x_start1 = cfg->x_start1;
+        P.x_start2 = cfg->x_start2;
+        P.dx1 = cfg->dx1;
+        P.dx2 = cfg->dx2;
+        P.x_stop1 = cfg->x_stop1;
+        P.x_stop2 = cfg->x_stop2;
+        P.a = cfg->a;
+        P.h_slope = cfg->h_slope;
+        P.r_0 = cfg->r_0;
+        P.b_unit = cfg->b_unit;
+        P.theta_e_unit = cfg->theta_e_unit;
+        P.n_e_unit = cfg->n_e_unit;
+        P.photon_n = cfg->photon_n;
+        P.bias_norm = cfg->bias_norm;
+        /* reference harm_model.cpp:73, :228-229 */
+        P.d_tau_k = 2.0 * kPi * cfg->l_unit / (kME * kCL * kCL / kHBAR);
+        P.x1_min = std::log(1.0 + std::sqrt(1.0 - cfg->a * cfg->a));
+        P.x1_max = std::log(kRMax);
+        P.seed_lo = (uint32_t)cfg->seed;
+        P.seed_hi = (uint32_t)(cfg->seed >> 32);
+        P.l_nu_min = std::log(kNuMin);
+        P.n_l_n = std::log(kNuMax) - std::log(kNuMin);
+        P.d_l_nu = (std::log(kNuMax) - std::log(kNuMin)) / kNESamp;
+        P.l_b_min = std::log(kBthsqMin);
+        P.d_l_b = std::log(kBthsqMax / kBthsqMin) / kNint;
+        P.hc_l_min_w = std::log10(kHcMinW);
+        P.hc_l_min_t = std::log10(kHcMinT);
+        P.hc_d_l_w = std::log10(kHcMaxW / kHcMinW) / kHcNW;
+        P.hc_d_l_t = std::log10(kHcMaxT / kHcMinT) / kHcNT;
+        P.jnu_l_min_k = std::log(kJnuMinK);
+        P.jnu_d_l_k = std::log(kJnuMaxK / kJnuMinK) / kNESamp;
+        P.jnu_l_min_t = std::log(kThetaEMin);
+        P.jnu_d_l_t = std::log(kJnuMaxT / kThetaEMin) / kNESamp;
+        P.spec_l_e_0 = std::log(1.0e-12);
+        P.nz_max = cfg->photon_n * std::log(kNuMax / kNuMin);
+
+        /* ---- model upload: primitives interleaved [n0][n1][8] ---- */
+        const size_t nz = (size_t)cfg->n0 * cfg->n1;
+        {
+            std::vector<double> inter(nz * 8);
+            const double *src[8] = {cfg->k_rho, cfg->u, cfg->u_1, cfg->u_2, cfg->u_3, cfg->b_1, cfg->b_2, cfg->b_3};
+            for (size_t z = 0; z < nz; ++z)
+                for (int v = 0; v < 8; ++v)
+                    inter[z * 8 + v] = src[v][z];
+            CK(upload(&ctx->d_grid, inter.data(), nz * 8));
+        }
+        CK(upload(&ctx->d_det, cfg->geom_det, nz));
+        CK(upload(&ctx->d_hotcross, cfg->hotcross, (size_t)GRMONTY_B200_HOTCROSS_N));
+        CK(upload(&ctx->d_f, cfg->f, (size_t)GRMONTY_B200_TABLE_N));
+        CK(upload(&ctx->d_k2, cfg->k2, (size_t)GRMONTY_B200_TABLE_N));
+        CK(upload(&ctx->d_weight, cfg->weight, (size_t)GRMONTY_B200_TABLE_N));
+        CK(upload(&ctx->d_nint, cfg->nint, (size_t)GRMONTY_B200_NINT_N));
+        CK(upload(&ctx->d_dnmax, cfg->dndlnu_max, (size_t)GRMONTY_B200_NINT_N));
+        P.grid = ctx->d_grid;
+        P.geom_det = ctx->d_det;
+        P.hotcross = ctx->d_hotcross;
+        P.f = ctx->d_f;
+        P.k2 = ctx->d_k2;
+        P.weight = ctx->d_weight;
+        P.nint = ctx->d_nint;
+        P.dndlnu_max = ctx->d_dnmax;
+
+        /* keep the fluid grid L2-resident (access-policy window; best effort) */
+        {
+            size_t bytes = nz * 8 * sizeof(double);
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+            if (max_persist > 0 && max_window > 0) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, (size_t)max_persist));
+                cudaStreamAttrValue attr;
+                memset(&attr, 0, sizeof(attr));
+                attr.accessPolicyWindow.base_ptr = ctx->d_grid;
+                attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+                attr.accessPolicyWindow.hitRatio =
+                    (float)std::min(1.0, (double)max_persist / (double)attr.accessPolicyWindow.num_bytes);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaGetLastError(); /* best effort */
+            }
+        }
+
+        /* ---- per-zone emission data and the zone -> primary index prefix ---- */
+        CK(cudaMalloc(&ctx->d_zones, nz * sizeof(ZoneData)));
+        CK(cudaMalloc(&ctx->d_num, nz * sizeof(long long)));
+        CK(cudaMalloc(&ctx->d_nz, nz * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_prefix, (nz + 1) * sizeof(long long)));
+        zone_kernel<<<(unsigned)((nz + 127) / 128), 128, 0, ctx->stream>>>(P, ctx->d_zones, ctx->d_nz, ctx->d_num);
+        CK(cudaGetLastError());
+        std::vector<long long> num(nz);
+        CK(cudaMemcpyAsync(num.data(), ctx->d_num, nz * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->prefix.assign(nz + 1, 0);
+        for (size_t z = 0; z < nz; ++z)
+            ctx->prefix[z + 1] = ctx->prefix[z] + num[z];
+        ctx->total = ctx->prefix[nz];
+        {
+            /* multiplier ~ total / golden ratio, coprime to total (same rule as the oracle's orc_perm_multiplier) */
+            long long mult = 1;
+            if (ctx->total >= 3) {
+                mult = std::max<long long>(1, (long long)((double)ctx->total * 0.6180339887498949));
+                auto gcd = [](long long a, long long b) {
+                    while (b) {
+                        const long long t = a % b;
+                        a = b;
+                        b = t;
+                    }
+                    return a;
+                };
+                while (gcd(mult, ctx->total) != 1)
+                    ++mult;
+            }
+            ctx->perm_mult = mult;
+        }
+        CK(cudaMemcpy(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+
+        /* ---- photon queue ---- */
+        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 24);
+        if (cap > 0xfffffff0ull)
+            cap = 0xfffffff0ull; /* slots are addressed with 32 bits */
+        ctx->Q.capacity = cap;
+        CK(cudaMalloc(&ctx->Q.f, (size_t)Q_NFIELDS * cap * sizeof(double)));
+        CK(cudaMalloc(&ctx->Q.rng, cap * sizeof(uint4)));
+        CK(cudaMalloc(&ctx->Q.n_scatt, cap * sizeof(int)));
+        CK(cudaMalloc(&ctx->Q.ready, cap * sizeof(unsigned int)));
+        CK(cudaMemset(ctx->Q.ready, 0, cap * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_qctr, 3 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->d_qctr, 0, 3 * sizeof(unsigned long long)));
+        ctx->Q.head = ctx->d_qctr;
+        ctx->Q.tail = ctx->d_qctr + 1;
+        ctx->Q.finished = ctx->d_qctr + 2;
+
+        /* ---- accumulators ---- */
+        const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
+        CK(cudaMalloc(&ctx->d_spectrum, nspec * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_counters, 3 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_maxtau, sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_work, 8 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_error, sizeof(unsigned int)));
+        ctx->A.spectrum = ctx->d_spectrum;
+        ctx->A.counters = ctx->d_counters;
+        ctx->A.max_tau_bits = ctx->d_maxtau;
+        ctx->A.work = ctx->d_work;
+        ctx->A.error = ctx->d_error;
+
+        /* ---- launch geometry ---- */
+        ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 128;
+        int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 2;
+        const Variant *v = find_variant(ctx->threads, want_bps);
+        if (!v)
+            return fail(ctx, GRMONTY_B200_EINVAL, "no compiled kernel variant for %d threads x %d blocks/SM",
+                        ctx->threads, want_bps);
+        const size_t smem = (size_t)13 * ctx->threads * sizeof(double);
+        CK(cudaFuncSetAttribute((const void *)v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)v->fn, ctx->threads, smem));
+        if (occ < 1)
+            return fail(ctx, GRMONTY_B200_ECUDA, "transport kernel does not fit on an SM");
+        ctx->blocks_per_sm = std::min(occ, want_bps);
+        ctx->grid_blocks = ctx->blocks_per_sm * ctx->sm_count;
+        if (cfg->gen0 > 0)
+            ctx->gen0 = cfg->gen0;
+        if (cfg->gen_cap > 0)
+            ctx->gen_cap = cfg->gen_cap;
+        return GRMONTY_B200_OK;
+    }();
+    if (rc != GRMONTY_B200_OK) {
+        g_create_err = ctx->err;
+        grmonty_b200_destroy(ctx);
+        return rc;
+    }
+    rc = grmonty_b200_reset(ctx);
+    if (rc != GRMONTY_B200_OK) {
+        g_create_err = ctx->err;
+        grmonty_b200_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_reset(grmonty_b200_ctx *ctx) {
+    if (!ctx)
+        return GRMONTY_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
+    CK(cudaMemsetAsync(ctx->d_spectrum, 0, nspec * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(unsigned int), ctx->stream));
+    unsigned long long bits;
+    const double mt = ctx->cfg.max_tau_scatt0;
+    memcpy(&bits, &mt, sizeof(bits));
+    CK(cudaMemcpyAsync(ctx->d_maxtau, &bits, sizeof(bits), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_total_primaries(grmonty_b200_ctx *ctx, int64_t *total) {
+    if (!ctx || !total)
+        return GRMONTY_B200_EINVAL;
+    *total = ctx->total;
+    return GRMONTY_B200_OK;
+}
+
+static long long generation_size(long long g, long long gen0, long long cap) {
+    long long s = gen0;
+    for (long long i = 0; i < g && s < cap; ++i)
+        s *= 2;
+    return std::min(s, cap);
+}
+
+/* run one batch of primaries (first, first+stride, ... count of them) with frozen bias statistics */
+static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, long long count,
+                     const GmBiasStats &bias, const DebugOut &dbg, bool preloaded) {
+    const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 2);
+    ++ctx->gen_tag;
+    unsigned long long qc[3] = {0ull, (unsigned long long)count, 0ull};
+    CK(cudaMemcpyAsync(ctx->d_qctr, qc, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
+    float ms = 0.f;
+    if (!preloaded) {
+        const int bb = 128;
+        const long long want = (count + bb - 1) / bb;
+        const int nb = (int)std::min<long long>(want, (long long)ctx->sm_count * 16);
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        birth_kernel<<<nb, bb, 0, ctx->stream>>>(ctx->P, ctx->Q, ctx->d_zones, ctx->d_prefix, first, stride, count,
+                                                 ctx->perm_mult, ctx->total, ctx->gen_tag);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.kernel_ms += ms;
+        ctx->stats.n_kernel_launches += 1;
+    }
+    TransportArgs args;
+    args.P = ctx->P;
+    args.bias = bias;
+    args.Q = ctx->Q;
+    args.A = ctx->A;
+    args.D = dbg;
+    args.gen_tag = ctx->gen_tag;
+    const size_t smem = (size_t)13 * ctx->threads * sizeof(double);
+    /* do not launch more threads than there are photons to start with (tiny test batches) */
+    long long blocks = std::min<long long>(ctx->grid_blocks, std::max<long long>(1, (count * 2 + ctx->threads - 1) / ctx->threads));
+    blocks = std::max<long long>(blocks, std::min<long long>(ctx->grid_blocks, ctx->sm_count));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    v->fn<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.kernel_ms += ms;
+    ctx->stats.transport_ms += ms;
+    ctx->stats.n_kernel_launches += 1;
+    unsigned int err = 0;
+    CK(cudaMemcpyAsync(&err, ctx->d_error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(qc, ctx->d_qctr, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.queue_high_water = std::max<uint64_t>(ctx->stats.queue_high_water, qc[1]);
+    if (err & 1u)
+        return fail(ctx, GRMONTY_B200_EQUEUE, "device photon queue overflow: %llu slots needed, capacity %llu",
+                    qc[1], ctx->Q.capacity);
+    if (err & 2u)
+        return fail(ctx, GRMONTY_B200_ECUDA, "device photon queue: ready-flag timeout");
+    return GRMONTY_B200_OK;
+}
+
+static int read_bias_stats(grmonty_b200_ctx *ctx, GmBiasStats *b) {
+    unsigned long long c[3], bits;
+    CK(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&bits, ctx->d_maxtau, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double mt;
+    memcpy(&mt, &bits, sizeof(mt));
+    b->max_tau_scatt = mt;
+    b->n_scatt = (double)c[1];
+    b->n_recorded = (double)c[2];
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
+    if (!ctx)
+        return GRMONTY_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    if (last < 0 || last > ctx->total)
+        last = ctx->total;
+    if (first < 0)
+        first = 0;
+    const long long world = ctx->cfg.world, rank = ctx->cfg.rank;
+    const DebugOut nodbg = {nullptr, nullptr, 0};
+    /* a batch never fills more than a quarter of the queue with primaries: the rest is room for children */
+    const long long chunk_cap = std::max<long long>(1024, (long long)(ctx->Q.capacity / 4));
+    long long g_start = 0;
+    unsigned long long created = 0;
+    for (long long g = 0; g_start < last; ++g) {
+        const long long g_end = g_start + generation_size(g, ctx->gen0, ctx->gen_cap);
+        const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
+        if (lo < hi) {
+            long long f0 = lo + ((rank - lo % world) % world + world) % world; /* first index >= lo, = rank mod world */
+            long long count = f0 < hi ? (hi - f0 + world - 1) / world : 0;
+            if (count > 0) {
+                GmBiasStats bias;
+                int rc = read_bias_stats(ctx, &bias);
+                if (rc)
+                    return rc;
+                while (count > 0) {
+                    const long long n = std::min(count, chunk_cap);
+                    rc = run_batch(ctx, f0, world, n, bias, nodbg, false);
+                    if (rc)
+                        return rc;
+                    created += (unsigned long long)n;
+                    f0 += n * world;
+                    count -= n;
+                }
+                ++ctx->stats.n_generations;
+            }
+        }
+        g_start = g_end;
+    }
+    /* counters[0] = created (host-side count; the reference counts primaries only, harm_model.cpp:395) */
+    unsigned long long c0;
+    CK(cudaMemcpy(&c0, ctx->d_counters, sizeof(c0), cudaMemcpyDeviceToHost));
+    c0 += created;
+    CK(cudaMemcpy(ctx->d_counters, &c0, sizeof(c0), cudaMemcpyHostToDevice));
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_run(grmonty_b200_ctx *ctx) { return grmonty_b200_run_range(ctx, 0, -1); }
+
+int grmonty_b200_device_accumulators(grmonty_b200_ctx *ctx, void **spectrum, void **counters, void **max_tau) {
+    if (!ctx)
+        return GRMONTY_B200_EINVAL;
+    if (spectrum)
+        *spectrum = ctx->d_spectrum;
+    if (counters)
+        *counters = ctx->d_counters;
+    if (max_tau)
+        *max_tau = ctx->d_maxtau;
+    return GRMONTY_B200_OK;
+}
+
+/* NCCL is resolved at run time so that the library has no link-time NCCL dependency and, inside a process
+ * that already loaded NCCL (e.g. PyTorch's bundled copy), uses that very copy. */
+int grmonty_b200_allreduce(grmonty_b200_ctx *ctx, void *nccl_comm, void *cuda_stream) {
+    if (!ctx)
+        return GRMONTY_B200_EINVAL;
+    if (ctx->cfg.world == 1)
+        return GRMONTY_B200_OK;
+    if (!nccl_comm)
+        return fail(ctx, GRMONTY_B200_EINVAL, "world > 1 needs an ncclComm_t");
+    typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*GroupFn)(void);
+    static AllReduceFn all_reduce = nullptr;
+    static GroupFn group_start = nullptr, group_end = nullptr;
+    if (!all_reduce) {
+        void *h = dlopen(nullptr, RTLD_NOW);
+        all_reduce = h ? (AllReduceFn)dlsym(h, "ncclAllReduce") : nullptr;
+        if (!all_reduce) {
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h)
+                h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            all_reduce = h ? (AllReduceFn)dlsym(h, "ncclAllReduce") : nullptr;
+        }
+        if (!all_reduce)
+            return fail(ctx, GRMONTY_B200_ENCCL, "ncclAllReduce not found (libnccl.so.2 not loadable)");
+        group_start = (GroupFn)dlsym(h, "ncclGroupStart");
+        group_end = (GroupFn)dlsym(h, "ncclGroupEnd");
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
+    enum { kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 }; /* nccl.h ncclDataType_t / ncclRedOp_t */
+    if (group_start)
+        group_start();
+    int r0 = all_reduce(ctx->d_spectrum, ctx->d_spectrum, nspec, kNcclFloat64, kNcclSum, nccl_comm, s);
+    int r1 = all_reduce(ctx->d_counters, ctx->d_counters, 3, kNcclUint64, kNcclSum, nccl_comm, s);
+    /* non-negative doubles order like their bit patterns, so max over uint64 is max over the doubles */
+    int r2 = all_reduce(ctx->d_maxtau, ctx->d_maxtau, 1, kNcclUint64, kNcclMax, nccl_comm, s);
+    int r3 = group_end ? group_end() : 0;
+    if (r0 || r1 || r2 || r3)
+        return fail(ctx, GRMONTY_B200_ENCCL, "ncclAllReduce failed (%d %d %d %d)", r0, r1, r2, r3);
+    CK(cudaStreamSynchronize(s));
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_result(grmonty_b200_ctx *ctx, double *spectrum, uint64_t counts[3], double *max_tau_scatt,
+                        grmonty_b200_stats *stats) {
+    if (!ctx)
+        return GRMONTY_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
+    if (spectrum)
+        CK(cudaMemcpy(spectrum, ctx->d_spectrum, nspec * sizeof(double), cudaMemcpyDeviceToHost));
+    if (counts) {
+        unsigned long long c[3];
+        CK(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        counts[0] = c[0];
+        counts[1] = c[1];
+        counts[2] = c[2];
+    }
+    if (max_tau_scatt) {
+        unsigned long long bits;
+        CK(cudaMemcpy(&bits, ctx->d_maxtau, sizeof(bits), cudaMemcpyDeviceToHost));
+        memcpy(max_tau_scatt, &bits, sizeof(double));
+    }
+    if (stats) {
+        unsigned long long w[8];
+        CK(cudaMemcpy(w, ctx->d_work, sizeof(w), cudaMemcpyDeviceToHost));
+        ctx->stats.n_tracked = w[0];
+        ctx->stats.n_steps = w[1];
+        ctx->stats.n_push_attempts = w[2];
+        ctx->stats.n_interactions = w[3];
+        ctx->stats.n_scatter_events = w[4];
+        *stats = ctx->stats;
+    }
+    return GRMONTY_B200_OK;
+}
+
+void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    void *bufs[] = {ctx->d_grid,  ctx->d_det,    ctx->d_hotcross, ctx->d_f,        ctx->d_k2,      ctx->d_weight,
+                    ctx->d_nint,  ctx->d_dnmax,  ctx->d_zones,    ctx->d_num,      ctx->d_prefix,  ctx->d_nz,
+                    ctx->Q.f,     ctx->Q.rng,    ctx->Q.n_scatt,  ctx->Q.ready,    ctx->d_qctr,    ctx->d_spectrum,
+                    ctx->d_counters, ctx->d_maxtau, ctx->d_work,  ctx->d_error};
+    for (void *b : bufs)
+        if (b)
+            cudaFree(b);
+    if (ctx->ev0)
+        cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1)
+        cudaEventDestroy(ctx->ev1);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops)
+        return GRMONTY_B200_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 16;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 1024); /* warm-up */
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaFree(d));
+    *tflops = best;
+    return GRMONTY_B200_OK;
+}
+
+} /* extern "C" */
+
+#include "gm_test_exports.inc"

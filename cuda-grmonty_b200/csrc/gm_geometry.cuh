@@ -1,0 +1,305 @@
+/*
+ * gm_geometry.cuh -- modified Kerr-Schild geometry and the geodesic integrator, sm_100a device code.
+ *
+ * What the reference computes (CPU path, cuda_grmonty/harm_model.cpp):
+ *   get_bl_coord :1632-1637   gcov_func :499-530   gcon_func :473-497   get_connection :1436-1569
+ *   init_dkdlam :1571-1587    step_size :1620-1630 push_photon :1217-1289
+ * How it is organised here (B200-first, not a translation):
+ *   - one GeoPoint per position holds exp/sincos results shared by the connection, the metric row needed
+ *     for the energy check and (in the interaction stage) the full metric: 1 exp + 2 sincos per position
+ *     instead of 3 exp + 6 sincos;
+ *   - the connection is kept as 4x10 packed symmetric coefficients contracted against the 10 products
+ *     k^j k^k; divisions are replaced by 4 reciprocals (fac2 == 2 rho^2 identically);
+ *   - push_photon's recursion (depth <= 7) is flattened into "attempts" driven by a (position, level) pair so
+ *     that every lane of a warp executes the same attempt code each iteration (see gm_transport.cuh).
+ */
+#pragma once
+#include "gm_params.h"
+
+namespace gm {
+
+struct GeoPoint {
+    double r;        /* exp(x1): radius used by the connection (reference ignores r_0 there, :1438) */
+    double rm;       /* r + r_0: radius used by the metric (:1634) */
+    double sx, cx;   /* sin, cos(2 pi x2) */
+    double sth, cth; /* sin, cos(theta), theta = pi x2 + (1-h)/2 sin(2 pi x2) */
+    double hfac;     /* dtheta/dx2 = pi (1 + (1-h) cos(2 pi x2)) */
+};
+
+__device__ __forceinline__ GeoPoint geo_point(const GmParams &P, double x1, double x2) {
+    GeoPoint g;
+    g.r = exp(x1);
+    g.rm = g.r + P.r_0;
+    sincospi(2.0 * x2, &g.sx, &g.cx);
+    const double omh = 1.0 - P.h_slope;
+    const double th = kPi * x2 + 0.5 * omh * g.sx;
+    sincos(th, &g.sth, &g.cth);
+    g.hfac = kPi * (1.0 + omh * g.cx);
+    return g;
+}
+
+/* the seven independent non-zero covariant components */
+struct MetricCov {
+    double g00, g01, g03, g11, g13, g22, g33;
+};
+
+__device__ __forceinline__ MetricCov metric_cov(const GmParams &P, const GeoPoint &q) {
+    const double s = fabs(q.sth) + kEps;
+    const double s2 = s * s;
+    const double a = P.a;
+    const double r = q.rm;
+    const double rho2 = r * r + a * a * q.cth * q.cth;
+    const double rfac = r - P.r_0;
+    const double tr = 2.0 * r / rho2;
+    MetricCov m;
+    m.g00 = -1.0 + tr;
+    m.g01 = tr * rfac;
+    m.g03 = -a * s2 * tr;
+    m.g11 = (1.0 + tr) * rfac * rfac;
+    m.g13 = -a * s2 * (1.0 + tr) * rfac;
+    m.g22 = rho2 * q.hfac * q.hfac;
+    m.g33 = s2 * (rho2 + a * a * s2 * (1.0 + tr));
+    return m;
+}
+
+/* row 0 only: what push_photon needs for e = -k^mu g_{0 mu} (the reference GPU build has gcov_0_func) */
+__device__ __forceinline__ void metric_cov_row0(const GmParams &P, const GeoPoint &q, double &g00, double &g01,
+                                                double &g03) {
+    const double s = fabs(q.sth) + kEps;
+    const double r = q.rm;
+    const double rho2 = r * r + P.a * P.a * q.cth * q.cth;
+    const double tr = 2.0 * r / rho2;
+    g00 = -1.0 + tr;
+    g01 = tr * (r - P.r_0);
+    g03 = -P.a * (s * s) * tr;
+}
+
+/* contravariant components g^00, g^01 (g^02 = g^03 = 0) needed by get_fluid_params; full set for tests */
+struct MetricCon {
+    double g00, g01, g11, g13, g22, g33;
+};
+
+__device__ __forceinline__ MetricCon metric_con(const GmParams &P, const GeoPoint &q) {
+    const double s = fabs(q.sth) + kEps;
+    const double r = q.rm;
+    const double a = P.a;
+    const double irho2 = 1.0 / (r * r + a * a * q.cth * q.cth);
+    MetricCon m;
+    m.g00 = -1.0 - 2.0 * r * irho2;
+    m.g01 = 2.0 * irho2;
+    m.g11 = irho2 * (r * (r - 2.0) + a * a) / (r * r);
+    m.g13 = a * irho2 / r;
+    m.g22 = irho2 / (q.hfac * q.hfac);
+    m.g33 = irho2 / (s * s);
+    return m;
+}
+
+/* packed symmetric index of (j,k), j <= k: 00 01 02 03 11 12 13 22 23 33 */
+enum { S00 = 0, S01, S02, S03, S11, S12, S13, S22, S23, S33 };
+
+/* Gamma^i_{jk} in packed form G[i][S..]; G[1][S02] = G[1][S23] = G[2][S02] = G[2][S23] = 0 are not stored
+ * as variables the contraction reads (they are skipped below). */
+struct Connection {
+    double G0[10], G1[10], G2[10], G3[10];
+};
+
+__device__ __forceinline__ void connection_eval(const GmParams &P, const GeoPoint &q, Connection &c) {
+    const double r1 = q.r;
+    const double r2 = r1 * r1, r3 = r2 * r1, r4 = r2 * r2;
+    const double omh = 1.0 - P.h_slope;
+    const double dth = q.hfac;
+    const double d2th = -2.0 * kPi * kPi * omh * q.sx;
+    const double dth2 = dth * dth;
+    const double sth = q.sth, cth = q.cth;
+    const double sth2 = sth * sth, cth2 = cth * cth;
+    const double sth4 = sth2 * sth2, cth4 = cth2 * cth2;
+    const double r1sth2 = r1 * sth2;
+    const double cs = cth * sth;
+    const double s2th = 2.0 * cs;
+    const double a = P.a, a2 = a * a, a3 = a2 * a, a4 = a2 * a2;
+    const double a2sth2 = a2 * sth2, a2cth2 = a2 * cth2, a4cth4 = a4 * cth4;
+    const double rho2 = r2 + a2cth2;
+    const double rho22 = rho2 * rho2, rho23 = rho22 * rho2;
+    const double irho2 = 1.0 / rho2;
+    const double irho22 = irho2 * irho2, irho23 = irho22 * irho2;
+    const double idth = 1.0 / dth;
+    const double ir1 = 1.0 / r1;
+    const double isth = 1.0 / sth;
+    const double irho23_dth = irho23 * idth;
+    const double fac1 = r2 - a2cth2;
+    const double fac1_rho23 = fac1 * irho23;
+    const double fac2 = 2.0 * rho2; /* a^2 + 2 r^2 + a^2 cos(2 theta) */
+    const double fac3 = a2 + r1 * (r1 - 2.0);
+
+    c.G0[S00] = 2.0 * r1 * fac1_rho23;
+    c.G0[S01] = r1 * (2.0 * r1 + rho2) * fac1_rho23;
+    c.G0[S02] = -a2 * r1 * s2th * dth * irho22;
+    c.G0[S03] = -2.0 * a * r1sth2 * fac1_rho23;
+    c.G0[S11] = 2.0 * r2 * (r4 + r1 * fac1 - a4cth4) * irho23;
+    c.G0[S12] = r1 * c.G0[S02];
+    c.G0[S13] = a * r1 * (-r1 * (r3 + 2.0 * fac1) + a4cth4) * sth2 * irho23;
+    c.G0[S22] = -2.0 * r2 * dth2 * irho2;
+    c.G0[S23] = a3 * r1sth2 * s2th * dth * irho22;
+    c.G0[S33] = 2.0 * r1sth2 * (-r1 * rho22 + a2sth2 * fac1) * irho23;
+
+    c.G1[S00] = fac3 * fac1_rho23 * ir1;
+    c.G1[S01] = fac1 * (-2.0 * r1 + a2sth2) * irho23;
+    c.G1[S02] = 0.0;
+    c.G1[S03] = -a * sth2 * c.G1[S00];
+    c.G1[S11] = (r4 * (r1 - 2.0) * (1.0 + r1) +
+                 a2 * (a2 * r1 * (1.0 + 3.0 * r1) * cth4 + a4cth4 * cth2 + r3 * sth2 +
+                       r1 * cth2 * (2.0 * r1 + 3.0 * r3 - a2sth2))) *
+                irho23;
+    c.G1[S12] = -a2 * dth * s2th * (0.5 * irho2);
+    c.G1[S13] = a * sth2 *
+                (a4 * r1 * cth4 + r2 * (2.0 * r1 + r3 - a2sth2) + a2cth2 * (2.0 * r1 * (r2 - 1.0) + a2sth2)) *
+                irho23;
+    c.G1[S22] = -fac3 * dth2 * irho2;
+    c.G1[S23] = 0.0;
+    c.G1[S33] = -fac3 * sth2 * (r1 * rho22 - a2sth2 * fac1) * irho23 * ir1;
+
+    c.G2[S00] = -a2 * r1 * s2th * irho23_dth;
+    c.G2[S01] = r1 * c.G2[S00];
+    c.G2[S02] = 0.0;
+    c.G2[S03] = a * r1 * (a2 + r2) * s2th * irho23_dth;
+    c.G2[S11] = r2 * c.G2[S00];
+    c.G2[S12] = r2 * irho2;
+    c.G2[S13] = (a * r1 * cs * (r3 * (2.0 + r1) + a2 * (2.0 * r1 * (1.0 + r1) * cth2 + a2 * cth4 + 2.0 * r1sth2))) *
+                irho23_dth;
+    c.G2[S22] = -a2 * cs * dth * irho2 + d2th * idth;
+    c.G2[S23] = 0.0;
+    c.G2[S33] = -cs * (rho23 + a2sth2 * rho2 * (r1 * (4.0 + r1) + a2cth2) + 2.0 * r1 * a4 * sth4) * irho23_dth;
+
+    const double cot = cth * isth;
+    c.G3[S00] = a * fac1_rho23;
+    c.G3[S01] = r1 * c.G3[S00];
+    c.G3[S02] = -2.0 * a * r1 * cot * dth * irho22;
+    c.G3[S03] = -a2sth2 * fac1_rho23;
+    c.G3[S11] = r2 * c.G3[S00];
+    /* a^2 + 2 r (2 + r) + a^2 cos(2 theta) = fac2 + 4 r ; 1/fac2^2 = irho22 / 4 */
+    c.G3[S12] = -2.0 * a * r1 * (fac2 + 4.0 * r1) * cot * dth * (0.25 * irho22);
+    c.G3[S13] = r1 * (r1 * rho22 - a2sth2 * fac1) * irho23;
+    c.G3[S22] = -a * r1 * dth2 * irho2;
+    c.G3[S23] = dth * (0.25 * fac2 * fac2 * cot + a2 * r1 * s2th) * irho22;
+    c.G3[S33] = (-a * r1sth2 * rho22 + a3 * sth4 * fac1) * irho23;
+}
+
+/* dk^i/dlambda = -Gamma^i_{jk} k^j k^k (reference harm_model.cpp:1255-1262, :1578-1586) */
+__device__ __forceinline__ void geodesic_rhs(const Connection &c, const double k[4], double dk[4]) {
+    const double k00 = k[0] * k[0], k01 = 2.0 * k[0] * k[1], k02 = 2.0 * k[0] * k[2], k03 = 2.0 * k[0] * k[3];
+    const double k11 = k[1] * k[1], k12 = 2.0 * k[1] * k[2], k13 = 2.0 * k[1] * k[3];
+    const double k22 = k[2] * k[2], k23 = 2.0 * k[2] * k[3], k33 = k[3] * k[3];
+    dk[0] = -(c.G0[S00] * k00 + c.G0[S01] * k01 + c.G0[S02] * k02 + c.G0[S03] * k03 + c.G0[S11] * k11 +
+              c.G0[S12] * k12 + c.G0[S13] * k13 + c.G0[S22] * k22 + c.G0[S23] * k23 + c.G0[S33] * k33);
+    dk[1] = -(c.G1[S00] * k00 + c.G1[S01] * k01 + c.G1[S03] * k03 + c.G1[S11] * k11 + c.G1[S12] * k12 +
+              c.G1[S13] * k13 + c.G1[S22] * k22 + c.G1[S33] * k33);
+    dk[2] = -(c.G2[S00] * k00 + c.G2[S01] * k01 + c.G2[S03] * k03 + c.G2[S11] * k11 + c.G2[S12] * k12 +
+              c.G2[S13] * k13 + c.G2[S22] * k22 + c.G2[S33] * k33);
+    dk[3] = -(c.G3[S00] * k00 + c.G3[S01] * k01 + c.G3[S02] * k02 + c.G3[S03] * k03 + c.G3[S11] * k11 +
+              c.G3[S12] * k12 + c.G3[S13] * k13 + c.G3[S22] * k22 + c.G3[S23] * k23 + c.G3[S33] * k33);
+}
+
+__device__ __forceinline__ void init_dkdlam(const GmParams &P, const double x[4], const double k[4], double dk[4]) {
+    const GeoPoint q = geo_point(P, x[1], x[2]);
+    Connection c;
+    connection_eval(P, q, c);
+    geodesic_rhs(c, k, dk);
+}
+
+/* reference harm_model.cpp:1620-1630; 1/(A/B + eps) is evaluated as B/(A + eps B): 4 divisions instead of 7 */
+__device__ __forceinline__ double step_size(const GmParams &P, const double x[4], const double k[4]) {
+    const double b1 = fabs(k[1]) + kEps, b2 = fabs(k[2]) + kEps, b3 = fabs(k[3]) + kEps;
+    const double a1 = fabs(kStepEps * x[1]);
+    const double a2 = fabs(kStepEps * fmin(x[2], P.x_stop2 - x[2]));
+    const double a3 = kStepEps;
+    const double i1 = b1 / (a1 + kEps * b1);
+    const double i2 = b2 / (a2 + kEps * b2);
+    const double i3 = b3 / (a3 + kEps * b3);
+    return 1.0 / (i1 + i2 + i3);
+}
+
+/* One push_photon attempt of size dl from (x,k,dk) (reference harm_model.cpp:1230-1277): half kick, drift,
+ * connection at the new point, <= 2 fixed-point iterations, energy check.  Returns true if the attempt must
+ * be rejected and halved (the caller applies the depth limit).  Outputs are written to xn/kn/dkn/e1. */
+__device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4], const double k[4],
+                                             const double dk[4], double dl, double e_0_s, double xn[4],
+                                             double kn[4], double dkn[4], double &e1) {
+    const double dl_2 = 0.5 * dl;
+    double kh[4], kp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double d = dk[i] * dl_2;
+        kh[i] = k[i] + d;
+        kp[i] = kh[i] + d;
+        xn[i] = x[i] + kh[i] * dl;
+    }
+    const GeoPoint q = geo_point(P, xn[1], xn[2]);
+    Connection c;
+    connection_eval(P, q, c);
+    double err;
+    {
+        geodesic_rhs(c, kp, dkn);
+        err = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            kn[i] = kh[i] + dl_2 * dkn[i];
+            err += fabs((kp[i] - kn[i]) / (kn[i] + kEps));
+        }
+    }
+    if (err > kETol) { /* second (last) fixed-point iteration, kMaxIter = 2 */
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            kp[i] = kn[i];
+        geodesic_rhs(c, kp, dkn);
+        err = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            kn[i] = kh[i] + dl_2 * dkn[i];
+            err += fabs((kp[i] - kn[i]) / (kn[i] + kEps));
+        }
+    }
+    double g00, g01, g03;
+    metric_cov_row0(P, q, g00, g01, g03);
+    e1 = -(kn[0] * g00 + kn[1] * g01 + kn[3] * g03);
+    const double err_e = fabs((e1 - e_0_s) / e_0_s);
+    /* !(err <= tol) also catches NaN; isinf(err) > tol anyway (reference :1279) */
+    return (err_e > 1.0e-4) || !(err <= kETol);
+}
+
+/* Halving bookkeeping shared by the flattened transport loop and the stand-alone full push.
+ * A step of size dl is a binary tree of depth <= 7; `pos` counts completed 1/128ths, `level` is the depth
+ * of the attempt to make at `pos`.  After an accepted attempt at (pos, level) the recursion of the reference
+ * returns to the nearest ancestor whose second half has not run: level' = 7 - ctz(pos'). */
+__device__ __forceinline__ int halving_next_level(int pos) { return kMaxHalvings - (__ffs(pos) - 1); }
+
+/* complete push_photon (used for the scatter back-up and by tests); returns the number of attempts */
+__device__ __forceinline__ int push_photon_full(const GmParams &P, double x[4], double k[4], double dk[4],
+                                                double &e_0_s, double dl) {
+    int pos = 0, level = 0, attempts = 0;
+    while (pos < 128) {
+        if (x[1] < P.x_start1) { /* reference :1218-1220: silent no-op */
+            pos += 128 >> level;
+            level = (pos < 128) ? halving_next_level(pos) : 0;
+            continue;
+        }
+        double xn[4], kn[4], dkn[4], e1;
+        const bool fail = push_attempt(P, x, k, dk, ldexp(dl, -level), e_0_s, xn, kn, dkn, e1);
+        ++attempts;
+        if (fail && level < kMaxHalvings) {
+            ++level;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x[i] = xn[i];
+                k[i] = kn[i];
+                dk[i] = dkn[i];
+            }
+            e_0_s = e1;
+            pos += 128 >> level;
+            level = (pos < 128) ? halving_next_level(pos) : 0;
+        }
+    }
+    return attempts;
+}
+
+} /* namespace gm */

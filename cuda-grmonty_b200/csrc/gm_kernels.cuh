@@ -1,0 +1,359 @@
+/*
+ * gm_kernels.cuh -- __global__ entry points of the B200 transport path.
+ *
+ *   zone_kernel       per-zone emission data: photon count, dn_max, fluid state, tetrad   (once per context)
+ *   birth_kernel      make_super_photon for one generation of primaries -> photon queue   (per generation)
+ *   transport_kernel  persistent wavefront: pop / track / scatter / record                (per generation)
+ *
+ * Reference functions restated: init_zone harm_model.cpp:1337-1389, get_zone :673-704,
+ * sample_zone_photon :706-782, linear_interp_weight :784-792, run_simulation CPU loop :366-404.
+ */
+#pragma once
+#include "gm_transport.cuh"
+
+namespace gm {
+
+/* per-zone record used by the birth kernel (AoS: all photons of a zone read the same record) */
+struct ZoneData {
+    double n_e, theta_e, b, dn_max;
+    double e_con[4][4];
+    double e_cov_t[4]; /* e_cov[a][0], a = 0..3: gives e = -k_t */
+    double e_cov_p[4]; /* e_cov[a][3]: gives l = k_phi */
+};
+
+/* reference init_zone (+ get_zone's stochastic rounding, keyed by zone id instead of the global stream) */
+__global__ void zone_kernel(GmParams P, ZoneData *zones, double *nz_out, long long *num_to_gen) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= P.n0 * P.n1)
+        return;
+    const int i = z / P.n1, j = z % P.n1;
+    double x[4];
+    MetricCov g;
+    Fluid f;
+    fluid_zone(P, i, j, x, g, f);
+    ZoneData zd;
+    zd.n_e = f.n_e;
+    zd.theta_e = f.theta_e;
+    zd.b = f.b;
+    zd.dn_max = 0.0;
+    double nz = 0.0;
+    bool emits = !(f.n_e == 0.0 || f.theta_e < kThetaEMin);
+    if (emits) {
+        const double l_bth = log(f.b * f.theta_e * f.theta_e);
+        double d_l = (l_bth - P.l_b_min) / P.d_l_b;
+        const int l = (int)d_l;
+        d_l -= l;
+        double ninterp = 0.0, dn_max = 0.0;
+        if (l < 0) {
+            emits = false;
+        } else if (l >= kNint) {
+            /* out-of-table branch incl. the reference's index slip (:1358-1369, Appendix A.9) */
+            for (int s = 0; s <= kNESamp; ++s) {
+                const double dn =
+                    f_eval(P, f.theta_e, f.b, exp(j * P.d_l_nu + P.l_nu_min)) / (exp(P.weight[s]) + 1.0e-100);
+                dn_max = fmax(dn_max, dn);
+                ninterp += P.d_l_nu * dn;
+            }
+        } else if (!isinf(P.nint[l]) && !isinf(P.nint[l + 1])) {
+            ninterp = exp((1.0 - d_l) * P.nint[l] + d_l * P.nint[l + 1]);
+            dn_max = exp((1.0 - d_l) * P.dndlnu_max[l] + d_l * P.dndlnu_max[l + 1]);
+        }
+        if (emits) {
+            const double k2 = k2_eval(P, f.theta_e);
+            if (k2 == 0.0) {
+                emits = false;
+            } else {
+                nz = P.geom_det[z] * f.n_e * f.b * f.theta_e * f.theta_e * ninterp / k2;
+                if (nz > P.nz_max) {
+                    nz = 0.0;
+                    emits = false;
+                }
+                zd.dn_max = emits ? dn_max : 0.0;
+            }
+        }
+    }
+    if (!emits)
+        nz = 0.0;
+    Rng r = rng_zone((uint64_t)z);
+    const double u = rng_uniform(P, r);
+    long long n = (long long)nz;
+    if (fmod(nz, 1.0) > u)
+        n += 1;
+    num_to_gen[z] = n;
+    if (nz_out)
+        nz_out[z] = nz;
+    /* tetrad of the zone (reference sample_zone_photon :717-731) */
+    double b_hat[4];
+    if (f.b > 0.0) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            b_hat[d] = f.b_con[d] * P.b_unit / f.b;
+    } else {
+        b_hat[0] = 1.0;
+        b_hat[1] = b_hat[2] = b_hat[3] = 0.0;
+    }
+    double e_cov[4][4];
+    make_tetrad(g, f.u_con, b_hat, zd.e_con, e_cov);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        zd.e_cov_t[a] = e_cov[a][0];
+        zd.e_cov_p[a] = e_cov[a][3];
+    }
+    zones[z] = zd;
+}
+
+/* reference linear_interp_weight, harm_model.cpp:784-792 */
+__device__ __forceinline__ double linear_interp_weight(const GmParams &P, double nu) {
+    return interp_exp_table(P.weight, log(nu), P.l_nu_min, P.d_l_nu);
+}
+
+/* birth state of the primary with global index idx (reference sample_zone_photon :733-781) */
+struct Birth {
+    double x[4], k[4], w, e, l, n_e, theta_e, b;
+    Rng rng;
+};
+
+__device__ __forceinline__ void make_primary(const GmParams &P, const ZoneData *zones, const long long *prefix,
+                                             long long idx, Birth &B) {
+    /* zone z with prefix[z] <= idx < prefix[z+1] */
+    long long lo = 0, hi = (long long)P.n0 * P.n1;
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= idx)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const int i = (int)(lo / P.n1), j = (int)(lo % P.n1);
+    const ZoneData *zd = zones + lo;
+    const double n_e = __ldg(&zd->n_e), theta_e = __ldg(&zd->theta_e), b = __ldg(&zd->b);
+    const double dn_max = __ldg(&zd->dn_max);
+    Rng r = rng_primary((uint64_t)idx);
+    double nu, weight;
+    do {
+        nu = exp(rng_uniform(P, r) * P.n_l_n + P.l_nu_min);
+        weight = linear_interp_weight(P, nu);
+    } while (rng_uniform(P, r) > (f_eval(P, theta_e, b, nu) / (weight + 1.0e-100)) / dn_max);
+    const double j_max = synch_sin(P, nu, n_e, theta_e, b, 1.0);
+    double cos_th, sin_th;
+    do {
+        cos_th = 2.0 * rng_uniform(P, r) - 1.0;
+        sin_th = sqrt(1.0 - cos_th * cos_th);
+    } while (rng_uniform(P, r) > (synch_sin(P, nu, n_e, theta_e, b, sin_th) / j_max));
+    double sin_phi, cos_phi;
+    sincospi(2.0 * rng_uniform(P, r), &sin_phi, &cos_phi);
+    const double e = nu * kHPL / (kME * kCL * kCL);
+    double kt[4] = {e, e * cos_th, e * sin_th * cos_phi, e * sin_th * sin_phi};
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        B.k[m] = __ldg(&zd->e_con[0][m]) * kt[0] + __ldg(&zd->e_con[1][m]) * kt[1] +
+                 __ldg(&zd->e_con[2][m]) * kt[2] + __ldg(&zd->e_con[3][m]) * kt[3];
+    kt[0] = -kt[0];
+    B.e = -(__ldg(&zd->e_cov_t[0]) * kt[0] + __ldg(&zd->e_cov_t[1]) * kt[1] + __ldg(&zd->e_cov_t[2]) * kt[2] +
+            __ldg(&zd->e_cov_t[3]) * kt[3]);
+    B.l = __ldg(&zd->e_cov_p[0]) * kt[0] + __ldg(&zd->e_cov_p[1]) * kt[1] + __ldg(&zd->e_cov_p[2]) * kt[2] +
+          __ldg(&zd->e_cov_p[3]) * kt[3];
+    B.x[0] = 0.0;
+    B.x[1] = P.x_start1 + (i + 0.5) * P.dx1;
+    B.x[2] = P.x_start2 + (j + 0.5) * P.dx2;
+    B.x[3] = 0.0;
+    B.w = weight;
+    B.n_e = n_e;
+    B.theta_e = theta_e;
+    B.b = b;
+    B.rng = r;
+}
+
+__device__ __forceinline__ void store_birth(const PhotonQueue &Q, unsigned long long slot, const Birth &B,
+                                            unsigned int tag) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        qstore(Q, Q_X0 + m, slot, B.x[m]);
+        qstore(Q, Q_K0 + m, slot, B.k[m]);
+    }
+    qstore(Q, Q_W, slot, B.w);
+    qstore(Q, Q_E, slot, B.e);
+    qstore(Q, Q_L, slot, B.l);
+    qstore(Q, Q_X1I, slot, B.x[1]);
+    qstore(Q, Q_X2I, slot, B.x[2]);
+    qstore(Q, Q_NE0, slot, B.n_e);
+    qstore(Q, Q_TE0, slot, B.theta_e);
+    qstore(Q, Q_B0, slot, B.b);
+    qstore(Q, Q_E0, slot, B.e);
+    Q.rng[slot] = make_uint4(B.rng.id0, B.rng.id1, B.rng.id2, B.rng.ctr);
+    Q.n_scatt[slot] = 0;
+    Q.ready[slot] = tag;
+}
+
+/* Processing order: position j of a run handles primary (j * mult) mod total, a Weyl sequence with
+ * mult ~ total / golden ratio coprime to total, so that every contiguous range of positions samples all
+ * emission zones evenly and the bias statistics frozen at a generation start are representative.  The photon
+ * itself (Philox stream, birth zone) depends only on its primary index. */
+__host__ __device__ __forceinline__ long long permute_position(long long j, long long mult, long long total) {
+    return (long long)(((unsigned __int128)(unsigned long long)j * (unsigned long long)mult) %
+                       (unsigned long long)total);
+}
+
+/* positions first, first + stride, ... (count of them) -> queue slots 0..count-1 */
+__global__ void birth_kernel(GmParams P, PhotonQueue Q, const ZoneData *zones, const long long *prefix,
+                             long long first, long long stride, long long count, long long mult, long long total,
+                             unsigned int tag) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
+         t += (long long)gridDim.x * blockDim.x) {
+        Birth B;
+        make_primary(P, zones, prefix, permute_position(first + t * stride, mult, total), B);
+        store_birth(Q, (unsigned long long)t, B, tag);
+    }
+}
+
+/* ---- the persistent transport kernel ------------------------------------------------------------------- */
+extern __shared__ double gm_smem[];
+
+template <int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const TransportArgs A) {
+    const PhotonQueue &Q = A.Q;
+    const int lane = threadIdx.x & 31;
+    double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
+    Live L;
+    bool has = false;
+    Work wk = {0u, 0u, 0u, 0u, 0u};
+    unsigned int idle_spins = 0;
+
+    for (;;) {
+        /* ---- refill empty lanes from the queue (warp-aggregated pop) ---- */
+        const unsigned int need = __ballot_sync(0xffffffffu, !has);
+        int n_done = 0;
+        if (need) {
+            unsigned long long base = 0;
+            int n_got = 0;
+            if (lane == 0) {
+                const unsigned long long h = ld_volatile_u64(Q.head);
+                unsigned long long t = ld_volatile_u64(Q.tail);
+                t = t < Q.capacity ? t : Q.capacity;
+                if (t > h) {
+                    const unsigned long long avail = t - h;
+                    const int want = __popc(need);
+                    n_got = avail < (unsigned long long)want ? (int)avail : want;
+                    if (atomicCAS(Q.head, h, h + n_got) == h)
+                        base = h;
+                    else
+                        n_got = 0;
+                }
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            n_got = __shfl_sync(0xffffffffu, n_got, 0);
+            if (!has) {
+                const int my = __popc(need & ((1u << lane) - 1u));
+                if (my < n_got) {
+                    const unsigned int slot = (unsigned int)(base + my);
+                    /* the producer reserved the slot before publishing it: wait for its ready tag */
+                    unsigned int spins = 0;
+                    while (ld_volatile_u32(Q.ready + slot) != A.gen_tag) {
+                        if (++spins > (1u << 26)) {
+                            atomicOr(A.A.error, 2u);
+                            break;
+                        }
+                    }
+                    __threadfence();
+                    if (begin_track(A, slot, L)) {
+                        has = true;
+                        ++wk.tracked;
+                    } else {
+                        ++n_done; /* invalid photon (reference :895-900): dropped */
+                        if (A.D.status && slot < A.D.n)
+                            A.D.status[slot] = 4;
+                    }
+                }
+            }
+        }
+        /* ---- nothing to do in this warp? ---- */
+        const unsigned int live = __ballot_sync(0xffffffffu, has);
+        if (!live) {
+            const unsigned int dmask = __ballot_sync(0xffffffffu, n_done != 0);
+            if (dmask && lane == 0)
+                atomicAdd(Q.finished, (unsigned long long)__popc(dmask));
+            int quit = 0;
+            if (lane == 0) {
+                const unsigned long long fin = ld_volatile_u64(Q.finished);
+                __threadfence();
+                const unsigned long long t = ld_volatile_u64(Q.tail);
+                quit = (fin >= t) || (ld_volatile_u32(A.A.error) & 2u);
+            }
+            quit = __shfl_sync(0xffffffffu, quit, 0);
+            if (quit)
+                break;
+            if (++idle_spins > 8)
+                __nanosleep(256);
+            continue;
+        }
+        idle_spins = 0;
+        /* ---- one flattened iteration for every live lane ---- */
+        if (has) {
+            bool record;
+            if (advance(A, L, snap, BLOCK, wk, record)) {
+                if (record) {
+                    record_super_photon(A, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
+                    L.status |= 1;
+                }
+                if (A.D.final_state && L.slot < A.D.n) {
+                    double *o = A.D.final_state + (size_t)L.slot * 12;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        o[i] = L.x[i];
+                        o[4 + i] = L.k[i];
+                    }
+                    o[8] = L.w;
+                    o[9] = L.tau_abs;
+                    o[10] = L.tau_scatt;
+                    o[11] = L.e_0_s;
+                    A.D.status[L.slot] = L.status;
+                    const uint4 r = make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr);
+                    Q.rng[L.slot] = r;
+                }
+                has = false;
+                ++n_done;
+            }
+        }
+        const unsigned int dmask = __ballot_sync(0xffffffffu, n_done != 0);
+        if (dmask) {
+            /* n_done is 0, 1 or 2 per lane; sum over the warp */
+            int s = n_done;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0)
+                atomicAdd(Q.finished, (unsigned long long)s);
+        }
+    }
+    /* flush work counters: warp-reduce, one atomic per warp and counter */
+    unsigned int c[5] = {wk.tracked, wk.steps, wk.attempts, wk.interactions, wk.scatters};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        unsigned long long v = c[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v)
+            atomicAdd(A.A.work + q, v);
+    }
+}
+
+/* FP64 FMA peak probe: 8 independent dependent-FMA chains per thread */
+__global__ void fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+} /* namespace gm */

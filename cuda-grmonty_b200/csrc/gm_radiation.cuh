@@ -1,0 +1,195 @@
+/*
+ * gm_radiation.cuh -- emissivity, absorption, hot Compton cross-section, bias; sm_100a device code.
+ *
+ * Reference: radiation.cpp:59-146 (bk_angle, fluid_nu, alpha_inv_scatt, alpha_inv_abs, b_nu_inv, jnu_inv,
+ * kappa_es), jnu_mixed.cpp:75-125,150-168 (synch, k2_eval, f_eval), hotcross.cpp:81-179
+ * (total_compton_cross_lkup and its numeric fall-back), harm_model.cpp:1391-1404 (bias_func).
+ *
+ * B200 notes: the synchrotron formula only needs sin(theta), so the pitch angle is carried as its cosine
+ * (sqrt(1-mu^2) instead of acos + sin); pow(x,1/3) is cbrt; the table look-ups are tiny (hotcross 143 KB,
+ * k2/f 1.6 KB) and stay in L1/L2 via the read-only path.
+ */
+#pragma once
+#include "gm_fluid.cuh"
+#include "gm_params.h"
+
+namespace gm {
+
+/* exp of a linear interpolation in a 201-entry log table (reference jnu_mixed.cpp:150-168;
+ * upper index clamped) */
+__device__ __forceinline__ double interp_exp_table(const double *tab, double lx, double l_min, double d_l) {
+    double d_i = (lx - l_min) / d_l;
+    int i = (int)d_i;
+    i = min(i, kNESamp - 1);
+    d_i -= i;
+    return exp((1.0 - d_i) * __ldg(tab + i) + d_i * __ldg(tab + i + 1));
+}
+
+__device__ __forceinline__ double k2_eval(const GmParams &P, double theta_e) {
+    if (theta_e < kThetaEMin)
+        return 0.0;
+    if (theta_e > kJnuMaxT)
+        return 2.0 * theta_e * theta_e;
+    return interp_exp_table(P.k2, log(theta_e), P.jnu_l_min_t, P.jnu_d_l_t);
+}
+
+__device__ __forceinline__ double f_eval(const GmParams &P, double theta_e, double b_mag, double nu) {
+    const double k = kJnuKFac * nu / (b_mag * theta_e * theta_e);
+    if (k > kJnuMaxK)
+        return 0.0;
+    if (k < kJnuMinK) {
+        const double x = cbrt(k);
+        return x * (37.67503800178 + 2.240274341836 * x);
+    }
+    return interp_exp_table(P.f, log(k), P.jnu_l_min_k, P.jnu_d_l_k);
+}
+
+/* thermal synchrotron emissivity given sin(theta) (reference synch, jnu_mixed.cpp:75-100) */
+__device__ __forceinline__ double synch_sin(const GmParams &P, double nu, double n_e, double theta_e, double b,
+                                            double sin_th) {
+    if (theta_e < kThetaEMin)
+        return 0.0;
+    const double k2 = k2_eval(P, theta_e);
+    const double nu_c = kEE * b / (2.0 * kPi * kME * kCL);
+    const double nu_s = (2.0 / 9.0) * nu_c * theta_e * theta_e * sin_th;
+    if (nu > 1.0e12 * nu_s)
+        return 0.0;
+    const double x = nu / nu_s;
+    const double xp = cbrt(x);
+    const double xx = sqrt(x) + kJnuCst * sqrt(xp);
+    const double f = xx * xx;
+    return (1.41421356237309504880 * kPi * kEE * kEE * n_e * nu_s / (3.0 * kCL * k2)) * f * exp(-xp);
+}
+
+/* Klein-Nishina total cross-section / sigma_T (reference hotcross.cpp:144-152) */
+__device__ __forceinline__ double hc_klein_nishina(double w) {
+    if (w < 1.0e-3)
+        return (1.0 - 2.0 * w);
+    const double iw = 1.0 / w;
+    const double t = 1.0 + 2.0 * w;
+    return (3.0 / 4.0) * (2.0 * iw * iw + (0.5 * iw - (1.0 + w) * iw * iw * iw) * log(t) + (1.0 + w) / (t * t));
+}
+
+/* K2(1/theta) exp(1/theta): trapezoid rule on K_nu(x) e^x = int_0^inf exp(-x (cosh t - 1)) cosh(nu t) dt,
+ * which converges geometrically for this analytic integrand.  The reference calls std::cyl_bessel_k
+ * (hotcross.cpp:157); only the cold out-of-table fall-back needs it on the device. */
+__device__ __noinline__ double k2_scaled(double x) {
+    const double h = 0.125;
+    double s = 0.5;
+    for (int n = 1; n < 400; ++n) {
+        const double t = n * h;
+        const double arg = x * (cosh(t) - 1.0);
+        if (arg > 745.0)
+            break;
+        s += exp(-arg) * cosh(2.0 * t);
+    }
+    return s * h;
+}
+
+/* numeric integral over the electron distribution (reference total_compton_cross_num, hotcross.cpp:108-142);
+ * cold path: only reached when (w, theta_e) leaves the table, SURVEY hard part H4 */
+__device__ __noinline__ double hotcross_num(double w, double theta_e) {
+    if (isnan(w))
+        return 0.0;
+    if (theta_e < kHcMinT && w < kHcMinW)
+        return kSigmaThomson;
+    if (theta_e < kHcMinT)
+        return hc_klein_nishina(w) * kSigmaThomson;
+    const double k2f = (theta_e > 1.0e-2) ? k2_scaled(1.0 / theta_e) : sqrt(kPi * theta_e / 2.0);
+    double cross = 0.0;
+    for (double mu_e = -1.0 + 0.5 * kHcDMuE; mu_e < 1.0; mu_e += kHcDMuE) {
+        for (double gamma_e = 1.0 + 0.5 * theta_e * kHcDGammaE; gamma_e < 1.0 + kHcMaxGamma * theta_e;
+             gamma_e += theta_e * kHcDGammaE) {
+            const double sq = sqrt(gamma_e * gamma_e - 1.);
+            const double dnd = (gamma_e * sq / (theta_e * k2f)) * exp(-(gamma_e - 1.) / theta_e);
+            const double v = sq / gamma_e;
+            const double we = w * gamma_e * (1.0 - mu_e * v);
+            cross += theta_e * kHcDMuE * kHcDGammaE * (hc_klein_nishina(we) * (1.0 - mu_e * v)) * (0.5 * dnd);
+        }
+    }
+    return cross * kSigmaThomson;
+}
+
+/* reference total_compton_cross_lkup, hotcross.cpp:81-106 */
+__device__ __forceinline__ double hotcross_lkup(const GmParams &P, double w, double theta_e) {
+    if (w * theta_e < 1.0e-6)
+        return kSigmaThomson;
+    if (theta_e < kHcMinT)
+        return hc_klein_nishina(w) * kSigmaThomson;
+    if (w <= kHcMinW || w >= kHcMaxW || theta_e <= kHcMinT || theta_e >= kHcMaxT)
+        return hotcross_num(w, theta_e);
+    const double qw = (log10(w) - P.hc_l_min_w) / P.hc_d_l_w;
+    const double qt = (log10(theta_e) - P.hc_l_min_t) / P.hc_d_l_t;
+    const int i = (int)qw, j = (int)qt;
+    const double d_i = qw - i, d_j = qt - j;
+    const double *t = P.hotcross + i * (kHcNT + 1) + j;
+    const double l_cross = (1.0 - d_i) * (1.0 - d_j) * __ldg(t) + d_i * (1.0 - d_j) * __ldg(t + kHcNT + 1) +
+                           (1.0 - d_i) * d_j * __ldg(t + 1) + d_i * d_j * __ldg(t + kHcNT + 2);
+    return exp10(l_cross);
+}
+
+/* fluid-frame photon energy (units of m_e c^2) and cosine of the angle between k and b
+ * (reference bk_angle radiation.cpp:59-87, fluid_nu :89-101) */
+__device__ __forceinline__ void fluid_frame(const GmParams &P, const double k[4], const Fluid &f, double &e_fluid,
+                                            double &mu) {
+    const double ku = k[0] * f.u_cov[0] + k[1] * f.u_cov[1] + k[2] * f.u_cov[2] + k[3] * f.u_cov[3];
+    e_fluid = -ku;
+    if (f.b == 0.0) {
+        mu = 0.0; /* theta = pi/2 */
+    } else {
+        const double kb = k[0] * f.b_cov[0] + k[1] * f.b_cov[1] + k[2] * f.b_cov[2] + k[3] * f.b_cov[3];
+        mu = kb / (fabs(ku) * f.b / P.b_unit);
+        mu = fmin(fmax(mu, -1.0), 1.0);
+    }
+}
+
+/* invariant scattering opacity nu * sigma_hot * n_e (reference alpha_inv_scatt / kappa_es,
+ * radiation.cpp:103-107,142-146; the m_p factors cancel) */
+__device__ __forceinline__ double alpha_inv_scatt(const GmParams &P, double nu, double theta_e, double n_e) {
+    const double e_g = kHPL * nu / (kME * kCL * kCL);
+    return nu * hotcross_lkup(P, e_g, theta_e) * n_e;
+}
+
+/* reference b_nu_inv, radiation.cpp:120-128 */
+__device__ __forceinline__ double b_nu_inv(double nu, double theta_e) {
+    const double x = kHPL * nu / (kME * kCL * kCL * theta_e);
+    const double c = 2.0 * kHPL / (kCL * kCL);
+    if (x < 1.0e-3)
+        return c / (x / 24.0 * (24.0 + x * (12.0 + x * (4.0 + x))));
+    return c / (exp(x) - 1.0);
+}
+
+/* invariant absorption opacity by Kirchhoff's law (reference alpha_inv_abs, radiation.cpp:109-118) */
+__device__ __forceinline__ double alpha_inv_abs_sin(const GmParams &P, double nu, double theta_e, double n_e,
+                                                    double b, double sin_th) {
+    const double j = synch_sin(P, nu, n_e, theta_e, b, sin_th) / (nu * nu);
+    return j / (b_nu_inv(nu, theta_e) + 1.0e-100);
+}
+
+/* reference bias_func, harm_model.cpp:1391-1404, with the generation's frozen statistics */
+__device__ __forceinline__ double bias_func(const GmParams &P, const GmBiasStats &s, double theta_e, double w) {
+    const double mx = 0.5 * w / kWeightMin;
+    const double avg_num_scatt = s.n_scatt / (1.0 * s.n_recorded + 1.0);
+    double bias = 100.0 * theta_e * theta_e / (P.bias_norm * s.max_tau_scatt * (avg_num_scatt + 2.0));
+    bias = fmax(bias, kTpOverTe);
+    if (bias > mx)
+        bias = mx;
+    return bias / kTpOverTe;
+}
+
+/* both opacities at once for a photon with wave-vector k in fluid f */
+__device__ __forceinline__ void opacities(const GmParams &P, const double k[4], const Fluid &f, double &nu,
+                                          double &alpha_scatt, double &alpha_abs) {
+    double e_fluid, mu;
+    fluid_frame(P, k, f, e_fluid, mu);
+    nu = e_fluid * kME * kCL * kCL / kHPL;
+    if (nu < 0.0 || isnan(nu)) {
+        alpha_scatt = 0.0;
+        alpha_abs = 0.0;
+        return;
+    }
+    alpha_scatt = alpha_inv_scatt(P, nu, f.theta_e, f.n_e);
+    alpha_abs = alpha_inv_abs_sin(P, nu, f.theta_e, f.n_e, f.b, sqrt(1.0 - mu * mu));
+}
+
+} /* namespace gm */

@@ -95,8 +95,8 @@ typedef struct grmonty_b200_config {
     int32_t threads_per_block;
     int32_t blocks_per_sm;
     int64_t queue_capacity; /* photon slots in the device queue */
-    int64_t gen0;           /* primaries (global) in the first generation; doubles each generation ... */
-    int64_t gen_cap;        /* ... up to this cap.  Bias statistics are frozen within a generation. */
+    int64_t gen0;           /* positions in the first generation (default 32); doubles each generation ... */
+    int64_t gen_cap;        /* ... up to this cap (default 2^22).  Bias statistics are frozen within a generation. */
 } grmonty_b200_config;
 
 /* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */
@@ -123,8 +123,10 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg);
  * reference harm_model.cpp:673-704. */
 int grmonty_b200_total_primaries(grmonty_b200_ctx *ctx, int64_t *total);
 
-/* Generate, transport and record this rank's share of primaries [first, last) of the global sequence
- * (last < 0: to the end).  Blocking.  Replaces the CPU loop at reference harm_model.cpp:366-404. */
+/* Generate, transport and record this rank's share (j % world == rank) of positions [first, last) of the
+ * processing sequence (last < 0: to the end); position j handles primary (j * mult) mod total, a fixed
+ * permutation of the zone-ordered primaries (see DESIGN.md "processing order").  Blocking.
+ * Replaces the CPU loop at reference harm_model.cpp:366-404. */
 int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last);
 /* = run_range(ctx, 0, -1) */
 int grmonty_b200_run(grmonty_b200_ctx *ctx);

@@ -1331,6 +1331,34 @@ void orc_run_primary(orc_model *m, const int64_t *prefix, const double *dn_max, 
     m->n_created++;
 }
 
+/* Processing order.  Position j of the run handles primary pi(j) = (j * mult) mod total with mult ~ total/phi
+ * coprime to total (a Weyl sequence): every contiguous range of positions samples the whole zone-ordered
+ * index range evenly, so the bias statistics frozen at a generation start are representative of all zones.
+ * (The reference walks the zones in order, harm_model.cpp:673-704, and updates the statistics after every
+ * photon; frozen statistics in zone order would see only the horizon-crossing inner zones at first.)
+ * The photon itself -- its Philox stream and birth zone -- depends only on the primary index, not on j. */
+static int64_t gcd64(int64_t a, int64_t b) {
+    while (b) {
+        int64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+int64_t orc_perm_multiplier(int64_t total) {
+    if (total < 3)
+        return 1;
+    int64_t mult = (int64_t)((double)total * 0.6180339887498949);
+    if (mult < 1)
+        mult = 1;
+    while (gcd64(mult, total) != 1)
+        ++mult;
+    return mult;
+}
+int64_t orc_permute(int64_t j, int64_t mult, int64_t total) {
+    return (int64_t)(((unsigned __int128)(uint64_t)j * (uint64_t)mult) % (uint64_t)total);
+}
+
 void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int64_t gen0, int64_t gen_cap) {
     int64_t nz = (int64_t)m->n0 * m->n1;
     int64_t *num = (int64_t *)malloc(sizeof(int64_t) * nz);
@@ -1342,6 +1370,7 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
         prefix[z + 1] = prefix[z] + num[z];
     if (last < 0 || last > (int64_t)total)
         last = (int64_t)total;
+    const int64_t mult = orc_perm_multiplier((int64_t)total);
     /* generations partition the global index range [0,total); statistics freeze at generation starts */
     int64_t g_start = 0;
     for (int64_t g = 0; g_start < last; ++g) {
@@ -1351,10 +1380,10 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
             m->bias_n_scatt = (double)m->acc_n_scatt;
             m->bias_n_recorded = (double)m->acc_n_recorded;
         }
-        for (int64_t idx = g_start; idx < g_end && idx < last; ++idx) {
-            if (idx < first || (idx % world) != rank)
+        for (int64_t j = g_start; j < g_end && j < last; ++j) {
+            if (j < first || (j % world) != rank)
                 continue;
-            orc_run_primary(m, prefix, dn_max, idx);
+            orc_run_primary(m, prefix, dn_max, m->zone_order ? j : orc_permute(j, mult, (int64_t)total));
         }
         g_start = g_end;
     }

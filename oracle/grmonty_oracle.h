@@ -76,6 +76,7 @@ typedef struct orc_model {
     uint64_t acc_n_scatt;
     uint64_t acc_n_recorded;
     int stats_mode; /* ORC_STATS_LIVE: bias_* track acc_* after every record */
+    int zone_order; /* 1: process primaries in zone order like the reference; 0: Weyl-permuted order (CUDA path) */
     /* outputs */
     double spectrum[ORC_N_TH_BINS][ORC_N_E_BINS][ORC_SPEC_FIELDS]; /* field order of harm_data.hpp:129-143 */
     uint64_t n_created;
@@ -153,7 +154,10 @@ void orc_track_super_photon(orc_model *m, orc_photon *ph);
 void orc_record_super_photon(orc_model *m, const orc_photon *ph);
 /* Generation schedule shared with the CUDA path: sizes gen0, 2*gen0, ... capped at gen_cap. */
 int64_t orc_generation_size(int64_t gen_index, int64_t gen0, int64_t gen_cap);
-/* Run primaries [first,last) of the global zone-ordered sequence that satisfy idx % world == rank. */
+/* Run positions [first,last) of the processing sequence that satisfy j % world == rank; position j handles
+ * primary orc_permute(j) (or j itself when m->zone_order). */
+int64_t orc_perm_multiplier(int64_t total);
+int64_t orc_permute(int64_t j, int64_t mult, int64_t total);
 void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int64_t gen0, int64_t gen_cap);
 /* track one primary by global index; optionally returns the flat birth state */
 void orc_run_primary(orc_model *m, const int64_t *prefix, const double *dn_max, int64_t idx);

@@ -35,7 +35,7 @@ class OrcModel(C.Structure):
         ("seed", C.c_uint64),
         ("bias_max_tau_scatt", C.c_double), ("bias_n_scatt", C.c_double), ("bias_n_recorded", C.c_double),
         ("acc_max_tau_scatt", C.c_double), ("acc_n_scatt", C.c_uint64), ("acc_n_recorded", C.c_uint64),
-        ("stats_mode", C.c_int),
+        ("stats_mode", C.c_int), ("zone_order", C.c_int),
         ("spectrum", C.c_double * (N_TH * N_E * N_F)),
         ("n_created", C.c_uint64),
         ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64), ("n_interactions", C.c_uint64),
@@ -89,6 +89,10 @@ def lib():
         L.orc_zone_counts.restype = C.c_uint64
         L.orc_generation_size.restype = C.c_int64
         L.orc_generation_size.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        L.orc_perm_multiplier.restype = C.c_int64
+        L.orc_perm_multiplier.argtypes = [C.c_int64]
+        L.orc_permute.restype = C.c_int64
+        L.orc_permute.argtypes = [C.c_int64, C.c_int64, C.c_int64]
         L.orc_run.argtypes = [C.POINTER(OrcModel), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64]
         L.orc_bias_func.argtypes = [C.POINTER(OrcModel), C.c_double, C.c_double]
         L.orc_alpha_inv_scatt.argtypes = [C.POINTER(OrcModel), C.c_double, C.c_double, C.c_double]
@@ -128,7 +132,7 @@ class Model:
     SCALARS = ["x_start1", "x_start2", "dx1", "dx2", "dx3", "x_stop1", "x_stop2", "a", "h_slope", "r_0", "l_unit",
                "rho_unit", "b_unit", "theta_e_unit", "n_e_unit", "photon_n", "bias_norm", "d_tau_k", "x1_min"]
 
-    def __init__(self, d, seed=123, stats_mode=0):
+    def __init__(self, d, seed=123, stats_mode=0, zone_order=0):
         self.L = lib()
         self.m = OrcModel()
         self._keep = {}
@@ -141,6 +145,7 @@ class Model:
             setattr(self.m, k, ptr)
         self.m.seed = seed
         self.m.stats_mode = stats_mode
+        self.m.zone_order = zone_order
         self.set_bias_stats(float(d["max_tau_scatt0"]), 0, 0)
         self.m.acc_max_tau_scatt = float(d["max_tau_scatt0"])
 
@@ -245,5 +250,5 @@ class Model:
         self.L.orc_track_super_photon(self.ptr, C.byref(ph))
         return self.flat(ph)
 
-    def run(self, first=0, last=-1, rank=0, world=1, gen0=1 << 14, gen_cap=1 << 22):
+    def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22):
         self.L.orc_run(self.ptr, first, last, rank, world, gen0, gen_cap)

@@ -141,6 +141,18 @@ def test_bias(golden, orc_model):
         assert M.L.orc_bias_func(M.ptr, te, w) == pytest.approx(want, rel=1e-14)
 
 
+def test_permutation_is_a_bijection():
+    L = orc.lib()
+    for total in (1, 2, 3, 10, 97, 1000, 32240):
+        mult = L.orc_perm_multiplier(total)
+        idx = sorted(L.orc_permute(j, mult, total) for j in range(total))
+        assert idx == list(range(total))
+    # large totals: 128-bit product, still in range
+    total = 16_120_000_123
+    mult = L.orc_perm_multiplier(total)
+    assert 0 <= L.orc_permute(total - 1, mult, total) < total
+
+
 def test_tetrads(golden, orc_model):
     M = orc_model
     for row in golden["tetrad"]:
