@@ -35,12 +35,15 @@ struct grmonty_b200_ctx {
     ZoneData *d_zones = nullptr;
     long long *d_num = nullptr, *d_prefix = nullptr;
     double *d_nz = nullptr;
-    PhotonQueue Q{};
-    unsigned long long *d_qctr = nullptr; /* head, tail, finished */
+    PhotonPool pool{};
+    SlotQueue ready{}, scatter{};
+    unsigned long long *d_qctr = nullptr; /* n_alloc, finished, ready head/tail, scatter head/tail */
+    unsigned long long used_ready = 0, used_scatter = 0; /* queue entries to clear before the next batch */
     Accumulators A{};
     double *d_spectrum = nullptr;
     unsigned long long *d_counters = nullptr, *d_maxtau = nullptr, *d_work = nullptr;
     unsigned int *d_error = nullptr;
+    TransportArgs *d_args = nullptr; /* device-global copy of the kernel arguments (cold stages) */
     /* host state */
     std::vector<long long> prefix; /* [nzones+1] */
     long long total = 0;
@@ -261,21 +264,30 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         }
         CK(cudaMemcpy(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice));
 
-        /* ---- photon queue ---- */
+        /* ---- photon pool and stage queues ---- */
         unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 24);
-        if (cap > 0xfffffff0ull)
-            cap = 0xfffffff0ull; /* slots are addressed with 32 bits */
-        ctx->Q.capacity = cap;
-        CK(cudaMalloc(&ctx->Q.f, (size_t)Q_NFIELDS * cap * sizeof(double)));
-        CK(cudaMalloc(&ctx->Q.rng, cap * sizeof(uint4)));
-        CK(cudaMalloc(&ctx->Q.n_scatt, cap * sizeof(int)));
-        CK(cudaMalloc(&ctx->Q.ready, cap * sizeof(unsigned int)));
-        CK(cudaMemset(ctx->Q.ready, 0, cap * sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->d_qctr, 3 * sizeof(unsigned long long)));
-        CK(cudaMemset(ctx->d_qctr, 0, 3 * sizeof(unsigned long long)));
-        ctx->Q.head = ctx->d_qctr;
-        ctx->Q.tail = ctx->d_qctr + 1;
-        ctx->Q.finished = ctx->d_qctr + 2;
+        if (cap > 0x3fffffffull)
+            cap = 0x3fffffffull; /* slots are addressed with 32 bits */
+        ctx->pool.capacity = (unsigned int)cap;
+        CK(cudaMalloc(&ctx->pool.f, (size_t)P_NFIELDS * cap * sizeof(double)));
+        CK(cudaMalloc(&ctx->pool.rng, cap * sizeof(uint4)));
+        CK(cudaMalloc(&ctx->pool.crng, cap * sizeof(uint4)));
+        CK(cudaMalloc(&ctx->pool.n_scatt, cap * sizeof(int)));
+        CK(cudaMalloc(&ctx->pool.n_step, cap * sizeof(int)));
+        ctx->ready.capacity = (unsigned int)std::min<unsigned long long>(2 * cap, 0x7fffffffull);
+        ctx->scatter.capacity = (unsigned int)cap;
+        CK(cudaMalloc(&ctx->ready.entries, (size_t)ctx->ready.capacity * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->scatter.entries, (size_t)ctx->scatter.capacity * sizeof(unsigned int)));
+        CK(cudaMemset(ctx->ready.entries, 0, (size_t)ctx->ready.capacity * sizeof(unsigned int)));
+        CK(cudaMemset(ctx->scatter.entries, 0, (size_t)ctx->scatter.capacity * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_qctr, 6 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->d_qctr, 0, 6 * sizeof(unsigned long long)));
+        ctx->pool.n_alloc = ctx->d_qctr;
+        ctx->pool.finished = ctx->d_qctr + 1;
+        ctx->ready.head = ctx->d_qctr + 2;
+        ctx->ready.tail = ctx->d_qctr + 3;
+        ctx->scatter.head = ctx->d_qctr + 4;
+        ctx->scatter.tail = ctx->d_qctr + 5;
 
         /* ---- accumulators ---- */
         const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
@@ -284,6 +296,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         CK(cudaMalloc(&ctx->d_maxtau, sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_work, 8 * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_error, sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_args, sizeof(TransportArgs)));
         ctx->A.spectrum = ctx->d_spectrum;
         ctx->A.counters = ctx->d_counters;
         ctx->A.max_tau_bits = ctx->d_maxtau;
@@ -358,21 +371,49 @@ static long long generation_size(long long g, long long gen0, long long cap) {
     return std::min(s, cap);
 }
 
-/* run one batch of primaries (first, first+stride, ... count of them) with frozen bias statistics */
+static void fill_args(grmonty_b200_ctx *ctx, const GmBiasStats &bias, const DebugOut &dbg, TransportArgs &args) {
+    args.P = ctx->P;
+    args.bias = bias;
+    args.pool = ctx->pool;
+    args.ready = ctx->ready;
+    args.scatter = ctx->scatter;
+    args.A = ctx->A;
+    args.D = dbg;
+    args.self = ctx->d_args;
+}
+
+/* reset pool and queues for a batch whose first `count` records / ready entries are (or will be) filled */
+static int begin_batch(grmonty_b200_ctx *ctx, long long count) {
+    if (ctx->used_ready)
+        CK(cudaMemsetAsync(ctx->ready.entries, 0, ctx->used_ready * sizeof(unsigned int), ctx->stream));
+    if (ctx->used_scatter)
+        CK(cudaMemsetAsync(ctx->scatter.entries, 0, ctx->used_scatter * sizeof(unsigned int), ctx->stream));
+    ctx->used_ready = ctx->used_scatter = 0;
+    const unsigned long long qc[6] = {(unsigned long long)count, 0ull, 0ull, (unsigned long long)count, 0ull, 0ull};
+    CK(cudaMemcpyAsync(ctx->d_qctr, qc, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); /* qc is a stack buffer */
+    return GRMONTY_B200_OK;
+}
+
+/* run one batch of positions (first, first+stride, ... count of them) with frozen bias statistics;
+ * preloaded: records 0..count-1 and their ready entries were already written (test export) */
 static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, long long count,
                      const GmBiasStats &bias, const DebugOut &dbg, bool preloaded) {
     const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 2);
-    ++ctx->gen_tag;
-    unsigned long long qc[3] = {0ull, (unsigned long long)count, 0ull};
-    CK(cudaMemcpyAsync(ctx->d_qctr, qc, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
+    TransportArgs args;
+    fill_args(ctx, bias, dbg, args);
+    CK(cudaMemcpy(ctx->d_args, &args, sizeof(args), cudaMemcpyHostToDevice));
     float ms = 0.f;
     if (!preloaded) {
+        int rc = begin_batch(ctx, count);
+        if (rc)
+            return rc;
         const int bb = 128;
         const long long want = (count + bb - 1) / bb;
         const int nb = (int)std::min<long long>(want, (long long)ctx->sm_count * 16);
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        birth_kernel<<<nb, bb, 0, ctx->stream>>>(ctx->P, ctx->Q, ctx->d_zones, ctx->d_prefix, first, stride, count,
-                                                 ctx->perm_mult, ctx->total, ctx->gen_tag);
+        birth_kernel<<<nb, bb, 0, ctx->stream>>>(args, ctx->d_zones, ctx->d_prefix, first, stride, count,
+                                                 ctx->perm_mult, ctx->total);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaEventSynchronize(ctx->ev1));
@@ -380,16 +421,10 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         ctx->stats.kernel_ms += ms;
         ctx->stats.n_kernel_launches += 1;
     }
-    TransportArgs args;
-    args.P = ctx->P;
-    args.bias = bias;
-    args.Q = ctx->Q;
-    args.A = ctx->A;
-    args.D = dbg;
-    args.gen_tag = ctx->gen_tag;
     const size_t smem = (size_t)13 * ctx->threads * sizeof(double);
-    /* do not launch more threads than there are photons to start with (tiny test batches) */
-    long long blocks = std::min<long long>(ctx->grid_blocks, std::max<long long>(1, (count * 2 + ctx->threads - 1) / ctx->threads));
+    /* do not launch far more threads than there are photons to start with (tiny generations / test batches) */
+    long long blocks = std::min<long long>(ctx->grid_blocks,
+                                           std::max<long long>(1, (count * 2 + ctx->threads - 1) / ctx->threads));
     blocks = std::max<long long>(blocks, std::min<long long>(ctx->grid_blocks, ctx->sm_count));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     v->fn<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
@@ -401,15 +436,25 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     ctx->stats.transport_ms += ms;
     ctx->stats.n_kernel_launches += 1;
     unsigned int err = 0;
+    unsigned long long qc[6];
     CK(cudaMemcpyAsync(&err, ctx->d_error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(qc, ctx->d_qctr, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.queue_high_water = std::max<uint64_t>(ctx->stats.queue_high_water, qc[1]);
+    ctx->used_ready = std::min<unsigned long long>(qc[3], ctx->ready.capacity);
+    ctx->used_scatter = std::min<unsigned long long>(qc[5], ctx->scatter.capacity);
+    ctx->stats.queue_high_water = std::max<uint64_t>(ctx->stats.queue_high_water, qc[0]);
+    /* photons tracked = records created: primaries here, scattered children counted on the device */
+    unsigned long long w0;
+    CK(cudaMemcpy(&w0, ctx->d_work, sizeof(w0), cudaMemcpyDeviceToHost));
+    w0 += (unsigned long long)count;
+    CK(cudaMemcpy(ctx->d_work, &w0, sizeof(w0), cudaMemcpyHostToDevice));
     if (err & 1u)
-        return fail(ctx, GRMONTY_B200_EQUEUE, "device photon queue overflow: %llu slots needed, capacity %llu",
-                    qc[1], ctx->Q.capacity);
+        return fail(ctx, GRMONTY_B200_EQUEUE,
+                    "device photon pool/queue overflow: %llu records, %llu ready, %llu scatter entries needed "
+                    "(capacity %u); raise queue_capacity or lower gen_cap",
+                    qc[0], qc[3], qc[5], ctx->pool.capacity);
     if (err & 2u)
-        return fail(ctx, GRMONTY_B200_ECUDA, "device photon queue: ready-flag timeout");
+        return fail(ctx, GRMONTY_B200_ECUDA, "device photon queue: entry publication timeout");
     return GRMONTY_B200_OK;
 }
 
@@ -437,7 +482,7 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
     const long long world = ctx->cfg.world, rank = ctx->cfg.rank;
     const DebugOut nodbg = {nullptr, nullptr, 0};
     /* a batch never fills more than a quarter of the queue with primaries: the rest is room for children */
-    const long long chunk_cap = std::max<long long>(1024, (long long)(ctx->Q.capacity / 4));
+    const long long chunk_cap = std::max<long long>(1024, (long long)(ctx->pool.capacity / 4));
     long long g_start = 0;
     unsigned long long created = 0;
     for (long long g = 0; g_start < last; ++g) {
@@ -570,8 +615,9 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *bufs[] = {ctx->d_grid,  ctx->d_det,    ctx->d_hotcross, ctx->d_f,        ctx->d_k2,      ctx->d_weight,
                     ctx->d_nint,  ctx->d_dnmax,  ctx->d_zones,    ctx->d_num,      ctx->d_prefix,  ctx->d_nz,
-                    ctx->Q.f,     ctx->Q.rng,    ctx->Q.n_scatt,  ctx->Q.ready,    ctx->d_qctr,    ctx->d_spectrum,
-                    ctx->d_counters, ctx->d_maxtau, ctx->d_work,  ctx->d_error};
+                    ctx->pool.f,  ctx->pool.rng, ctx->pool.crng,  ctx->pool.n_scatt, ctx->pool.n_step, ctx->ready.entries,
+                    ctx->scatter.entries, ctx->d_qctr, ctx->d_spectrum,
+                    ctx->d_counters, ctx->d_maxtau, ctx->d_work,  ctx->d_error, ctx->d_args};
     for (void *b : bufs)
         if (b)
             cudaFree(b);

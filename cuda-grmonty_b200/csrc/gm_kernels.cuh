@@ -164,27 +164,6 @@ __device__ __forceinline__ void make_primary(const GmParams &P, const ZoneData *
     B.rng = r;
 }
 
-__device__ __forceinline__ void store_birth(const PhotonQueue &Q, unsigned long long slot, const Birth &B,
-                                            unsigned int tag) {
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        qstore(Q, Q_X0 + m, slot, B.x[m]);
-        qstore(Q, Q_K0 + m, slot, B.k[m]);
-    }
-    qstore(Q, Q_W, slot, B.w);
-    qstore(Q, Q_E, slot, B.e);
-    qstore(Q, Q_L, slot, B.l);
-    qstore(Q, Q_X1I, slot, B.x[1]);
-    qstore(Q, Q_X2I, slot, B.x[2]);
-    qstore(Q, Q_NE0, slot, B.n_e);
-    qstore(Q, Q_TE0, slot, B.theta_e);
-    qstore(Q, Q_B0, slot, B.b);
-    qstore(Q, Q_E0, slot, B.e);
-    Q.rng[slot] = make_uint4(B.rng.id0, B.rng.id1, B.rng.id2, B.rng.ctr);
-    Q.n_scatt[slot] = 0;
-    Q.ready[slot] = tag;
-}
-
 /* Processing order: position j of a run handles primary (j * mult) mod total, a Weyl sequence with
  * mult ~ total / golden ratio coprime to total, so that every contiguous range of positions samples all
  * emission zones evenly and the bias statistics frozen at a generation start are representative.  The photon
@@ -194,105 +173,123 @@ __host__ __device__ __forceinline__ long long permute_position(long long j, long
                        (unsigned long long)total);
 }
 
-/* positions first, first + stride, ... (count of them) -> queue slots 0..count-1 */
-__global__ void birth_kernel(GmParams P, PhotonQueue Q, const ZoneData *zones, const long long *prefix,
-                             long long first, long long stride, long long count, long long mult, long long total,
-                             unsigned int tag) {
+/* Complete start-of-track record of a photon born at x with wave-vector k (reference track_super_photon
+ * :902-915 -- done here, by the producer, with all lanes active, instead of by the consumer). */
+__device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigned int slot, const double x[4],
+                                                 const double k[4], double w, double e, double x1i, double x2i,
+                                                 double n_e_0, double theta_e_0, double b_0, double e_0,
+                                                 int n_scatt, const Rng &rng) {
+    const GmParams &P = A.P;
+    const GeoPoint q = geo_point(P, x[1], x[2]);
+    const MetricCov g = metric_cov(P, q);
+    Fluid f;
+    fluid_params(P, x[1], x[2], g, q, f);
+    const TrackInit t = track_init(P, A.bias, k, w, f);
+    Connection c;
+    connection_eval(P, q, c);
+    double dk[4];
+    geodesic_rhs(c, k, dk);
+    pool_store_hot(A.pool, slot, x, k, dk, w, e, 0.0, 0.0, t, rng, 0);
+    pstore(A.pool, P_E, slot, e);
+    pstore(A.pool, P_X1I, slot, x1i);
+    pstore(A.pool, P_X2I, slot, x2i);
+    pstore(A.pool, P_NE0, slot, n_e_0);
+    pstore(A.pool, P_TE0, slot, theta_e_0);
+    pstore(A.pool, P_B0, slot, b_0);
+    pstore(A.pool, P_E0, slot, e_0);
+    __stcg(A.pool.n_scatt + slot, n_scatt);
+}
+
+/* positions first, first + stride, ... (count of them) -> pool slots / ready-queue entries 0..count-1 */
+__global__ void birth_kernel(TransportArgs A, const ZoneData *zones, const long long *prefix, long long first,
+                             long long stride, long long count, long long mult, long long total) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
          t += (long long)gridDim.x * blockDim.x) {
         Birth B;
-        make_primary(P, zones, prefix, permute_position(first + t * stride, mult, total), B);
-        store_birth(Q, (unsigned long long)t, B, tag);
+        make_primary(A.P, zones, prefix, permute_position(first + t * stride, mult, total), B);
+        store_new_photon(A, (unsigned int)t, B.x, B.k, B.w, B.e, B.x[1], B.x[2], B.n_e, B.theta_e, B.b, B.e, 0,
+                         B.rng);
+        A.ready.entries[t] = (unsigned int)t + 1u;
     }
 }
 
 /* ---- the persistent transport kernel ------------------------------------------------------------------- */
 extern __shared__ double gm_smem[];
 
+__device__ __noinline__ void record_call(const TransportArgs *Ag, unsigned int slot, double x2, double x3, double w,
+                                         double tau_abs, double tau_scatt) {
+    record_super_photon(*Ag, slot, x2, x3, w, tau_abs, tau_scatt);
+}
+
 template <int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const TransportArgs A) {
-    const PhotonQueue &Q = A.Q;
     const int lane = threadIdx.x & 31;
     double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
     Live L;
     bool has = false;
     Work wk = {0u, 0u, 0u, 0u, 0u};
-    unsigned int idle_spins = 0;
+    unsigned int idle_spins = 0, iter = 0;
 
     for (;;) {
-        /* ---- refill empty lanes from the queue (warp-aggregated pop) ---- */
-        const unsigned int need = __ballot_sync(0xffffffffu, !has);
         int n_done = 0;
-        if (need) {
-            unsigned long long base = 0;
-            int n_got = 0;
-            if (lane == 0) {
-                const unsigned long long h = ld_volatile_u64(Q.head);
-                unsigned long long t = ld_volatile_u64(Q.tail);
-                t = t < Q.capacity ? t : Q.capacity;
-                if (t > h) {
-                    const unsigned long long avail = t - h;
-                    const int want = __popc(need);
-                    n_got = avail < (unsigned long long)want ? (int)avail : want;
-                    if (atomicCAS(Q.head, h, h + n_got) == h)
-                        base = h;
-                    else
-                        n_got = 0;
-                }
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            n_got = __shfl_sync(0xffffffffu, n_got, 0);
-            if (!has) {
-                const int my = __popc(need & ((1u << lane) - 1u));
-                if (my < n_got) {
-                    const unsigned int slot = (unsigned int)(base + my);
-                    /* the producer reserved the slot before publishing it: wait for its ready tag */
-                    unsigned int spins = 0;
-                    while (ld_volatile_u32(Q.ready + slot) != A.gen_tag) {
-                        if (++spins > (1u << 26)) {
-                            atomicOr(A.A.error, 2u);
-                            break;
-                        }
-                    }
-                    __threadfence();
-                    if (begin_track(A, slot, L)) {
-                        has = true;
-                        ++wk.tracked;
-                    } else {
-                        ++n_done; /* invalid photon (reference :895-900): dropped */
-                        if (A.D.status && slot < A.D.n)
-                            A.D.status[slot] = 4;
-                    }
+        const bool idle_warp = __ballot_sync(0xffffffffu, has) == 0u;
+        /* ---- scattering stage: any warp serves a full batch of parked photons (or, when it has nothing
+         *      else to do, whatever is parked), keeping its own live photons in registers ---- */
+        if (idle_warp || (iter & 3u) == 0u) {
+            unsigned int sslot = 0;
+            const bool got = queue_pop_warp(A, A.scatter, true, idle_warp ? 1 : 32, sslot);
+            if (got)
+                n_done += scatter_stage(A.self, sslot, wk.attempts, wk.scatters, wk.tracked);
+        }
+        /* ---- refill empty lanes from the ready queue: loads only ---- */
+        {
+            unsigned int slot = 0;
+            if (queue_pop_warp(A, A.ready, !has, 1, slot)) {
+                live_load(A, slot, L);
+                bool bad = (L.w == 0.0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
+                if (bad) {
+                    ++n_done; /* invalid photon (reference :895-900): dropped */
+                    if (A.D.status && slot < A.D.n)
+                        atomicOr(A.D.status + slot, 4);
+                } else {
+                    has = true;
                 }
             }
         }
         /* ---- nothing to do in this warp? ---- */
-        const unsigned int live = __ballot_sync(0xffffffffu, has);
-        if (!live) {
-            const unsigned int dmask = __ballot_sync(0xffffffffu, n_done != 0);
-            if (dmask && lane == 0)
-                atomicAdd(Q.finished, (unsigned long long)__popc(dmask));
+        if (__ballot_sync(0xffffffffu, has) == 0u) {
+            int s = n_done;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                s += __shfl_xor_sync(0xffffffffu, s, o);
             int quit = 0;
             if (lane == 0) {
-                const unsigned long long fin = ld_volatile_u64(Q.finished);
+                if (s)
+                    atomicAdd(A.pool.finished, (unsigned long long)s);
+                const unsigned long long fin = ld_volatile_u64(A.pool.finished);
                 __threadfence();
-                const unsigned long long t = ld_volatile_u64(Q.tail);
-                quit = (fin >= t) || (ld_volatile_u32(A.A.error) & 2u);
+                const unsigned long long na = ld_volatile_u64(A.pool.n_alloc);
+                quit = (fin >= na) || (ld_volatile_u32(A.A.error) & 2u);
             }
             quit = __shfl_sync(0xffffffffu, quit, 0);
             if (quit)
                 break;
-            if (++idle_spins > 8)
-                __nanosleep(256);
+            if (++idle_spins > 4)
+                __nanosleep(512);
             continue;
         }
         idle_spins = 0;
+        ++iter;
         /* ---- one flattened iteration for every live lane ---- */
         if (has) {
             bool record;
-            if (advance(A, L, snap, BLOCK, wk, record)) {
+            const StepResult r = advance(A, L, snap, BLOCK, wk, record);
+            if (r == STEP_FINISHED) {
                 if (record) {
-                    record_super_photon(A, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
+                    record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
                     L.status |= 1;
                 }
                 if (A.D.final_state && L.slot < A.D.n) {
@@ -306,23 +303,22 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                     o[9] = L.tau_abs;
                     o[10] = L.tau_scatt;
                     o[11] = L.e_0_s;
-                    A.D.status[L.slot] = L.status;
-                    const uint4 r = make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr);
-                    Q.rng[L.slot] = r;
+                    atomicOr(A.D.status + L.slot, L.status);
+                    A.pool.rng[L.slot] = make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr);
                 }
                 has = false;
                 ++n_done;
+            } else if (r == STEP_SCATTER) {
+                has = false; /* parked for the scattering stage */
             }
         }
-        const unsigned int dmask = __ballot_sync(0xffffffffu, n_done != 0);
-        if (dmask) {
-            /* n_done is 0, 1 or 2 per lane; sum over the warp */
+        if (__ballot_sync(0xffffffffu, n_done != 0)) {
             int s = n_done;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
                 s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0)
-                atomicAdd(Q.finished, (unsigned long long)s);
+                atomicAdd(A.pool.finished, (unsigned long long)s);
         }
     }
     /* flush work counters: warp-reduce, one atomic per warp and counter */

@@ -76,6 +76,7 @@ __device__ __forceinline__ double hc_klein_nishina(double w) {
 __device__ __noinline__ double k2_scaled(double x) {
     const double h = 0.125;
     double s = 0.5;
+#pragma unroll 1
     for (int n = 1; n < 400; ++n) {
         const double t = n * h;
         const double arg = x * (cosh(t) - 1.0);
@@ -97,7 +98,9 @@ __device__ __noinline__ double hotcross_num(double w, double theta_e) {
         return hc_klein_nishina(w) * kSigmaThomson;
     const double k2f = (theta_e > 1.0e-2) ? k2_scaled(1.0 / theta_e) : sqrt(kPi * theta_e / 2.0);
     double cross = 0.0;
+#pragma unroll 1
     for (double mu_e = -1.0 + 0.5 * kHcDMuE; mu_e < 1.0; mu_e += kHcDMuE) {
+#pragma unroll 1
         for (double gamma_e = 1.0 + 0.5 * theta_e * kHcDGammaE; gamma_e < 1.0 + kHcMaxGamma * theta_e;
              gamma_e += theta_e * kHcDGammaE) {
             const double sq = sqrt(gamma_e * gamma_e - 1.);

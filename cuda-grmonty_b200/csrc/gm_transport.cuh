@@ -1,23 +1,29 @@
 /*
- * gm_transport.cuh -- the superphoton life cycle on the device: birth, persistent transport loop, record.
+ * gm_transport.cuh -- the superphoton life cycle on the device: photon pool, stage queues, the flattened
+ * geodesic/interaction step, the warp-coherent scattering stage, and spectrum recording.
  *
- * Reference (CPU path, cuda_grmonty/harm_model.cpp): make_super_photon :794-811, get_zone :673-704,
- * init_zone :1337-1389, sample_zone_photon :706-782, track_super_photon :894-1069, stop_criterion :1589-1616,
- * record_super_photon :1291-1335.
+ * Reference (CPU path, cuda_grmonty/harm_model.cpp): track_super_photon :894-1069, stop_criterion :1589-1616,
+ * scatter_super_photon :1071-1145, record_super_photon :1291-1335.
  *
  * Design (B200-first):
- *   - ONE persistent kernel per generation of primaries.  Every thread owns one live photon whose hot state
- *     (x, k, dk/dlambda, weight, optical depths, opacities at the previous point, RNG counter) stays in
- *     registers for the photon's whole flight; nothing is written back per step.
- *   - push_photon's recursive halving is flattened: one loop iteration = one push attempt for every lane, so
- *     lanes that are re-taking a halved sub-step and lanes starting a new step execute the same code.
- *   - photons waiting to be tracked (this generation's primaries, written by the birth kernel, and scattered
- *     children, appended by the transport kernel itself) live in a monotone multi-producer/multi-consumer
- *     queue in HBM (field-major SoA, coalesced warp-aggregated pops and pushes).  Cold per-photon data
- *     (emission-point diagnostics, e, l, n_scatt) is never carried in registers: it stays in the photon's
- *     queue slot and is read back at record / scatter time.
- *   - spectrum bins and counters are accumulated with atomics (RED.F64) aggregated per warp by bin.
- *   - scattering-bias statistics are frozen per generation (GmBiasStats), so results do not depend on the
+ *   - ONE persistent kernel per generation of primaries.  A thread owns one live photon whose hot state
+ *     (x, k, dk/dlambda, weight, optical depths, previous-point opacities, RNG counter) stays in registers
+ *     while it is being stepped; nothing is written back per step.
+ *   - Photons live in a POOL of records in HBM (field-major SoA).  Two monotone multi-producer /
+ *     multi-consumer index queues connect the stages:
+ *         ready queue    photons that can be stepped (primaries from the birth kernel, scattered children,
+ *                        parents coming back from a scattering), with ALL derived start-of-track quantities
+ *                        (dk/dlambda, opacities, bias) already computed by the producer, so that taking a
+ *                        photon is a handful of coalesced loads and never a divergent computation;
+ *         scatter queue  photons that decided to scatter in this step.
+ *   - Stage compaction: the rare, expensive scattering stage (back-up push, tetrad, electron and
+ *     Klein-Nishina rejection sampling, child creation: ~15x a step) is NOT executed inline by the one
+ *     lane that needs it.  The lane parks the photon in its pool record and takes new work; any warp that
+ *     sees >= 32 parked photons processes them with all 32 lanes active, keeping its own live photons in
+ *     registers meanwhile.  (ncu on the inline version: 10.8 of 32 threads active per instruction.)
+ *   - push_photon's recursive halving is flattened: one loop iteration = one push attempt for every lane.
+ *   - Spectrum bins / counters use global atomics (RED.F64) aggregated per warp by bin.
+ *   - Scattering-bias statistics are frozen per generation (GmBiasStats): results do not depend on the
  *     order in which the hardware happens to finish photons.
  */
 #pragma once
@@ -30,44 +36,65 @@
 
 namespace gm {
 
-/* ---- photon queue -------------------------------------------------------------------------------------- */
-enum QField {
-    Q_X0 = 0, Q_X1, Q_X2, Q_X3, Q_K0, Q_K1, Q_K2, Q_K3, Q_W, Q_E, Q_L, Q_X1I, Q_X2I, Q_NE0, Q_TE0, Q_B0, Q_E0,
-    Q_NFIELDS
+/* ---- photon pool ------------------------------------------------------------------------------------------ */
+enum PField {
+    /* hot state */
+    P_X0 = 0, P_X1, P_X2, P_X3, P_K0, P_K1, P_K2, P_K3, P_DK0, P_DK1, P_DK2, P_DK3,
+    P_W, P_E0S, P_TAU_ABS, P_TAU_SCATT,
+    P_ALPHA_SCATT, /* while parked for scattering: dl * frac */
+    P_ALPHA_ABS,   /* while parked for scattering: weight of the child */
+    P_BI,
+    /* cold data: written at birth, read at record / scatter time only */
+    P_E, P_X1I, P_X2I, P_NE0, P_TE0, P_B0, P_E0,
+    P_NFIELDS
 };
 
-struct PhotonQueue {
-    double *f;          /* [Q_NFIELDS][capacity] */
-    uint4 *rng;         /* [capacity] id0 id1 id2 ctr */
-    int *n_scatt;       /* [capacity] */
-    unsigned int *ready; /* [capacity] generation tag once the slot is fully written */
-    unsigned long long *head, *tail, *finished;
-    unsigned long long capacity;
+struct PhotonPool {
+    double *f;       /* [P_NFIELDS][capacity] */
+    uint4 *rng;      /* [capacity] id0 id1 id2 ctr */
+    uint4 *crng;     /* [capacity] identity of the child to be created (while parked for scattering) */
+    int *n_scatt;    /* [capacity] */
+    int *n_step;     /* [capacity] bit 31: fluid n_e > 0 at the previous evaluation */
+    unsigned long long *n_alloc;  /* bump allocator */
+    unsigned long long *finished; /* photons whose life is over */
+    unsigned int capacity;
+};
+
+/* monotone MPMC queue of pool slots; an entry holds slot + 1 once the record is completely written */
+struct SlotQueue {
+    unsigned int *entries;
+    unsigned long long *head, *tail;
+    unsigned int capacity;
 };
 
 /* optional per-slot debug output for the test exports */
 struct DebugOut {
     double *final_state; /* [n][12]: x[4] k[4] w tau_abs tau_scatt e_0_s, or nullptr */
     int *status;         /* [n]: bit0 recorded, bit1 scattered, bit2 absorbed/dropped */
-    unsigned long long n;
+    unsigned int n;
 };
 
 struct Accumulators {
-    double *spectrum;               /* [6][200][13] */
-    unsigned long long *counters;   /* [0] created [1] scattered [2] recorded */
+    double *spectrum;                 /* [6][200][13] */
+    unsigned long long *counters;     /* [0] created [1] scattered [2] recorded */
     unsigned long long *max_tau_bits; /* max_tau_scatt as the bit pattern of a non-negative double */
-    unsigned long long *work;       /* [0] tracked [1] steps [2] attempts [3] interactions [4] scatter events */
-    unsigned int *error;            /* bit0 queue overflow, bit1 ready-flag timeout */
+    unsigned long long *work;         /* [0] tracked [1] steps [2] attempts [3] interactions [4] scatter events */
+    unsigned int *error;              /* bit0 pool/queue overflow, bit1 queue entry timeout */
 };
 
 struct TransportArgs {
     GmParams P;
     GmBiasStats bias;
-    PhotonQueue Q;
+    PhotonPool pool;
+    SlotQueue ready, scatter;
     Accumulators A;
     DebugOut D;
-    unsigned int gen_tag;
+    /* device-global copy of this very struct: out-of-line (cold) stages take it by pointer so that the kernel
+     * parameter itself never has its address taken and stays in the constant bank for the hot loop */
+    const TransportArgs *self;
 };
+
+constexpr int kNeposBit = 1 << 30;
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
     return *reinterpret_cast<const volatile unsigned long long *>(p);
@@ -75,13 +102,86 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
     return *reinterpret_cast<const volatile unsigned int *>(p);
 }
-__device__ __forceinline__ double qload(const PhotonQueue &Q, int field, unsigned int slot) {
-    return __ldcg(Q.f + (size_t)field * Q.capacity + slot);
+__device__ __forceinline__ double pload(const PhotonPool &pool, int field, unsigned int slot) {
+    return __ldcg(pool.f + (size_t)field * pool.capacity + slot);
 }
-__device__ __forceinline__ void qstore(const PhotonQueue &Q, int field, unsigned long long slot, double v) {
-    Q.f[(size_t)field * Q.capacity + slot] = v;
+__device__ __forceinline__ void pstore(const PhotonPool &pool, int field, unsigned int slot, double v) {
+    __stcg(pool.f + (size_t)field * pool.capacity + slot, v);
 }
 
+/* allocate a pool record; returns false (and flags the overflow) when the pool is full */
+__device__ __forceinline__ bool pool_alloc(const TransportArgs &A, unsigned int &slot) {
+    const unsigned long long s = atomicAdd(A.pool.n_alloc, 1ull);
+    if (s >= A.pool.capacity) {
+        atomicOr(A.A.error, 1u);
+        atomicAdd(A.pool.finished, 1ull); /* keep finished == n_alloc reachable */
+        return false;
+    }
+    slot = (unsigned int)s;
+    return true;
+}
+
+/* publish a completely written record on a queue */
+__device__ __forceinline__ void queue_push(const TransportArgs &A, const SlotQueue &q, unsigned int slot) {
+    __threadfence();
+    const unsigned long long pos = atomicAdd(q.tail, 1ull);
+    if (pos >= q.capacity) {
+        atomicOr(A.A.error, 1u);
+        atomicAdd(A.pool.finished, 1ull);
+        return;
+    }
+    *reinterpret_cast<volatile unsigned int *>(q.entries + pos) = slot + 1u;
+}
+
+/* Warp-collective pop: lanes with `want` set receive a slot (returns true) if the queue has one.
+ * `min_batch`: take nothing unless at least that many entries are available. */
+__device__ __forceinline__ bool queue_pop_warp(const TransportArgs &A, const SlotQueue &q, bool want, int min_batch,
+                                               unsigned int &slot) {
+    const unsigned int need = __ballot_sync(0xffffffffu, want);
+    if (!need)
+        return false;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    int n_got = 0;
+    if (lane == 0) {
+        const unsigned long long h = ld_volatile_u64(q.head);
+        unsigned long long t = ld_volatile_u64(q.tail);
+        t = t < q.capacity ? t : q.capacity;
+        if (t > h && t - h >= (unsigned long long)min_batch) {
+            const unsigned long long avail = t - h;
+            const int n_want = __popc(need);
+            n_got = avail < (unsigned long long)n_want ? (int)avail : n_want;
+            if (atomicCAS(q.head, h, h + n_got) == h)
+                base = h;
+            else
+                n_got = 0;
+        }
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    n_got = __shfl_sync(0xffffffffu, n_got, 0);
+    bool got = false;
+    if (want) {
+        const int my = __popc(need & ((1u << lane) - 1u));
+        if (my < n_got) {
+            /* the producer reserved the position before publishing the slot: wait for it */
+            unsigned int v, spins = 0;
+            while ((v = ld_volatile_u32(q.entries + base + my)) == 0u) {
+                if (++spins > (1u << 26)) {
+                    atomicOr(A.A.error, 2u);
+                    break;
+                }
+            }
+            if (v) {
+                slot = v - 1u;
+                got = true;
+            }
+            __threadfence();
+        }
+    }
+    return got;
+}
+
+/* ---- small physics helpers ----------------------------------------------------------------------------------- */
 /* reference stop_criterion, harm_model.cpp:1589-1616 */
 __device__ __forceinline__ bool stop_criterion(const GmParams &P, double x1, double &w, Rng &rng) {
     if (x1 < P.x1_min)
@@ -113,12 +213,35 @@ __device__ __forceinline__ double attenuation(double d_tau, bool use_series) {
     return exp(-d_tau);
 }
 
+/* start-of-track quantities at a position where geometry and fluid are known
+ * (reference track_super_photon :902-915): opacities and bias for wave-vector k and weight w */
+struct TrackInit {
+    double alpha_scatt, alpha_abs, bi;
+    bool ne_pos;
+};
+
+__device__ __forceinline__ TrackInit track_init(const GmParams &P, const GmBiasStats &bias, const double k[4],
+                                                double w, const Fluid &f) {
+    TrackInit t;
+    t.ne_pos = f.n_e > 0.0;
+    if (t.ne_pos) {
+        double nu;
+        opacities(P, k, f, nu, t.alpha_scatt, t.alpha_abs);
+        t.bi = bias_func(P, bias, f.theta_e, w);
+    } else {
+        t.alpha_scatt = 0.0;
+        t.alpha_abs = 0.0;
+        t.bi = 0.0;
+    }
+    return t;
+}
+
 /* reference record_super_photon, harm_model.cpp:1291-1335.  Lanes of the calling (possibly partial) warp
  * that hit the same spectrum bin are combined before the global atomics. */
 __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsigned int slot, double x2, double x3,
                                                     double w, double tau_abs, double tau_scatt) {
     const GmParams &P = A.P;
-    const double e = qload(A.Q, Q_E, slot);
+    const double e = pload(A.pool, P_E, slot);
     bool ok = !(isnan(w) || isnan(e));
     int bin = -1;
     int n_scatt = 0;
@@ -135,24 +258,24 @@ __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsi
         ok = !(ix2 < 0 || ix2 >= kNThBins || i_e < 0 || i_e >= kNEBins);
         if (ok) {
             bin = ix2 * kNEBins + i_e;
-            n_scatt = __ldcg(A.Q.n_scatt + slot);
+            n_scatt = __ldcg(A.pool.n_scatt + slot);
         }
     }
     double v[12];
     if (ok) {
-        const double x1i = qload(A.Q, Q_X1I, slot), x2i = qload(A.Q, Q_X2I, slot);
-        v[0] = w;                               /* dn_dle   */
-        v[1] = w * e;                           /* de_dle   */
-        v[2] = 1.0;                             /* nph      */
-        v[3] = (double)n_scatt;                 /* nscatt   */
-        v[4] = w * x1i;                         /* x1i_av   */
-        v[5] = w * (x2i * x2i);                 /* x2i_sq   */
-        v[6] = w * (x3 * x3);                   /* x3f_sq   */
-        v[7] = w * tau_abs;                     /* tau_abs  */
-        v[8] = w * tau_scatt;                   /* tau_scatt*/
-        v[9] = w * qload(A.Q, Q_NE0, slot);     /* ne_0     */
-        v[10] = w * qload(A.Q, Q_TE0, slot);    /* theta_e_0*/
-        v[11] = w * qload(A.Q, Q_B0, slot);     /* b_0      */
+        const double x1i = pload(A.pool, P_X1I, slot), x2i = pload(A.pool, P_X2I, slot);
+        v[0] = w;                              /* dn_dle    */
+        v[1] = w * e;                          /* de_dle    */
+        v[2] = 1.0;                            /* nph       */
+        v[3] = (double)n_scatt;                /* nscatt    */
+        v[4] = w * x1i;                        /* x1i_av    */
+        v[5] = w * (x2i * x2i);                /* x2i_sq    */
+        v[6] = w * (x3 * x3);                  /* x3f_sq    */
+        v[7] = w * tau_abs;                    /* tau_abs   */
+        v[8] = w * tau_scatt;                  /* tau_scatt */
+        v[9] = w * pload(A.pool, P_NE0, slot);  /* ne_0      */
+        v[10] = w * pload(A.pool, P_TE0, slot); /* theta_e_0 */
+        v[11] = w * pload(A.pool, P_B0, slot);  /* b_0       */
     }
     /* warp-aggregate by bin among the lanes that are here together */
     const unsigned int active = __activemask();
@@ -161,7 +284,6 @@ __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsi
     const int leader = __ffs(peers) - 1;
     unsigned long long cnt_scatt = (unsigned long long)n_scatt;
     if (bin >= 0 && peers != (1u << lane)) {
-        /* serial reduction over the peer set (peer sets are tiny: records are rare events) */
         unsigned int rest = peers & ~(1u << leader);
         while (rest) {
             const int src = __ffs(rest) - 1;
@@ -188,38 +310,6 @@ __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsi
     }
 }
 
-/* append a scattered photon to the queue; returns false on overflow */
-__device__ __forceinline__ bool enqueue_child(const TransportArgs &A, const double x[4], const ScatterChild &ch,
-                                              double w, double b0, unsigned int parent_slot, const Rng &crng) {
-    const PhotonQueue &Q = A.Q;
-    const unsigned long long slot = atomicAdd(Q.tail, 1ull);
-    if (slot >= Q.capacity) {
-        atomicOr(A.A.error, 1u);
-        /* the slot index is beyond the arrays: count it as finished so the kernel still terminates */
-        atomicAdd(Q.finished, 1ull);
-        return false;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        qstore(Q, Q_X0 + i, slot, x[i]);
-        qstore(Q, Q_K0 + i, slot, ch.k[i]);
-    }
-    qstore(Q, Q_W, slot, w);
-    qstore(Q, Q_E, slot, ch.e);
-    qstore(Q, Q_L, slot, ch.l);
-    qstore(Q, Q_X1I, slot, x[1]);
-    qstore(Q, Q_X2I, slot, x[2]);
-    qstore(Q, Q_NE0, slot, qload(Q, Q_NE0, parent_slot));
-    qstore(Q, Q_TE0, slot, qload(Q, Q_TE0, parent_slot));
-    qstore(Q, Q_B0, slot, b0);
-    qstore(Q, Q_E0, slot, qload(Q, Q_E0, parent_slot));
-    Q.rng[slot] = make_uint4(crng.id0, crng.id1, crng.id2, crng.ctr);
-    Q.n_scatt[slot] = __ldcg(Q.n_scatt + parent_slot) + 1;
-    __threadfence();
-    *reinterpret_cast<volatile unsigned int *>(Q.ready + slot) = A.gen_tag;
-    return true;
-}
-
 /* per-lane live photon (registers) */
 struct Live {
     double x[4], k[4], dk[4];
@@ -229,59 +319,40 @@ struct Live {
     Rng rng;
     unsigned int slot;
     int n_step;
-    int pos, level;  /* halving state of the step in progress; pos == 0 && level == 0: at a step start */
-    bool ne_pos;     /* fluid n_e > 0 at the previous evaluation */
+    int pos, level; /* halving state of the step in progress; pos == 0 && level == 0: at a step start */
+    bool ne_pos;    /* fluid n_e > 0 at the previous evaluation */
     int status;
 };
 
-/* start of track_super_photon (reference harm_model.cpp:894-917): validate, initial opacities, dk/dlambda */
-__device__ __forceinline__ bool begin_track(const TransportArgs &A, unsigned int slot, Live &L) {
-    const GmParams &P = A.P;
-    const PhotonQueue &Q = A.Q;
+/* take a photon from its pool record: loads only (the producer computed every derived quantity) */
+__device__ __forceinline__ void live_load(const TransportArgs &A, unsigned int slot, Live &L) {
+    const PhotonPool &pool = A.pool;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        L.x[i] = qload(Q, Q_X0 + i, slot);
-        L.k[i] = qload(Q, Q_K0 + i, slot);
+        L.x[i] = pload(pool, P_X0 + i, slot);
+        L.k[i] = pload(pool, P_K0 + i, slot);
+        L.dk[i] = pload(pool, P_DK0 + i, slot);
     }
-    L.w = qload(Q, Q_W, slot);
-    L.e_0_s = qload(Q, Q_E, slot);
-    const uint4 r = __ldcg(Q.rng + slot);
+    L.w = pload(pool, P_W, slot);
+    L.e_0_s = pload(pool, P_E0S, slot);
+    L.tau_abs = pload(pool, P_TAU_ABS, slot);
+    L.tau_scatt = pload(pool, P_TAU_SCATT, slot);
+    L.alpha_scatt = pload(pool, P_ALPHA_SCATT, slot);
+    L.alpha_abs = pload(pool, P_ALPHA_ABS, slot);
+    L.bi = pload(pool, P_BI, slot);
+    const uint4 r = __ldcg(pool.rng + slot);
     L.rng.id0 = r.x;
     L.rng.id1 = r.y;
     L.rng.id2 = r.z;
     L.rng.ctr = r.w;
+    const int ns = __ldcg(pool.n_step + slot);
+    L.ne_pos = (ns & kNeposBit) != 0;
+    L.n_step = ns & (kNeposBit - 1);
     L.slot = slot;
-    L.tau_abs = 0.0;
-    L.tau_scatt = 0.0;
-    L.n_step = 0;
     L.pos = 0;
     L.level = 0;
-    L.status = 0;
     L.dl = 0.0;
-    bool bad = (L.w == 0.0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
-    if (bad)
-        return false;
-    const GeoPoint q = geo_point(P, L.x[1], L.x[2]);
-    const MetricCov g = metric_cov(P, q);
-    Fluid f;
-    fluid_params(P, L.x[1], L.x[2], g, q, f);
-    L.ne_pos = f.n_e > 0.0;
-    if (L.ne_pos) {
-        double nu;
-        opacities(P, L.k, f, nu, L.alpha_scatt, L.alpha_abs);
-        L.bi = bias_func(P, A.bias, f.theta_e, L.w);
-    } else {
-        L.alpha_scatt = 0.0;
-        L.alpha_abs = 0.0;
-        L.bi = 0.0;
-    }
-    Connection c;
-    connection_eval(P, q, c);
-    geodesic_rhs(c, L.k, L.dk);
-    return true;
+    L.status = 0;
 }
 
 /* work counters kept per thread and flushed once */
@@ -289,11 +360,12 @@ struct Work {
     unsigned int tracked, steps, attempts, interactions, scatters;
 };
 
-/* Interaction with the fluid after an accepted step (reference harm_model.cpp:936-1056), scattering inline.
- * `snap` points at this thread's column of the shared-memory snapshot (stride = blockDim.x).
- * Returns true if the photon is finished (absorbed or dropped). */
-__device__ __forceinline__ bool interact(const TransportArgs &A, Live &L, const double *snap, int snap_stride,
-                                         Work &wk) {
+enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2 };
+
+/* Interaction with the fluid after an accepted step (reference harm_model.cpp:936-1056).
+ * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER). */
+__device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const double *snap, int snap_stride,
+                                               Work &wk) {
     const GmParams &P = A.P;
     ++wk.interactions;
     const GeoPoint q = geo_point(P, L.x[1], L.x[2]);
@@ -330,74 +402,57 @@ __device__ __forceinline__ bool interact(const TransportArgs &A, Live &L, const 
     const double x1r = -log(rng_uniform(P, L.rng));
     const double w_child = L.w / bias;
     if (bias * d_tau_scatt > x1r && w_child > kWeightMin) {
-        /* ---- scattering (reference :985-1039) ---- */
-        Rng crng = rng_child(P, L.rng);
+        /* ---- the photon scatters in this step (reference :985-1005): park it ---- */
+        const Rng crng = rng_child(P, L.rng);
         const double frac = x1r / (bias * d_tau_scatt);
         d_tau_abs *= frac;
         if (d_tau_abs > 100) {
             L.status |= 4;
-            return true; /* absorbed before scattering */
+            return STEP_FINISHED; /* absorbed before scattering */
         }
         d_tau_scatt *= frac;
         L.w *= attenuation(d_tau_abs + d_tau_scatt, d_tau_abs < 1.0e-3);
-        /* back up: re-push the pre-step snapshot by dl * frac */
+        const PhotonPool &pool = A.pool;
+        const unsigned int s = L.slot;
+        /* the scattering stage restarts from the pre-step snapshot and pushes it by dl * frac */
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            L.x[i] = snap[(0 + i) * snap_stride];
-            L.k[i] = snap[(4 + i) * snap_stride];
-            L.dk[i] = snap[(8 + i) * snap_stride];
-        }
-        L.e_0_s = snap[12 * snap_stride];
-        wk.attempts += push_photon_full(P, L.x, L.k, L.dk, L.e_0_s, L.dl * frac);
-        const GeoPoint q2 = geo_point(P, L.x[1], L.x[2]);
-        const MetricCov g2 = metric_cov(P, q2);
-        fluid_params(P, L.x[1], L.x[2], g2, q2, f);
-        L.ne_pos = f.n_e > 0.0;
-        if (L.ne_pos) {
-            ++wk.scatters;
-            L.status |= 2;
-            ScatterChild ch;
-            const bool child_ok = scatter_super_photon(P, L.rng, L.k, L.w, f, g2, ch);
-            if (L.w < 1.0e-100) {
-                L.status |= 4;
-                return true; /* k could not be put back on the light cone (:1018-1021) */
-            }
-            if (child_ok)
-                enqueue_child(A, L.x, ch, w_child, f.b, L.slot, crng);
-            double nu2;
-            opacities(P, L.k, f, nu2, L.alpha_scatt, L.alpha_abs);
-            L.bi = bias_func(P, A.bias, f.theta_e, L.w);
-        } else {
-            /* left the grid while backing up (reference reads uninitialised data here, Appendix A.15) */
-            L.alpha_scatt = 0.0;
-            L.alpha_abs = 0.0;
-            L.bi = 0.0;
-        }
-    } else {
-        if (d_tau_abs > 100) {
-            L.status |= 4;
-            return true; /* absorbed */
-        }
-        const double d_tau = d_tau_abs + d_tau_scatt;
-        L.w *= attenuation(d_tau, d_tau < 1.0e-3);
+        for (int i = 0; i < 12; ++i)
+            pstore(pool, P_X0 + i, s, snap[i * snap_stride]);
+        pstore(pool, P_E0S, s, snap[12 * snap_stride]);
+        pstore(pool, P_W, s, L.w);
+        pstore(pool, P_TAU_ABS, s, L.tau_abs + d_tau_abs);
+        pstore(pool, P_TAU_SCATT, s, L.tau_scatt + d_tau_scatt);
+        pstore(pool, P_ALPHA_SCATT, s, L.dl * frac);
+        pstore(pool, P_ALPHA_ABS, s, w_child);
+        __stcg(pool.rng + s, make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr));
+        __stcg(pool.crng + s, make_uint4(crng.id0, crng.id1, crng.id2, crng.ctr));
+        __stcg(pool.n_step + s, L.n_step);
+        queue_push(A, A.scatter, s);
+        return STEP_SCATTER;
     }
+    if (d_tau_abs > 100) {
+        L.status |= 4;
+        return STEP_FINISHED; /* absorbed */
+    }
+    const double d_tau = d_tau_abs + d_tau_scatt;
+    L.w *= attenuation(d_tau, d_tau < 1.0e-3);
     L.tau_abs += d_tau_abs;
     L.tau_scatt += d_tau_scatt;
-    return false;
+    return STEP_CONTINUE;
 }
 
 /* One iteration of the flattened per-photon loop: (step start bookkeeping) + one push attempt +
- * (step end: stop test, interaction).  Returns true when the photon's life is over; `record` tells whether
- * it escaped through r > r_max (reference :1066-1068). */
-__device__ __forceinline__ bool advance(const TransportArgs &A, Live &L, double *snap, int snap_stride, Work &wk,
-                                        bool &record) {
+ * (step end: stop test, interaction).  `record` tells whether a finished photon escaped through r > r_max
+ * (reference :1066-1068). */
+__device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, double *snap, int snap_stride,
+                                              Work &wk, bool &record) {
     const GmParams &P = A.P;
     record = false;
     if (L.pos == 0 && L.level == 0) {
         /* top of the while loop (:919) */
         if (stop_criterion(P, L.x[1], L.w, L.rng)) {
             record = L.x[1] > P.x1_max;
-            return true;
+            return STEP_FINISHED;
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -428,12 +483,12 @@ __device__ __forceinline__ bool advance(const TransportArgs &A, Live &L, double 
     }
     if (!accept) {
         ++L.level;
-        return false;
+        return STEP_CONTINUE;
     }
     L.pos += 128 >> L.level;
     if (L.pos < 128) {
         L.level = halving_next_level(L.pos);
-        return false;
+        return STEP_CONTINUE;
     }
     /* the step is complete */
     L.pos = 0;
@@ -441,16 +496,124 @@ __device__ __forceinline__ bool advance(const TransportArgs &A, Live &L, double 
     ++wk.steps;
     if (stop_criterion(P, L.x[1], L.w, L.rng)) {
         record = L.x[1] > P.x1_max;
-        return true;
+        return STEP_FINISHED;
     }
     if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos) {
-        if (interact(A, L, snap, snap_stride, wk))
-            return true;
+        const StepResult r = interact(A, L, snap, snap_stride, wk);
+        if (r != STEP_CONTINUE)
+            return r;
     }
     ++L.n_step;
     if (L.n_step > kMaxNStep)
-        return true; /* step cap: not recorded (:1060-1066) */
-    return false;
+        return STEP_FINISHED; /* step cap: not recorded (:1060-1066) */
+    return STEP_CONTINUE;
+}
+
+/* write the start-of-track record of a photon (hot part); cold fields are written by the caller */
+__device__ __forceinline__ void pool_store_hot(const PhotonPool &pool, unsigned int s, const double x[4],
+                                               const double k[4], const double dk[4], double w, double e_0_s,
+                                               double tau_abs, double tau_scatt, const TrackInit &t, const Rng &rng,
+                                               int n_step) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pstore(pool, P_X0 + i, s, x[i]);
+        pstore(pool, P_K0 + i, s, k[i]);
+        pstore(pool, P_DK0 + i, s, dk[i]);
+    }
+    pstore(pool, P_W, s, w);
+    pstore(pool, P_E0S, s, e_0_s);
+    pstore(pool, P_TAU_ABS, s, tau_abs);
+    pstore(pool, P_TAU_SCATT, s, tau_scatt);
+    pstore(pool, P_ALPHA_SCATT, s, t.alpha_scatt);
+    pstore(pool, P_ALPHA_ABS, s, t.alpha_abs);
+    pstore(pool, P_BI, s, t.bi);
+    __stcg(pool.rng + s, make_uint4(rng.id0, rng.id1, rng.id2, rng.ctr));
+    __stcg(pool.n_step + s, n_step | (t.ne_pos ? kNeposBit : 0));
+}
+
+/* The scattering stage for one parked photon (reference harm_model.cpp:1005-1039 + scatter_super_photon).
+ * Called with all lanes of a warp holding a parked photon (or idle).  Returns the number of photons whose
+ * life ended here (0 or 1); the parent and the child that continue are pushed on the ready queue. */
+__device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int slot, unsigned int &n_attempts,
+                                          unsigned int &n_scatters, unsigned int &n_children) {
+    const TransportArgs &A = *Ag;
+    const GmParams &P = A.P;
+    const PhotonPool &pool = A.pool;
+    double x[4], k[4], dk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        x[i] = pload(pool, P_X0 + i, slot);
+        k[i] = pload(pool, P_K0 + i, slot);
+        dk[i] = pload(pool, P_DK0 + i, slot);
+    }
+    double e_0_s = pload(pool, P_E0S, slot);
+    double w = pload(pool, P_W, slot);
+    const double tau_abs = pload(pool, P_TAU_ABS, slot), tau_scatt = pload(pool, P_TAU_SCATT, slot);
+    const double dl_frac = pload(pool, P_ALPHA_SCATT, slot);
+    const double w_child = pload(pool, P_ALPHA_ABS, slot);
+    const uint4 r4 = __ldcg(pool.rng + slot);
+    Rng rng = {r4.x, r4.y, r4.z, r4.w};
+    int n_step = __ldcg(pool.n_step + slot) & (kNeposBit - 1);
+
+    /* back up to the scattering point */
+    n_attempts += push_photon_full(P, x, k, dk, e_0_s, dl_frac);
+    const GeoPoint q = geo_point(P, x[1], x[2]);
+    const MetricCov g = metric_cov(P, q);
+    Fluid f;
+    fluid_params(P, x[1], x[2], g, q, f);
+    TrackInit ti;
+    if (f.n_e > 0.0) {
+        ++n_scatters;
+        ScatterChild ch;
+        const bool child_ok = scatter_super_photon(P, rng, k, w, f, g, ch);
+        if (w < 1.0e-100) {
+            if (A.D.status && slot < A.D.n)
+                A.D.status[slot] = 4 | 2;
+            return 1; /* k could not be put back on the light cone (:1018-1021): dropped */
+        }
+        if (child_ok) {
+            unsigned int cs;
+            if (pool_alloc(A, cs)) {
+                const uint4 c4 = __ldcg(pool.crng + slot);
+                const Rng crng = {c4.x, c4.y, c4.z, c4.w};
+                Connection c;
+                connection_eval(P, q, c);
+                double dkc[4];
+                geodesic_rhs(c, ch.k, dkc);
+                const TrackInit tc = track_init(P, A.bias, ch.k, w_child, f);
+                pool_store_hot(pool, cs, x, ch.k, dkc, w_child, ch.e, 0.0, 0.0, tc, crng, 0);
+                pstore(pool, P_E, cs, ch.e);
+                pstore(pool, P_X1I, cs, x[1]);
+                pstore(pool, P_X2I, cs, x[2]);
+                pstore(pool, P_NE0, cs, pload(pool, P_NE0, slot));
+                pstore(pool, P_TE0, cs, pload(pool, P_TE0, slot));
+                pstore(pool, P_B0, cs, f.b);
+                pstore(pool, P_E0, cs, pload(pool, P_E0, slot));
+                __stcg(pool.n_scatt + cs, __ldcg(pool.n_scatt + slot) + 1);
+                ++n_children;
+                queue_push(A, A.ready, cs);
+            }
+        }
+        ti = track_init(P, A.bias, k, w, f);
+    } else {
+        /* left the grid while backing up (the reference reads uninitialised data here, Appendix A.15) */
+        ti.alpha_scatt = 0.0;
+        ti.alpha_abs = 0.0;
+        ti.bi = 0.0;
+        ti.ne_pos = false;
+    }
+    if (A.D.status && slot < A.D.n)
+        atomicOr(A.D.status + slot, 2);
+    /* end of the loop body (:1054-1063) */
+    ++n_step;
+    if (n_step > kMaxNStep) {
+        if (A.D.status && slot < A.D.n)
+            atomicOr(A.D.status + slot, 4);
+        return 1;
+    }
+    pool_store_hot(pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, ti, rng, n_step);
+    queue_push(A, A.ready, slot);
+    return 0;
 }
 
 } /* namespace gm */
