@@ -24,7 +24,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 HOST = os.path.join(PKG_DIR, "host")
 INCLUDE = os.path.join(ROOT, "include")
-LIB_CUDA = os.path.join(PKG_DIR, "libgrmonty_b200.so")
+LIB_CUDA = os.environ.get("GRMONTY_B200_LIB", os.path.join(PKG_DIR, "libgrmonty_b200.so"))
 LIB_HOST = os.path.join(PKG_DIR, "libgrmonty_b200_host.so")
 CLI = os.path.join(PKG_DIR, "grmonty_b200")
 

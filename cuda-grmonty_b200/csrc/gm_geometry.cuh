@@ -223,7 +223,7 @@ __device__ __forceinline__ double step_size(const GmParams &P, const double x[4]
  * be rejected and halved (the caller applies the depth limit).  Outputs are written to xn/kn/dkn/e1. */
 __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4], const double k[4],
                                              const double dk[4], double dl, double e_0_s, double xn[4],
-                                             double kn[4], double dkn[4], double &e1) {
+                                             double kn[4], double dkn[4], double &e1, GeoPoint &q) {
     const double dl_2 = 0.5 * dl;
     double kh[4], kp[4];
 #pragma unroll
@@ -233,7 +233,7 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
         kp[i] = kh[i] + d;
         xn[i] = x[i] + kh[i] * dl;
     }
-    const GeoPoint q = geo_point(P, xn[1], xn[2]);
+    q = geo_point(P, xn[1], xn[2]);
     Connection c;
     connection_eval(P, q, c);
     double err;
@@ -283,7 +283,8 @@ __device__ __forceinline__ int push_photon_full(const GmParams &P, double x[4], 
             continue;
         }
         double xn[4], kn[4], dkn[4], e1;
-        const bool fail = push_attempt(P, x, k, dk, ldexp(dl, -level), e_0_s, xn, kn, dkn, e1);
+        GeoPoint q;
+        const bool fail = push_attempt(P, x, k, dk, ldexp(dl, -level), e_0_s, xn, kn, dkn, e1, q);
         ++attempts;
         if (fail && level < kMaxHalvings) {
             ++level;

@@ -223,64 +223,120 @@ __device__ __noinline__ void record_call(const TransportArgs *Ag, unsigned int s
 
 template <int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const TransportArgs A) {
+    /* Control words shared by the block.  The warps of a block run the loop in lockstep (one barrier per
+     * iteration): they then execute the same code region at the same time, which matters because the loop body
+     * (~60 KB of SASS) does not fit the instruction cache -- with free-running warps ncu showed 72% of all
+     * stall cycles as "no instruction". */
+    __shared__ unsigned long long s_base; /* first scatter-queue position claimed for the block */
+    __shared__ int s_count;               /* number of scatter-queue entries claimed (0: no service) */
+    __shared__ int s_quit;
     const int lane = threadIdx.x & 31;
     double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
     Live L;
     bool has = false;
+    long long ticket = -1; /* position in the ready queue this lane is entitled to (monotone queue, no wrap) */
     Work wk = {0u, 0u, 0u, 0u, 0u};
-    unsigned int idle_spins = 0, iter = 0;
+    unsigned int iter = 0, idle_spins = 0;
+    bool was_idle = true;
 
     for (;;) {
         int n_done = 0;
-        const bool idle_warp = __ballot_sync(0xffffffffu, has) == 0u;
-        /* ---- scattering stage: any warp serves a full batch of parked photons (or, when it has nothing
-         *      else to do, whatever is parked), keeping its own live photons in registers ---- */
-        if (idle_warp || (iter & 3u) == 0u) {
-            unsigned int sslot = 0;
-            const bool got = queue_pop_warp(A, A.scatter, true, idle_warp ? 1 : 32, sslot);
-            if (got)
-                n_done += scatter_stage(A.self, sslot, wk.attempts, wk.scatters, wk.tracked);
+        /* ---- block control (one thread): claim parked photons for the scattering stage ---- */
+        if (threadIdx.x == 0) {
+            int cnt = 0;
+            if (was_idle || (iter & 3u) == 0u) {
+                const unsigned long long h = ld_volatile_u64(A.scatter.head);
+                unsigned long long t = ld_volatile_u64(A.scatter.tail);
+                t = t < A.scatter.capacity ? t : A.scatter.capacity;
+                const unsigned long long avail = t > h ? t - h : 0ull;
+                /* a full block-load of parked photons, or -- when the block has nothing else to do -- any */
+                if (avail >= (unsigned long long)BLOCK || (was_idle && avail > 0)) {
+                    cnt = avail < (unsigned long long)BLOCK ? (int)avail : BLOCK;
+                    if (atomicCAS(A.scatter.head, h, h + cnt) == h)
+                        s_base = h;
+                    else
+                        cnt = 0;
+                }
+            }
+            s_count = cnt;
         }
-        /* ---- refill empty lanes from the ready queue: loads only ---- */
+        __syncthreads();
+        /* ---- scattering stage, all lanes of the block that got a parked photon ---- */
         {
-            unsigned int slot = 0;
-            if (queue_pop_warp(A, A.ready, !has, 1, slot)) {
-                live_load(A, slot, L);
-                bool bad = (L.w == 0.0);
+            const int cnt = s_count;
+            if ((int)threadIdx.x < cnt) {
+                const unsigned long long pos = s_base + threadIdx.x;
+                unsigned int v, spins = 0;
+                while ((v = ld_volatile_u32(A.scatter.entries + pos)) == 0u) {
+                    if (++spins > (1u << 26)) {
+                        atomicOr(A.A.error, 2u);
+                        break;
+                    }
+                }
+                __threadfence();
+                if (v)
+                    n_done += scatter_stage(A.self, v - 1u, wk.attempts, wk.scatters, wk.tracked);
+            }
+        }
+        /* ---- refill empty lanes from the ready queue: a ticket per empty lane (one atomicAdd per warp,
+         *      never fails), then loads only ---- */
+        {
+            const bool want = !has && ticket < 0;
+            const unsigned int need = __ballot_sync(0xffffffffu, want);
+            if (need) {
+                unsigned long long base = 0;
+                if (lane == 0)
+                    base = atomicAdd(A.ready.head, (unsigned long long)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (want)
+                    ticket = (long long)(base + __popc(need & ((1u << lane) - 1u)));
+            }
+            if (!has && ticket >= 0 && ticket < (long long)A.ready.capacity) {
+                const unsigned int v = ld_volatile_u32(A.ready.entries + ticket);
+                if (v) {
+                    __threadfence();
+                    const unsigned int slot = v - 1u;
+                    ticket = -1;
+                    live_load(A, slot, L);
+                    bool bad = (L.w == 0.0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
-                if (bad) {
-                    ++n_done; /* invalid photon (reference :895-900): dropped */
-                    if (A.D.status && slot < A.D.n)
-                        atomicOr(A.D.status + slot, 4);
-                } else {
-                    has = true;
+                    for (int i = 0; i < 4; ++i)
+                        bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
+                    if (bad) {
+                        ++n_done; /* invalid photon (reference :895-900): dropped */
+                        if (A.D.status && slot < A.D.n)
+                            atomicOr(A.D.status + slot, 4);
+                    } else {
+                        has = true;
+                    }
                 }
             }
         }
-        /* ---- nothing to do in this warp? ---- */
-        if (__ballot_sync(0xffffffffu, has) == 0u) {
+        /* ---- nothing to do in this block? ---- */
+        const int block_live = __syncthreads_or(has ? 1 : 0);
+        if (!block_live) {
             int s = n_done;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
                 s += __shfl_xor_sync(0xffffffffu, s, o);
-            int quit = 0;
-            if (lane == 0) {
-                if (s)
-                    atomicAdd(A.pool.finished, (unsigned long long)s);
+            if (lane == 0 && s)
+                atomicAdd(A.pool.finished, (unsigned long long)s);
+            __syncthreads(); /* all warps' finished counts are in before thread 0 looks */
+            if (threadIdx.x == 0) {
                 const unsigned long long fin = ld_volatile_u64(A.pool.finished);
                 __threadfence();
                 const unsigned long long na = ld_volatile_u64(A.pool.n_alloc);
-                quit = (fin >= na) || (ld_volatile_u32(A.A.error) & 2u);
+                s_quit = (fin >= na) || (ld_volatile_u32(A.A.error) & 2u);
             }
-            quit = __shfl_sync(0xffffffffu, quit, 0);
-            if (quit)
+            __syncthreads();
+            if (s_quit)
                 break;
-            if (++idle_spins > 4)
-                __nanosleep(512);
+            was_idle = true;
+            if (++idle_spins > 2)
+                __nanosleep(1000);
             continue;
         }
+        was_idle = false;
         idle_spins = 0;
         ++iter;
         /* ---- one flattened iteration for every live lane ---- */

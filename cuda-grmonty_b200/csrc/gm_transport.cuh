@@ -183,6 +183,32 @@ __device__ __forceinline__ bool queue_pop_warp(const TransportArgs &A, const Slo
 
 /* ---- small physics helpers ----------------------------------------------------------------------------------- */
 /* reference stop_criterion, harm_model.cpp:1589-1616 */
+__device__ __noinline__ bool stop_criterion_roulette(const GmParams *Pg, double x1, double &w, Rng &rng) {
+    /* cold part of stop_criterion: Russian roulette for light photons (draws from the photon's stream) */
+    const GmParams &P = *Pg;
+    if (x1 > P.x1_max) {
+        if (rng_uniform(P, rng) <= 1.0 / kRoulette)
+            w *= kRoulette;
+        else
+            w = 0.0;
+        return true;
+    }
+    if (rng_uniform(P, rng) <= 1.0 / kRoulette) {
+        w *= kRoulette;
+        return false;
+    }
+    w = 0.0;
+    return true;
+}
+
+__device__ __forceinline__ bool stop_criterion_fast(const TransportArgs &A, double x1, double &w, Rng &rng) {
+    if (x1 < A.P.x1_min)
+        return true;
+    if (w < kWeightMin)
+        return stop_criterion_roulette(&A.self->P, x1, w, rng);
+    return x1 > A.P.x1_max;
+}
+
 __device__ __forceinline__ bool stop_criterion(const GmParams &P, double x1, double &w, Rng &rng) {
     if (x1 < P.x1_min)
         return true;
@@ -364,11 +390,11 @@ enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2 };
 
 /* Interaction with the fluid after an accepted step (reference harm_model.cpp:936-1056).
  * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER). */
-__device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const double *snap, int snap_stride,
-                                               Work &wk) {
+__device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const GeoPoint &q,
+                                               const double *snap, int snap_stride, Work &wk) {
     const GmParams &P = A.P;
     ++wk.interactions;
-    const GeoPoint q = geo_point(P, L.x[1], L.x[2]);
+    /* q = geometry at the new position, already evaluated by the accepted push attempt */
     const MetricCov g = metric_cov(P, q);
     Fluid f;
     fluid_params(P, L.x[1], L.x[2], g, q, f);
@@ -450,7 +476,7 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, d
     record = false;
     if (L.pos == 0 && L.level == 0) {
         /* top of the while loop (:919) */
-        if (stop_criterion(P, L.x[1], L.w, L.rng)) {
+        if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) {
             record = L.x[1] > P.x1_max;
             return STEP_FINISHED;
         }
@@ -464,11 +490,13 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, d
         L.dl = step_size(P, L.x, L.k);
     }
     bool accept;
+    GeoPoint q;
     if (L.x[1] < P.x_start1) {
         accept = true; /* push_photon is a silent no-op below the grid's inner edge (:1218-1220) */
+        q = geo_point(P, L.x[1], L.x[2]);
     } else {
         double xn[4], kn[4], dkn[4], e1;
-        const bool fail = push_attempt(P, L.x, L.k, L.dk, ldexp(L.dl, -L.level), L.e_0_s, xn, kn, dkn, e1);
+        const bool fail = push_attempt(P, L.x, L.k, L.dk, ldexp(L.dl, -L.level), L.e_0_s, xn, kn, dkn, e1, q);
         ++wk.attempts;
         accept = !(fail && L.level < kMaxHalvings);
         if (accept) {
@@ -494,12 +522,12 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, d
     L.pos = 0;
     L.level = 0;
     ++wk.steps;
-    if (stop_criterion(P, L.x[1], L.w, L.rng)) {
+    if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) {
         record = L.x[1] > P.x1_max;
         return STEP_FINISHED;
     }
     if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos) {
-        const StepResult r = interact(A, L, snap, snap_stride, wk);
+        const StepResult r = interact(A, L, q, snap, snap_stride, wk);
         if (r != STEP_CONTINUE)
             return r;
     }
