@@ -98,7 +98,7 @@ class Config(C.Structure):
         ("seed", C.c_uint64),
         ("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32),
         ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
-        ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64),
+        ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64), ("gen_budget", C.c_int64),
     ]
 
 
@@ -174,7 +174,7 @@ class Context:
 
     def __init__(self, model: dict, seed: int = 123, rank: int = 0, world: int = 1, device: int = 0,
                  threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
-                 gen_cap: int = 0):
+                 gen_cap: int = 0, gen_budget: int = 0):
         self.L = lib()
         cfg = Config()
         cfg.abi_version = 1
@@ -196,7 +196,7 @@ class Context:
             setattr(cfg, k, _ptr(a))
         cfg.seed, cfg.rank, cfg.world, cfg.device = seed, rank, world, device
         cfg.threads_per_block, cfg.blocks_per_sm = threads_per_block, blocks_per_sm
-        cfg.queue_capacity, cfg.gen0, cfg.gen_cap = queue_capacity, gen0, gen_cap
+        cfg.queue_capacity, cfg.gen0, cfg.gen_cap, cfg.gen_budget = queue_capacity, gen0, gen_cap, gen_budget
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -37,8 +38,12 @@ struct grmonty_b200_ctx {
     double *d_nz = nullptr;
     PhotonPool pool{};
     SlotQueue ready{}, scatter{};
-    unsigned long long *d_qctr = nullptr; /* n_alloc, finished, ready head/tail, scatter head/tail */
-    unsigned long long used_ready = 0, used_scatter = 0; /* queue entries to clear before the next batch */
+    SlotQueue carry{};
+    PhotonPool stage{}; /* staging pool: suspended photons between two batches */
+    unsigned long long n_carry = 0; /* records in `stage` waiting for the next batch */
+    int budget = 256;               /* attempts a lineage may make per generation */
+    unsigned long long *d_qctr = nullptr; /* n_alloc, finished, ready head/tail, scatter head/tail, carry head/tail */
+    unsigned long long used_ready = 0, used_scatter = 0, used_carry = 0; /* entries to clear before the next batch */
     Accumulators A{};
     double *d_spectrum = nullptr;
     unsigned long long *d_counters = nullptr, *d_maxtau = nullptr, *d_work = nullptr;
@@ -268,26 +273,39 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 24);
         if (cap > 0x3fffffffull)
             cap = 0x3fffffffull; /* slots are addressed with 32 bits */
-        ctx->pool.capacity = (unsigned int)cap;
-        CK(cudaMalloc(&ctx->pool.f, (size_t)P_NFIELDS * cap * sizeof(double)));
-        CK(cudaMalloc(&ctx->pool.rng, cap * sizeof(uint4)));
-        CK(cudaMalloc(&ctx->pool.crng, cap * sizeof(uint4)));
-        CK(cudaMalloc(&ctx->pool.n_scatt, cap * sizeof(int)));
-        CK(cudaMalloc(&ctx->pool.n_step, cap * sizeof(int)));
+        auto alloc_pool = [&](PhotonPool &pl, unsigned long long c) -> cudaError_t {
+            pl.capacity = (unsigned int)c;
+            cudaError_t e;
+            if ((e = cudaMalloc(&pl.f, (size_t)P_NFIELDS * c * sizeof(double))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&pl.rng, c * sizeof(uint4))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&pl.crng, c * sizeof(uint4))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&pl.n_scatt, c * sizeof(int))) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&pl.n_step, c * sizeof(int))) != cudaSuccess) return e;
+            return cudaMalloc(&pl.gclock, c * sizeof(int));
+        };
+        CK(alloc_pool(ctx->pool, cap));
+        CK(alloc_pool(ctx->stage, std::max<unsigned long long>(1024, cap / 2)));
         ctx->ready.capacity = (unsigned int)std::min<unsigned long long>(2 * cap, 0x7fffffffull);
         ctx->scatter.capacity = (unsigned int)cap;
+        ctx->carry.capacity = ctx->stage.capacity;
         CK(cudaMalloc(&ctx->ready.entries, (size_t)ctx->ready.capacity * sizeof(unsigned int)));
         CK(cudaMalloc(&ctx->scatter.entries, (size_t)ctx->scatter.capacity * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->carry.entries, (size_t)ctx->carry.capacity * sizeof(unsigned int)));
         CK(cudaMemset(ctx->ready.entries, 0, (size_t)ctx->ready.capacity * sizeof(unsigned int)));
         CK(cudaMemset(ctx->scatter.entries, 0, (size_t)ctx->scatter.capacity * sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->d_qctr, 6 * sizeof(unsigned long long)));
-        CK(cudaMemset(ctx->d_qctr, 0, 6 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->carry.entries, 0, (size_t)ctx->carry.capacity * sizeof(unsigned int)));
+        CK(cudaMalloc(&ctx->d_qctr, 8 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->d_qctr, 0, 8 * sizeof(unsigned long long)));
         ctx->pool.n_alloc = ctx->d_qctr;
         ctx->pool.finished = ctx->d_qctr + 1;
         ctx->ready.head = ctx->d_qctr + 2;
         ctx->ready.tail = ctx->d_qctr + 3;
         ctx->scatter.head = ctx->d_qctr + 4;
         ctx->scatter.tail = ctx->d_qctr + 5;
+        ctx->carry.head = ctx->d_qctr + 6;
+        ctx->carry.tail = ctx->d_qctr + 7;
+        if (cfg->gen_budget > 0)
+            ctx->budget = (int)std::min<long long>(cfg->gen_budget, INT_MAX);
 
         /* ---- accumulators ---- */
         const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
@@ -304,8 +322,8 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         ctx->A.error = ctx->d_error;
 
         /* ---- launch geometry ---- */
-        ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 128;
-        int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 2;
+        ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;
+        int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 1;
         const Variant *v = find_variant(ctx->threads, want_bps);
         if (!v)
             return fail(ctx, GRMONTY_B200_EINVAL, "no compiled kernel variant for %d threads x %d blocks/SM",
@@ -371,12 +389,15 @@ static long long generation_size(long long g, long long gen0, long long cap) {
     return std::min(s, cap);
 }
 
-static void fill_args(grmonty_b200_ctx *ctx, const GmBiasStats &bias, const DebugOut &dbg, TransportArgs &args) {
+static void fill_args(grmonty_b200_ctx *ctx, const GmBiasStats &bias, const DebugOut &dbg, int budget,
+                      TransportArgs &args) {
     args.P = ctx->P;
     args.bias = bias;
     args.pool = ctx->pool;
     args.ready = ctx->ready;
     args.scatter = ctx->scatter;
+    args.carry = ctx->carry;
+    args.budget = budget;
     args.A = ctx->A;
     args.D = dbg;
     args.self = ctx->d_args;
@@ -388,43 +409,59 @@ static int begin_batch(grmonty_b200_ctx *ctx, long long count) {
         CK(cudaMemsetAsync(ctx->ready.entries, 0, ctx->used_ready * sizeof(unsigned int), ctx->stream));
     if (ctx->used_scatter)
         CK(cudaMemsetAsync(ctx->scatter.entries, 0, ctx->used_scatter * sizeof(unsigned int), ctx->stream));
-    ctx->used_ready = ctx->used_scatter = 0;
-    const unsigned long long qc[6] = {(unsigned long long)count, 0ull, 0ull, (unsigned long long)count, 0ull, 0ull};
+    if (ctx->used_carry)
+        CK(cudaMemsetAsync(ctx->carry.entries, 0, ctx->used_carry * sizeof(unsigned int), ctx->stream));
+    ctx->used_ready = ctx->used_scatter = ctx->used_carry = 0;
+    const unsigned long long qc[8] = {(unsigned long long)count, 0ull, 0ull, (unsigned long long)count, 0ull, 0ull,
+                                      0ull, 0ull};
     CK(cudaMemcpyAsync(ctx->d_qctr, qc, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); /* qc is a stack buffer */
     return GRMONTY_B200_OK;
 }
 
-/* run one batch of positions (first, first+stride, ... count of them) with frozen bias statistics;
- * preloaded: records 0..count-1 and their ready entries were already written (test export) */
+/* Run one batch with frozen bias statistics: `count` new primaries at positions first, first+stride, ...
+ * plus the photons carried over from the previous batch (ctx->n_carry records in the staging pool).
+ * preloaded: records 0..count-1 and their ready entries were already written (test export).
+ * budget: attempts a lineage may make in this batch before it is suspended and carried over. */
 static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, long long count,
-                     const GmBiasStats &bias, const DebugOut &dbg, bool preloaded) {
-    const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 2);
+                     const GmBiasStats &bias, const DebugOut &dbg, bool preloaded, int budget) {
+    const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
     TransportArgs args;
-    fill_args(ctx, bias, dbg, args);
+    fill_args(ctx, bias, dbg, budget, args);
     CK(cudaMemcpy(ctx->d_args, &args, sizeof(args), cudaMemcpyHostToDevice));
     float ms = 0.f;
+    const long long n_carry = preloaded ? 0 : (long long)ctx->n_carry;
+    const long long n_start = count + n_carry;
     if (!preloaded) {
-        int rc = begin_batch(ctx, count);
+        int rc = begin_batch(ctx, n_start);
         if (rc)
             return rc;
-        const int bb = 128;
-        const long long want = (count + bb - 1) / bb;
-        const int nb = (int)std::min<long long>(want, (long long)ctx->sm_count * 16);
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        birth_kernel<<<nb, bb, 0, ctx->stream>>>(args, ctx->d_zones, ctx->d_prefix, first, stride, count,
-                                                 ctx->perm_mult, ctx->total);
-        CK(cudaGetLastError());
+        if (count > 0) {
+            const int bb = 128;
+            const long long want = (count + bb - 1) / bb;
+            const int nb = (int)std::min<long long>(want, (long long)ctx->sm_count * 16);
+            birth_kernel<<<nb, bb, 0, ctx->stream>>>(args, ctx->d_zones, ctx->d_prefix, first, stride, count,
+                                                     ctx->perm_mult, ctx->total);
+            CK(cudaGetLastError());
+            ctx->stats.n_kernel_launches += 1;
+        }
+        if (n_carry > 0) {
+            carry_copy_kernel<<<(unsigned)((n_carry + 127) / 128), 128, 0, ctx->stream>>>(
+                ctx->pool, (unsigned int)count, ctx->stage, 0u, nullptr, (unsigned int)n_carry, ctx->ready.entries);
+            CK(cudaGetLastError());
+            ctx->stats.n_kernel_launches += 1;
+            ctx->n_carry = 0;
+        }
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         CK(cudaEventSynchronize(ctx->ev1));
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->stats.kernel_ms += ms;
-        ctx->stats.n_kernel_launches += 1;
     }
     const size_t smem = (size_t)13 * ctx->threads * sizeof(double);
     /* do not launch far more threads than there are photons to start with (tiny generations / test batches) */
     long long blocks = std::min<long long>(ctx->grid_blocks,
-                                           std::max<long long>(1, (count * 2 + ctx->threads - 1) / ctx->threads));
+                                           std::max<long long>(1, (n_start * 2 + ctx->threads - 1) / ctx->threads));
     blocks = std::max<long long>(blocks, std::min<long long>(ctx->grid_blocks, ctx->sm_count));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     v->fn<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
@@ -436,12 +473,13 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     ctx->stats.transport_ms += ms;
     ctx->stats.n_kernel_launches += 1;
     unsigned int err = 0;
-    unsigned long long qc[6];
+    unsigned long long qc[8];
     CK(cudaMemcpyAsync(&err, ctx->d_error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(qc, ctx->d_qctr, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->used_ready = std::min<unsigned long long>(qc[3], ctx->ready.capacity);
     ctx->used_scatter = std::min<unsigned long long>(qc[5], ctx->scatter.capacity);
+    ctx->used_carry = std::min<unsigned long long>(qc[7], ctx->carry.capacity);
     ctx->stats.queue_high_water = std::max<uint64_t>(ctx->stats.queue_high_water, qc[0]);
     /* photons tracked = records created: primaries here, scattered children counted on the device */
     unsigned long long w0;
@@ -450,11 +488,23 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     CK(cudaMemcpy(ctx->d_work, &w0, sizeof(w0), cudaMemcpyHostToDevice));
     if (err & 1u)
         return fail(ctx, GRMONTY_B200_EQUEUE,
-                    "device photon pool/queue overflow: %llu records, %llu ready, %llu scatter entries needed "
-                    "(capacity %u); raise queue_capacity or lower gen_cap",
-                    qc[0], qc[3], qc[5], ctx->pool.capacity);
+                    "device photon pool/queue overflow: %llu records, %llu ready, %llu scatter, %llu carry entries "
+                    "needed (capacity %u); raise queue_capacity or lower gen_cap",
+                    qc[0], qc[3], qc[5], qc[7], ctx->pool.capacity);
     if (err & 2u)
         return fail(ctx, GRMONTY_B200_ECUDA, "device photon queue: entry publication timeout");
+    /* stash the suspended photons for the next batch */
+    if (qc[7] > 0) {
+        if (qc[7] > ctx->stage.capacity)
+            return fail(ctx, GRMONTY_B200_EQUEUE, "carry-over staging pool overflow: %llu records (capacity %u)", qc[7],
+                        ctx->stage.capacity);
+        carry_copy_kernel<<<(unsigned)((qc[7] + 127) / 128), 128, 0, ctx->stream>>>(
+            ctx->stage, 0u, ctx->pool, 0u, ctx->carry.entries, (unsigned int)qc[7], nullptr);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.n_kernel_launches += 1;
+        ctx->n_carry = qc[7];
+    }
     return GRMONTY_B200_OK;
 }
 
@@ -481,34 +531,45 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
         first = 0;
     const long long world = ctx->cfg.world, rank = ctx->cfg.rank;
     const DebugOut nodbg = {nullptr, nullptr, 0};
-    /* a batch never fills more than a quarter of the queue with primaries: the rest is room for children */
+    /* a batch never fills more than a quarter of the pool with primaries: the rest is room for carried
+     * photons and scattered children */
     const long long chunk_cap = std::max<long long>(1024, (long long)(ctx->pool.capacity / 4));
     long long g_start = 0;
     unsigned long long created = 0;
+    GmBiasStats bias;
     for (long long g = 0; g_start < last; ++g) {
         const long long g_end = g_start + generation_size(g, ctx->gen0, ctx->gen_cap);
         const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
         if (lo < hi) {
             long long f0 = lo + ((rank - lo % world) % world + world) % world; /* first index >= lo, = rank mod world */
             long long count = f0 < hi ? (hi - f0 + world - 1) / world : 0;
-            if (count > 0) {
-                GmBiasStats bias;
+            if (count > 0 || ctx->n_carry > 0) {
                 int rc = read_bias_stats(ctx, &bias);
                 if (rc)
                     return rc;
-                while (count > 0) {
+                do {
                     const long long n = std::min(count, chunk_cap);
-                    rc = run_batch(ctx, f0, world, n, bias, nodbg, false);
+                    rc = run_batch(ctx, f0, world, n, bias, nodbg, false, ctx->budget);
                     if (rc)
                         return rc;
                     created += (unsigned long long)n;
                     f0 += n * world;
                     count -= n;
-                }
+                } while (count > 0);
                 ++ctx->stats.n_generations;
             }
         }
         g_start = g_end;
+    }
+    /* drain: photons still suspended after the last generation run to completion (no budget) */
+    while (ctx->n_carry > 0) {
+        int rc = read_bias_stats(ctx, &bias);
+        if (rc)
+            return rc;
+        rc = run_batch(ctx, 0, 1, 0, bias, nodbg, false, INT_MAX);
+        if (rc)
+            return rc;
+        ++ctx->stats.n_generations;
     }
     /* counters[0] = created (host-side count; the reference counts primaries only, harm_model.cpp:395) */
     unsigned long long c0;
@@ -615,8 +676,9 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *bufs[] = {ctx->d_grid,  ctx->d_det,    ctx->d_hotcross, ctx->d_f,        ctx->d_k2,      ctx->d_weight,
                     ctx->d_nint,  ctx->d_dnmax,  ctx->d_zones,    ctx->d_num,      ctx->d_prefix,  ctx->d_nz,
-                    ctx->pool.f,  ctx->pool.rng, ctx->pool.crng,  ctx->pool.n_scatt, ctx->pool.n_step, ctx->ready.entries,
-                    ctx->scatter.entries, ctx->d_qctr, ctx->d_spectrum,
+                    ctx->pool.f,  ctx->pool.rng, ctx->pool.crng,  ctx->pool.n_scatt, ctx->pool.n_step, ctx->pool.gclock,
+                    ctx->stage.f, ctx->stage.rng, ctx->stage.crng, ctx->stage.n_scatt, ctx->stage.n_step, ctx->stage.gclock,
+                    ctx->ready.entries, ctx->scatter.entries, ctx->carry.entries, ctx->d_qctr, ctx->d_spectrum,
                     ctx->d_counters, ctx->d_maxtau, ctx->d_work,  ctx->d_error, ctx->d_args};
     for (void *b : bufs)
         if (b)

@@ -198,6 +198,7 @@ __device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigne
     pstore(A.pool, P_B0, slot, b_0);
     pstore(A.pool, P_E0, slot, e_0);
     __stcg(A.pool.n_scatt + slot, n_scatt);
+    __stcg(A.pool.gclock + slot, 0);
 }
 
 /* positions first, first + stride, ... (count of them) -> pool slots / ready-queue entries 0..count-1 */
@@ -211,6 +212,24 @@ __global__ void birth_kernel(TransportArgs A, const ZoneData *zones, const long 
                          B.rng);
         A.ready.entries[t] = (unsigned int)t + 1u;
     }
+}
+
+/* copy carried records between pools: dst slot (dst0 + i) <- src slot (list ? list[i] - 1 : src0 + i);
+ * when `ready` is given the destination slots are also published on that queue at position dst0 + i */
+__global__ void carry_copy_kernel(PhotonPool dst, unsigned int dst0, PhotonPool src, unsigned int src0,
+                                  const unsigned int *list, unsigned int n, unsigned int *ready_entries) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const unsigned int s = list ? list[i] - 1u : src0 + i, d = dst0 + i;
+    for (int f = 0; f < P_NFIELDS; ++f)
+        dst.f[(size_t)f * dst.capacity + d] = src.f[(size_t)f * src.capacity + s];
+    dst.rng[d] = src.rng[s];
+    dst.n_scatt[d] = src.n_scatt[s];
+    dst.n_step[d] = src.n_step[s];
+    dst.gclock[d] = 0;
+    if (ready_entries)
+        ready_entries[d] = d + 1u;
 }
 
 /* ---- the persistent transport kernel ------------------------------------------------------------------- */
@@ -366,6 +385,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                 ++n_done;
             } else if (r == STEP_SCATTER) {
                 has = false; /* parked for the scattering stage */
+            } else if (r == STEP_SUSPEND) {
+                suspend_photon(A.self, L.slot, L.x, L.k, L.dk, L.w, L.e_0_s, L.tau_abs, L.tau_scatt, L.alpha_scatt,
+                               L.alpha_abs, L.bi, L.ne_pos, L.rng, L.n_step);
+                has = false;
+                ++n_done; /* done as far as this generation is concerned */
             }
         }
         if (__ballot_sync(0xffffffffu, n_done != 0)) {

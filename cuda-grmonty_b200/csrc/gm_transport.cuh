@@ -54,7 +54,8 @@ struct PhotonPool {
     uint4 *rng;      /* [capacity] id0 id1 id2 ctr */
     uint4 *crng;     /* [capacity] identity of the child to be created (while parked for scattering) */
     int *n_scatt;    /* [capacity] */
-    int *n_step;     /* [capacity] bit 31: fluid n_e > 0 at the previous evaluation */
+    int *n_step;     /* [capacity] bit 30: fluid n_e > 0 at the previous evaluation */
+    int *gclock;     /* [capacity] push attempts made by the photon's lineage in the current generation */
     unsigned long long *n_alloc;  /* bump allocator */
     unsigned long long *finished; /* photons whose life is over */
     unsigned int capacity;
@@ -87,6 +88,8 @@ struct TransportArgs {
     GmBiasStats bias;
     PhotonPool pool;
     SlotQueue ready, scatter;
+    SlotQueue carry; /* photons suspended at their attempt budget: they continue in the next generation */
+    int budget;      /* attempts a lineage may make per generation ("generation clock") */
     Accumulators A;
     DebugOut D;
     /* device-global copy of this very struct: out-of-line (cold) stages take it by pointer so that the kernel
@@ -345,6 +348,7 @@ struct Live {
     Rng rng;
     unsigned int slot;
     int n_step;
+    int clock; /* generation clock, see PhotonPool::gclock */
     int pos, level; /* halving state of the step in progress; pos == 0 && level == 0: at a step start */
     bool ne_pos;    /* fluid n_e > 0 at the previous evaluation */
     int status;
@@ -374,6 +378,7 @@ __device__ __forceinline__ void live_load(const TransportArgs &A, unsigned int s
     const int ns = __ldcg(pool.n_step + slot);
     L.ne_pos = (ns & kNeposBit) != 0;
     L.n_step = ns & (kNeposBit - 1);
+    L.clock = __ldcg(pool.gclock + slot);
     L.slot = slot;
     L.pos = 0;
     L.level = 0;
@@ -386,7 +391,7 @@ struct Work {
     unsigned int tracked, steps, attempts, interactions, scatters;
 };
 
-enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2 };
+enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_SUSPEND = 3 };
 
 /* Interaction with the fluid after an accepted step (reference harm_model.cpp:936-1056).
  * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER). */
@@ -453,6 +458,7 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         __stcg(pool.rng + s, make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr));
         __stcg(pool.crng + s, make_uint4(crng.id0, crng.id1, crng.id2, crng.ctr));
         __stcg(pool.n_step + s, L.n_step);
+        __stcg(pool.gclock + s, L.clock);
         queue_push(A, A.scatter, s);
         return STEP_SCATTER;
     }
@@ -475,6 +481,10 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, d
     const GmParams &P = A.P;
     record = false;
     if (L.pos == 0 && L.level == 0) {
+        /* out of attempts for this generation: continue in the next one.  Checked BEFORE the stop test so
+         * that the test (and its roulette draw) runs exactly once per loop iteration, on resumption. */
+        if (L.clock >= A.budget)
+            return STEP_SUSPEND;
         /* top of the while loop (:919) */
         if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) {
             record = L.x[1] > P.x1_max;
@@ -498,6 +508,7 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, d
         double xn[4], kn[4], dkn[4], e1;
         const bool fail = push_attempt(P, L.x, L.k, L.dk, ldexp(L.dl, -L.level), L.e_0_s, xn, kn, dkn, e1, q);
         ++wk.attempts;
+        ++L.clock;
         accept = !(fail && L.level < kMaxHalvings);
         if (accept) {
 #pragma unroll
@@ -559,6 +570,23 @@ __device__ __forceinline__ void pool_store_hot(const PhotonPool &pool, unsigned 
     __stcg(pool.n_step + s, n_step | (t.ne_pos ? kNeposBit : 0));
 }
 
+/* Suspend a live photon at a step boundary: its complete hot state goes back to its pool record and the record
+ * is put on the carry queue; the host moves carried records into the next generation's batch. */
+__device__ __noinline__ void suspend_photon(const TransportArgs *Ag, unsigned int slot, const double *x,
+                                            const double *k, const double *dk, double w, double e_0_s,
+                                            double tau_abs, double tau_scatt, double alpha_scatt, double alpha_abs,
+                                            double bi, bool ne_pos, Rng rng, int n_step) {
+    const TransportArgs &A = *Ag;
+    TrackInit t;
+    t.alpha_scatt = alpha_scatt;
+    t.alpha_abs = alpha_abs;
+    t.bi = bi;
+    t.ne_pos = ne_pos;
+    pool_store_hot(A.pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, t, rng, n_step);
+    __stcg(A.pool.gclock + slot, 0);
+    queue_push(A, A.carry, slot);
+}
+
 /* The scattering stage for one parked photon (reference harm_model.cpp:1005-1039 + scatter_super_photon).
  * Called with all lanes of a warp holding a parked photon (or idle).  Returns the number of photons whose
  * life ended here (0 or 1); the parent and the child that continue are pushed on the ready queue. */
@@ -582,9 +610,14 @@ __device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int 
     const uint4 r4 = __ldcg(pool.rng + slot);
     Rng rng = {r4.x, r4.y, r4.z, r4.w};
     int n_step = __ldcg(pool.n_step + slot) & (kNeposBit - 1);
+    int clock = __ldcg(pool.gclock + slot);
 
     /* back up to the scattering point */
-    n_attempts += push_photon_full(P, x, k, dk, e_0_s, dl_frac);
+    {
+        const int att = push_photon_full(P, x, k, dk, e_0_s, dl_frac);
+        n_attempts += att;
+        clock += att;
+    }
     const GeoPoint q = geo_point(P, x[1], x[2]);
     const MetricCov g = metric_cov(P, q);
     Fluid f;
@@ -618,6 +651,7 @@ __device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int 
                 pstore(pool, P_B0, cs, f.b);
                 pstore(pool, P_E0, cs, pload(pool, P_E0, slot));
                 __stcg(pool.n_scatt + cs, __ldcg(pool.n_scatt + slot) + 1);
+                __stcg(pool.gclock + cs, clock); /* the child inherits its lineage's clock */
                 ++n_children;
                 queue_push(A, A.ready, cs);
             }
@@ -640,6 +674,7 @@ __device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int 
         return 1;
     }
     pool_store_hot(pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, ti, rng, n_step);
+    __stcg(pool.gclock + slot, clock);
     queue_push(A, A.ready, slot);
     return 0;
 }

@@ -1,0 +1,731 @@
+/*
+ * harm_model.cpp -- host side of the B200 path (see harm_model.hpp).
+ *
+ * Reference behaviour restated (cuda_grmonty/): units harm_model.cpp:64-79,139-141; dump format :81-232;
+ * init_geometry :242-266; init_weight_table :268-306; init_nint_table :308-338; hot cross-section table
+ * hotcross.cpp:60-79,108-179; emissivity tables jnu_mixed.cpp:57-73,127-148; report_spectrum
+ * harm_model.cpp:416-471.  The transport itself is NOT here: run_simulation() calls the CUDA library through
+ * include/grmonty_b200.h.
+ */
+#include "harm_model.hpp"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <charconv>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <format>
+#include <fstream>
+#include <numbers>
+#include <stdexcept>
+#include <thread>
+
+#include "../../include/grmonty_b200.h"
+#include "../csrc/gm_params.h" /* constants only (same values as the reference's consts.hpp) */
+
+namespace harm {
+
+using std::numbers::pi;
+
+/* ---- logging (spdlog is not part of this build; same information, plain stderr) ------------------------- */
+static int g_verbosity = 2;
+void set_verbosity(int level) { g_verbosity = level; }
+void log_info(const char *fmt, ...) {
+    if (g_verbosity > 2)
+        return;
+    va_list ap;
+    va_start(ap, fmt);
+    std::fputs("[info] ", stderr);
+    std::vfprintf(stderr, fmt, ap);
+    std::fputc('\n', stderr);
+    va_end(ap);
+}
+
+static unsigned hw_threads(int requested) {
+    if (requested > 0)
+        return (unsigned)requested;
+    const unsigned n = std::thread::hardware_concurrency();
+    return n ? n : 1;
+}
+
+template <typename F> static void parallel_for(int n, unsigned nthreads, F &&body) {
+    nthreads = std::max(1u, std::min<unsigned>(nthreads, (unsigned)n));
+    if (nthreads == 1) {
+        for (int i = 0; i < n; ++i)
+            body(i);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] {
+            for (int i = (int)t; i < n; i += (int)nthreads)
+                body(i);
+        });
+    for (auto &th : pool)
+        th.join();
+}
+
+/* ---- construction / units (reference harm_model.cpp:64-79) --------------------------------------------- */
+HARMModel::HARMModel(int photon_n, double mass_unit) : photon_n_(photon_n) {
+    units_.mass_unit = mass_unit;
+    units_.l_unit = gm::kGNewt * gm::kMBH / (gm::kCL * gm::kCL);
+    units_.t_unit = units_.l_unit / gm::kCL;
+    units_.rho_unit = units_.mass_unit / std::pow(units_.l_unit, 3);
+    units_.u_unit = units_.rho_unit * gm::kCL * gm::kCL;
+    units_.b_unit = gm::kCL * std::sqrt(4.0 * pi * units_.rho_unit);
+    units_.n_e_unit = units_.rho_unit / (gm::kMP + gm::kME);
+    max_tau_scatt_ = 6.0 * units_.l_unit * units_.rho_unit * 0.4;
+    d_tau_k_ = 2.0 * pi * units_.l_unit / (gm::kME * gm::kCL * gm::kCL / gm::kHBAR);
+    spectrum_.assign((size_t)kNThBins * kNEBins * kSpecFields, 0.0);
+}
+
+/* ---- dump loader ------------------------------------------------------------------------------------------ */
+namespace {
+struct Tokenizer {
+    const char *p, *end;
+    bool next(double &v) {
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\r'))
+            ++p;
+        if (p >= end || *p == '\n')
+            return false;
+        if (*p == '+')
+            ++p;
+        auto [q, ec] = std::from_chars(p, end, v);
+        if (ec != std::errc()) {
+            /* tolerate tokens from_chars rejects (e.g. "nan"): skip to the next blank */
+            v = std::nan("");
+            while (p < end && *p != ' ' && *p != '\t' && *p != '\n')
+                ++p;
+            return true;
+        }
+        p = q;
+        return true;
+    }
+    void end_line() {
+        while (p < end && *p != '\n')
+            ++p;
+        if (p < end)
+            ++p;
+    }
+};
+} /* namespace */
+
+void HARMModel::read_file(std::string filepath) {
+    log_info("Reading file %s", filepath.c_str());
+    if (!std::filesystem::exists(filepath))
+        throw std::runtime_error("File does not exist " + filepath);
+    std::ifstream in(filepath, std::ios::binary | std::ios::ate);
+    if (!in.is_open())
+        throw std::runtime_error("Cannot open file " + filepath);
+    const std::streamsize size = in.tellg();
+    in.seekg(0);
+    std::string buf((size_t)size, '\0');
+    in.read(buf.data(), size);
+    Tokenizer tk{buf.data(), buf.data() + buf.size()};
+
+    /* header: 26 fields (reference :99-137) */
+    double h[26] = {0};
+    for (int i = 0; i < 26; ++i)
+        if (!tk.next(h[i]))
+            break;
+    tk.end_line();
+    Header &H = header_;
+    H.t = h[0];
+    H.n[0] = (int)h[1];
+    H.n[1] = (int)h[2];
+    H.x_start[0] = 0.0;
+    H.x_start[1] = h[3];
+    H.x_start[2] = h[4];
+    H.x_start[3] = 0.0;
+    H.dx[0] = 1.0;
+    H.dx[1] = h[5];
+    H.dx[2] = h[6];
+    H.dx[3] = 2.0 * pi;
+    H.x_stop[0] = 1.0;
+    H.x_stop[1] = H.x_start[1] + H.n[0] * H.dx[1];
+    H.x_stop[2] = H.x_start[2] + H.n[1] * H.dx[2];
+    H.x_stop[3] = 2.0 * pi;
+    H.t_final = h[7];
+    H.n_step = (int)h[8];
+    H.a = h[9];
+    H.gamma = h[10];
+    H.courant = h[11];
+    H.dt_dump = h[12];
+    H.dt_log = h[13];
+    H.dt_img = h[14];
+    H.dt_rdump = (int)h[15];
+    H.cnt_dump = (int)h[16];
+    H.cnt_img = (int)h[17];
+    H.cnt_rdump = (int)h[18];
+    H.dt = h[19];
+    H.lim = (int)h[20];
+    H.failed = (int)h[21];
+    H.r_in = h[22];
+    H.r_out = h[23];
+    H.h_slope = h[24];
+    H.r_0 = h[25];
+    if (H.n[0] < 1 || H.n[1] < 1)
+        throw std::runtime_error("Bad HARM dump header in " + filepath);
+
+    /* reference :139-141 */
+    const double two_temp_gamma = 0.5 * ((1. + 2. / 3. * (gm::kTpOverTe + 1.) / (gm::kTpOverTe + 2.)) + H.gamma);
+    units_.theta_e_unit = (two_temp_gamma - 1.) * (gm::kMP / gm::kME) / (1. + gm::kTpOverTe);
+
+    const size_t nz = (size_t)H.n[0] * H.n[1];
+    std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
+                                     &data_.u_3,   &data_.b_1, &data_.b_2, &data_.b_3};
+    for (auto *g : grids)
+        g->assign(nz, 0.0);
+    const double d_v = H.dx[1] * H.dx[2] * H.dx[3];
+    double v = 0.0;
+    bias_norm_ = 0.0;
+    /* data: 34 columns per zone, i outer / j inner (reference :175-215); used: 4..11 primitives, 33 gdet */
+    for (size_t z = 0; z < nz; ++z) {
+        double c[34] = {0};
+        for (int k = 0; k < 34; ++k)
+            if (!tk.next(c[k]))
+                break;
+        tk.end_line();
+        for (int k = 0; k < 8; ++k)
+            (*grids[k])[z] = c[4 + k];
+        const double g_det = c[33];
+        bias_norm_ += d_v * g_det * std::pow(data_.u[z] / data_.k_rho[z] * units_.theta_e_unit, 2.);
+        v += d_v * g_det;
+    }
+    bias_norm_ /= v;
+    rh_ = 1.0 + std::sqrt(1.0 - H.a * H.a);
+    x1_min_ = std::log(rh_);
+    log_info("Reading file done");
+}
+
+/* ---- geometry (reference gcov_func :499-530, gcon_func :473-497, get_bl_coord :1632-1637) --------------- */
+void HARMModel::gcov(const double x[4], double g[4][4]) const {
+    std::memset(g, 0, sizeof(double) * 16);
+    const double a = header_.a, hs = header_.h_slope;
+    const double r = std::exp(x[1]) + header_.r_0;
+    const double th = pi * x[2] + ((1.0 - hs) / 2.0) * std::sin(2.0 * pi * x[2]);
+    const double st = std::fabs(std::sin(th)) + gm::kEps, ct = std::cos(th);
+    const double s2 = st * st, rho2 = r * r + a * a * ct * ct;
+    const double rfac = r - header_.r_0;
+    const double hfac = pi + (1.0 - hs) * pi * std::cos(2.0 * pi * x[2]);
+    g[0][0] = (-1.0 + 2.0 * r / rho2);
+    g[0][1] = (2.0 * r / rho2) * rfac;
+    g[0][3] = (-2.0 * a * r * s2 / rho2);
+    g[1][0] = g[0][1];
+    g[1][1] = (1.0 + 2.0 * r / rho2) * rfac * rfac;
+    g[1][3] = (-a * s2 * (1.0 + 2.0 * r / rho2)) * rfac;
+    g[2][2] = rho2 * hfac * hfac;
+    g[3][0] = g[0][3];
+    g[3][1] = g[1][3];
+    g[3][3] = s2 * (rho2 + a * a * s2 * (1.0 + 2.0 * r / rho2));
+}
+
+void HARMModel::gcon(const double x[4], double g[4][4]) const {
+    std::memset(g, 0, sizeof(double) * 16);
+    const double a = header_.a, hs = header_.h_slope;
+    const double r = std::exp(x[1]) + header_.r_0;
+    const double th = pi * x[2] + ((1.0 - hs) / 2.0) * std::sin(2.0 * pi * x[2]);
+    const double st = std::fabs(std::sin(th)) + gm::kEps, ct = std::cos(th);
+    const double irho2 = 1.0 / (r * r + a * a * ct * ct);
+    const double hfac = pi + (1.0 - hs) * pi * std::cos(2.0 * pi * x[2]);
+    g[0][0] = -1.0 - 2.0 * r * irho2;
+    g[0][1] = 2.0 * irho2;
+    g[1][0] = g[0][1];
+    g[1][1] = irho2 * (r * (r - 2.0) + a * a) / (r * r);
+    g[1][3] = a * irho2 / r;
+    g[2][2] = irho2 / (hfac * hfac);
+    g[3][1] = g[1][3];
+    g[3][3] = irho2 / (st * st);
+}
+
+/* Laplace expansion along the first row, 3x3 minors by cofactors */
+static double det3(const double r0[3], const double r1[3], const double r2[3]) {
+    return r0[0] * (r1[1] * r2[2] - r1[2] * r2[1]) - r0[1] * (r1[0] * r2[2] - r1[2] * r2[0]) +
+           r0[2] * (r1[0] * r2[1] - r1[1] * r2[0]);
+}
+static double det4(const double m[4][4]) {
+    double acc = 0.0, sign = 1.0;
+    for (int c = 0; c < 4; ++c) {
+        double minor[3][3];
+        for (int r = 1; r < 4; ++r) {
+            int cc = 0;
+            for (int k = 0; k < 4; ++k)
+                if (k != c)
+                    minor[r - 1][cc++] = m[r][k];
+        }
+        const double term = m[0][c] * det3(minor[0], minor[1], minor[2]);
+        acc = (c == 0) ? term : acc + sign * term;
+        sign = -sign;
+    }
+    return acc;
+}
+
+void HARMModel::init_geometry() {
+    log_info("Initializing HARM model geometry");
+    const int n0 = header_.n[0], n1 = header_.n[1];
+    det_.assign((size_t)n0 * n1, 0.0);
+    parallel_for(n0, hw_threads(init_threads), [&](int i) {
+        for (int j = 0; j < n1; ++j) {
+            const double x[4] = {header_.x_start[0], header_.x_start[1] + (i + 0.5) * header_.dx[1],
+                                 header_.x_start[2] + (j + 0.5) * header_.dx[2], header_.x_start[3]};
+            double g[4][4];
+            gcov(x, g);
+            det_[(size_t)i * n1 + j] = std::sqrt(std::abs(det4(g)));
+        }
+    });
+    log_info("Initializing HARM model geometry done");
+}
+
+/* ---- hot cross-section table (reference hotcross.cpp:60-79, :108-179) ------------------------------------- */
+static double hc_klein_nishina(double w) {
+    if (w < 1.0e-3)
+        return (1.0 - 2.0 * w);
+    return (3.0 / 4.0) * (2.0 / (w * w) + (1.0 / (2.0 * w) - (1.0 + w) / (w * w * w)) * std::log(1.0 + 2.0 * w) +
+                          (1.0 + w) / ((1.0 + 2.0 * w) * (1.0 + 2.0 * w)));
+}
+
+/* total_compton_cross_num with the (gamma-independent) Bessel factor evaluated once per cell instead of once
+ * per quadrature node -- the reference spends its 33 s start-up in std::cyl_bessel_k */
+static double total_compton_cross_num(double w, double theta_e) {
+    if (std::isnan(w))
+        return 0.0;
+    if (theta_e < gm::kHcMinT && w < gm::kHcMinW)
+        return gm::kSigmaThomson;
+    if (theta_e < gm::kHcMinT)
+        return hc_klein_nishina(w) * gm::kSigmaThomson;
+    const double k2f = (theta_e > 1.0e-2) ? std::cyl_bessel_k(2, 1.0 / theta_e) * std::exp(1.0 / theta_e)
+                                          : std::sqrt(pi * theta_e / 2.0);
+    double cross = 0.0;
+    for (double mu_e = -1.0 + 0.5 * gm::kHcDMuE; mu_e < 1.0; mu_e += gm::kHcDMuE) {
+        for (double gamma_e = 1.0 + 0.5 * theta_e * gm::kHcDGammaE; gamma_e < 1.0 + gm::kHcMaxGamma * theta_e;
+             gamma_e += theta_e * gm::kHcDGammaE) {
+            const double dnd = ((gamma_e * std::sqrt(gamma_e * gamma_e - 1.) / (theta_e * k2f)) *
+                                std::exp(-(gamma_e - 1.) / theta_e));
+            const double f = 0.5 * dnd;
+            const double v = std::sqrt(gamma_e * gamma_e - 1.0) / gamma_e;
+            const double we = w * gamma_e * (1.0 - mu_e * v);
+            const double boostcross = hc_klein_nishina(we) * (1.0 - mu_e * v);
+            cross += theta_e * gm::kHcDMuE * gm::kHcDGammaE * boostcross * f;
+        }
+    }
+    return cross * gm::kSigmaThomson;
+}
+
+void HARMModel::init_hotcross_table() {
+    log_info("Initializing HARM model hotcross");
+    hotcross_.assign((size_t)(kHcNW + 1) * (kHcNT + 1), 0.0);
+    const double l_min_w = std::log10(gm::kHcMinW), l_min_t = std::log10(gm::kHcMinT);
+    const double d_l_w = std::log10(gm::kHcMaxW / gm::kHcMinW) / kHcNW;
+    const double d_l_t = std::log10(gm::kHcMaxT / gm::kHcMinT) / kHcNT;
+    parallel_for(kHcNW + 1, hw_threads(init_threads), [&](int i) {
+        for (int j = 0; j <= kHcNT; ++j) {
+            const double l_w = l_min_w + i * d_l_w, l_t = l_min_t + j * d_l_t;
+            hotcross_[(size_t)i * (kHcNT + 1) + j] =
+                std::log10(total_compton_cross_num(std::pow(10.0, l_w), std::pow(10.0, l_t)));
+        }
+    });
+    log_info("Initializing HARM model hotcross done");
+}
+
+/* ---- emissivity tables (reference jnu_mixed.cpp:57-73, :127-148) ---------------------------------------- */
+/* Gauss-Legendre nodes/weights on [-1,1] by Newton iteration on P_n */
+static void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w) {
+    x.resize(n);
+    w.resize(n);
+    for (int i = 0; i < (n + 1) / 2; ++i) {
+        double z = std::cos(pi * (i + 0.75) / (n + 0.5)), pp = 0.0;
+        for (int it = 0; it < 100; ++it) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 1; j <= n; ++j) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0 * j - 1.0) * z * p2 - (j - 1.0) * p3) / j;
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1.0);
+            const double dz = p1 / pp;
+            z -= dz;
+            if (std::fabs(dz) < 1e-16)
+                break;
+        }
+        x[i] = -z;
+        x[n - 1 - i] = z;
+        w[i] = w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+    }
+}
+
+static double jnu_integrand(double th, double k) {
+    const double sin_th = std::sin(th);
+    const double x = k / sin_th;
+    if (sin_th < 1.0e-150 || x > 2.0e8)
+        return 0.0;
+    return sin_th * sin_th * std::pow(std::sqrt(x) + gm::kJnuCst * std::pow(x, 1.0 / 6.0), 2.0) *
+           std::exp(-std::pow(x, 1.0 / 3.0));
+}
+
+void HARMModel::init_emiss_tables() {
+    log_info("Initializing HARM model emission tables");
+    /* F(K) = 4 pi int_0^{pi/2} jnu_integrand d(theta).  The reference integrates adaptively (Gauss-Kronrod 61,
+     * eps_rel = 1e-6); here: composite 32-point Gauss-Legendre on 64 panels, converged far below 1e-6. */
+    std::vector<double> gx, gw;
+    gauss_legendre(32, gx, gw);
+    const int panels = 64;
+    const double l_min_k = std::log(gm::kJnuMinK), d_l_k = std::log(gm::kJnuMaxK / gm::kJnuMinK) / kNESamp;
+    parallel_for(kNESamp + 1, hw_threads(init_threads), [&](int i) {
+        const double k = std::exp(i * d_l_k + l_min_k);
+        double sum = 0.0;
+        const double hp = (pi / 2.0) / panels;
+        for (int p = 0; p < panels; ++p) {
+            const double a = p * hp, mid = a + 0.5 * hp;
+            double s = 0.0;
+            for (size_t q = 0; q < gx.size(); ++q)
+                s += gw[q] * jnu_integrand(mid + 0.5 * hp * gx[q], k);
+            sum += 0.5 * hp * s;
+        }
+        f_[i] = std::log(4 * pi * sum);
+    });
+    const double l_min_t = std::log(gm::kThetaEMin), d_l_t = std::log(gm::kJnuMaxT / gm::kThetaEMin) / kNESamp;
+    for (int i = 0; i <= kNESamp; ++i) {
+        const double t = std::exp(i * d_l_t + l_min_t);
+        k2_[i] = std::log(std::cyl_bessel_k(2, 1.0 / t));
+    }
+    log_info("Initializing HARM model emission tables done");
+}
+
+/* reference k2_eval jnu_mixed.cpp:102-111, f_eval :113-125 */
+static double interp_exp(const double *tab, double lx, double l_min, double d_l) {
+    double d_i = (lx - l_min) / d_l;
+    int i = (int)d_i;
+    i = std::min(i, kNESamp - 1);
+    d_i -= i;
+    return std::exp((1.0 - d_i) * tab[i] + d_i * tab[i + 1]);
+}
+double HARMModel::k2_eval(double theta_e) const {
+    if (theta_e < gm::kThetaEMin)
+        return 0.0;
+    if (theta_e > gm::kJnuMaxT)
+        return 2.0 * theta_e * theta_e;
+    return interp_exp(k2_.data(), std::log(theta_e), std::log(gm::kThetaEMin),
+                      std::log(gm::kJnuMaxT / gm::kThetaEMin) / kNESamp);
+}
+double HARMModel::f_eval(double theta_e, double b_mag, double nu) const {
+    const double k = gm::kJnuKFac * nu / (b_mag * theta_e * theta_e);
+    if (k > gm::kJnuMaxK)
+        return 0.0;
+    if (k < gm::kJnuMinK) {
+        const double x = std::pow(k, 1.0 / 3.0);
+        return x * (37.67503800178 + 2.240274341836 * x);
+    }
+    return interp_exp(f_.data(), std::log(k), std::log(gm::kJnuMinK), std::log(gm::kJnuMaxK / gm::kJnuMinK) / kNESamp);
+}
+
+/* zone-centre n_e, theta_e, |B| (reference get_fluid_zone :538-593; only what the weight table needs) */
+HARMModel::ZoneFluid HARMModel::fluid_zone(int i, int j) const {
+    const int n1 = header_.n[1];
+    const size_t z = (size_t)i * n1 + j;
+    const double x[4] = {header_.x_start[0], header_.x_start[1] + (i + 0.5) * header_.dx[1],
+                         header_.x_start[2] + (j + 0.5) * header_.dx[2], header_.x_start[3]};
+    double gc[4][4], gn[4][4];
+    gcov(x, gc);
+    gcon(x, gn);
+    const double v_con[4] = {0.0, data_.u_1[z], data_.u_2[z], data_.u_3[z]};
+    const double bp[4] = {0.0, data_.b_1[z], data_.b_2[z], data_.b_3[z]};
+    ZoneFluid f;
+    f.n_e = data_.k_rho[z] * units_.n_e_unit;
+    f.theta_e = (data_.u[z] / f.n_e) * units_.n_e_unit * units_.theta_e_unit;
+    double v_dot_v = 0.0;
+    for (int a = 1; a < 4; ++a)
+        for (int b = 1; b < 4; ++b)
+            v_dot_v += gc[a][b] * v_con[a] * v_con[b];
+    const double v_fac = std::sqrt(-1.0 / gn[0][0] * (1.0 + std::abs(v_dot_v)));
+    double u_con[4], u_cov[4], b_con[4], b_cov[4];
+    u_con[0] = -v_fac * gn[0][0];
+    for (int a = 1; a < 4; ++a)
+        u_con[a] = v_con[a] - v_fac * gn[0][a];
+    for (int a = 0; a < 4; ++a)
+        u_cov[a] = gc[a][0] * u_con[0] + gc[a][1] * u_con[1] + gc[a][2] * u_con[2] + gc[a][3] * u_con[3];
+    double u_dot_b = 0.0;
+    for (int a = 1; a < 4; ++a)
+        u_dot_b += u_cov[a] * bp[a];
+    b_con[0] = u_dot_b;
+    for (int a = 1; a < 4; ++a)
+        b_con[a] = (bp[a] + u_con[a] * u_dot_b) / u_con[0];
+    for (int a = 0; a < 4; ++a)
+        b_cov[a] = gc[a][0] * b_con[0] + gc[a][1] * b_con[1] + gc[a][2] * b_con[2] + gc[a][3] * b_con[3];
+    f.b = std::sqrt(b_con[0] * b_cov[0] + b_con[1] * b_cov[1] + b_con[2] * b_cov[2] + b_con[3] * b_cov[3]) *
+          units_.b_unit;
+    return f;
+}
+
+/* reference init_weight_table :268-306 (zone sums kept in zone order so that the table does not depend on the
+ * number of threads: each thread owns whole frequency columns) */
+void HARMModel::init_weight_table() {
+    log_info("Initializing super photon weight table");
+    const int n0 = header_.n[0], n1 = header_.n[1];
+    const double l_nu_min = std::log(gm::kNuMin);
+    const double d_l_nu = (std::log(gm::kNuMax) - std::log(gm::kNuMin)) / kNESamp;
+    const double s_fac = header_.dx[1] * header_.dx[2] * header_.dx[3] * units_.l_unit * units_.l_unit * units_.l_unit;
+    /* per-zone prefactor and state, computed once */
+    std::vector<double> fac((size_t)n0 * n1, 0.0), te((size_t)n0 * n1, 0.0), bb((size_t)n0 * n1, 0.0);
+    parallel_for(n0, hw_threads(init_threads), [&](int i) {
+        for (int j = 0; j < n1; ++j) {
+            const size_t z = (size_t)i * n1 + j;
+            const ZoneFluid f = fluid_zone(i, j);
+            if (f.n_e == 0.0 || f.theta_e < gm::kThetaEMin)
+                continue;
+            const double k2 = k2_eval(f.theta_e);
+            fac[z] = (gm::kJcst * f.n_e * f.b * f.theta_e * f.theta_e / k2) * s_fac * det_[z];
+            te[z] = f.theta_e;
+            bb[z] = f.b;
+        }
+    });
+    parallel_for(kNESamp + 1, hw_threads(init_threads), [&](int k) {
+        const double nu = std::exp(k * d_l_nu + l_nu_min);
+        double sum = 0.0;
+        for (size_t z = 0; z < fac.size(); ++z)
+            if (te[z] != 0.0)
+                sum += fac[z] * f_eval(te[z], bb[z], nu);
+        weight_[k] = std::log(sum / (gm::kHPL * photon_n_));
+    });
+    log_info("Initializing super photon weight table done");
+}
+
+/* reference init_nint_table :308-338 */
+void HARMModel::init_nint_table() {
+    log_info("Initializing nint table");
+    nint_.assign(kNint + 1, 0.0);
+    dndlnu_max_.assign(kNint + 1, 0.0);
+    const double l_nu_min = std::log(gm::kNuMin);
+    const double d_l_nu = (std::log(gm::kNuMax) - std::log(gm::kNuMin)) / kNESamp;
+    const double l_b_min = std::log(gm::kBthsqMin), d_l_b = std::log(gm::kBthsqMax / gm::kBthsqMin) / kNint;
+    std::array<double, kNESamp> nu_j, ew_j;
+    for (int j = 0; j < kNESamp; ++j) {
+        nu_j[j] = std::exp(j * d_l_nu + l_nu_min);
+        ew_j[j] = std::exp(weight_[j]) + 1.0e-100;
+    }
+    parallel_for(kNint + 1, hw_threads(init_threads), [&](int i) {
+        double nint = 0.0, dndlnu_max = 0.0;
+        const double b_mag = std::exp(i * d_l_b + l_b_min);
+        for (int j = 0; j < kNESamp; ++j) {
+            const double dn = f_eval(1.0, b_mag, nu_j[j]) / ew_j[j];
+            if (dn > dndlnu_max)
+                dndlnu_max = dn;
+            nint += d_l_nu * dn;
+        }
+        nint *= header_.dx[1] * header_.dx[2] * header_.dx[3] * units_.l_unit * units_.l_unit * units_.l_unit *
+                std::numbers::sqrt2 * gm::kEE * gm::kEE * gm::kEE / (27.0 * gm::kME * gm::kCL * gm::kCL) *
+                (1.0 / gm::kHPL);
+        nint_[i] = std::log(nint);
+        dndlnu_max_[i] = std::log(dndlnu_max);
+    });
+    log_info("Initializing nint table done");
+}
+
+void HARMModel::init() {
+    init_geometry();
+    init_hotcross_table();
+    init_emiss_tables();
+    init_weight_table();
+    init_nint_table();
+}
+
+/* ---- run_simulation: the C ABI call sequence (replaces reference harm_model.cpp:345-405) ----------------- */
+namespace {
+struct CudaLib {
+    void *h = nullptr;
+    decltype(&grmonty_b200_create) create = nullptr;
+    decltype(&grmonty_b200_run) run = nullptr;
+    decltype(&grmonty_b200_allreduce) allreduce = nullptr;
+    decltype(&grmonty_b200_result) result = nullptr;
+    decltype(&grmonty_b200_destroy) destroy = nullptr;
+    decltype(&grmonty_b200_last_error) last_error = nullptr;
+};
+
+std::string self_dir() {
+    Dl_info info;
+    if (dladdr((void *)&self_dir, &info) && info.dli_fname)
+        return std::filesystem::path(info.dli_fname).parent_path().string();
+    return ".";
+}
+
+CudaLib load_cuda_lib(const std::string &hint) {
+    std::vector<std::string> candidates;
+    if (!hint.empty())
+        candidates.push_back(hint);
+    if (const char *e = std::getenv("GRMONTY_B200_LIB"))
+        candidates.push_back(e);
+    candidates.push_back(self_dir() + "/libgrmonty_b200.so");
+    candidates.push_back("libgrmonty_b200.so");
+    CudaLib L;
+    std::string tried;
+    for (const auto &c : candidates) {
+        L.h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (L.h)
+            break;
+        tried += "\n  " + c + ": " + dlerror();
+    }
+    if (!L.h)
+        throw std::runtime_error("cannot load the CUDA library libgrmonty_b200.so (there is no CPU fallback):" + tried);
+#define SYM(name)                                                                 \
+    L.name = reinterpret_cast<decltype(L.name)>(dlsym(L.h, "grmonty_b200_" #name)); \
+    if (!L.name)                                                                  \
+        throw std::runtime_error("libgrmonty_b200.so lacks grmonty_b200_" #name);
+    SYM(create) SYM(run) SYM(allreduce) SYM(result) SYM(destroy) SYM(last_error)
+#undef SYM
+    return L;
+}
+} /* namespace */
+
+void HARMModel::run_simulation() {
+    const auto start = std::chrono::steady_clock::now();
+    log_info("Starting main loop");
+    CudaLib L = load_cuda_lib(options.cuda_library);
+
+    grmonty_b200_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = GRMONTY_B200_ABI_VERSION;
+    cfg.struct_size = sizeof(cfg);
+    cfg.n0 = header_.n[0];
+    cfg.n1 = header_.n[1];
+    cfg.x_start1 = header_.x_start[1];
+    cfg.x_start2 = header_.x_start[2];
+    cfg.dx1 = header_.dx[1];
+    cfg.dx2 = header_.dx[2];
+    cfg.dx3 = header_.dx[3];
+    cfg.x_stop1 = header_.x_stop[1];
+    cfg.x_stop2 = header_.x_stop[2];
+    cfg.a = header_.a;
+    cfg.h_slope = header_.h_slope;
+    cfg.r_0 = header_.r_0;
+    cfg.mass_unit = units_.mass_unit;
+    cfg.l_unit = units_.l_unit;
+    cfg.t_unit = units_.t_unit;
+    cfg.rho_unit = units_.rho_unit;
+    cfg.u_unit = units_.u_unit;
+    cfg.b_unit = units_.b_unit;
+    cfg.theta_e_unit = units_.theta_e_unit;
+    cfg.n_e_unit = units_.n_e_unit;
+    cfg.k_rho = data_.k_rho.data();
+    cfg.u = data_.u.data();
+    cfg.u_1 = data_.u_1.data();
+    cfg.u_2 = data_.u_2.data();
+    cfg.u_3 = data_.u_3.data();
+    cfg.b_1 = data_.b_1.data();
+    cfg.b_2 = data_.b_2.data();
+    cfg.b_3 = data_.b_3.data();
+    cfg.geom_det = det_.data();
+    cfg.hotcross = hotcross_.data();
+    cfg.f = f_.data();
+    cfg.k2 = k2_.data();
+    cfg.weight = weight_.data();
+    cfg.nint = nint_.data();
+    cfg.dndlnu_max = dndlnu_max_.data();
+    cfg.photon_n = photon_n_;
+    cfg.bias_norm = bias_norm_;
+    cfg.max_tau_scatt0 = max_tau_scatt_;
+    cfg.seed = options.seed;
+    cfg.rank = options.rank;
+    cfg.world = options.world;
+    cfg.device = options.device;
+    cfg.threads_per_block = options.threads_per_block;
+    cfg.blocks_per_sm = options.blocks_per_sm;
+    cfg.queue_capacity = options.queue_capacity;
+    cfg.gen0 = options.gen0;
+    cfg.gen_cap = options.gen_cap;
+    cfg.gen_budget = options.gen_budget;
+
+    grmonty_b200_ctx *ctx = nullptr;
+    if (L.create(&ctx, &cfg) != 0)
+        throw std::runtime_error(std::string("grmonty_b200_create: ") + L.last_error(nullptr));
+    auto fail = [&](const char *what) {
+        const std::string msg = std::string(what) + ": " + L.last_error(ctx);
+        L.destroy(ctx);
+        throw std::runtime_error(msg);
+    };
+    if (L.run(ctx) != 0)
+        fail("grmonty_b200_run");
+    if (options.world > 1 && options.nccl_comm && L.allreduce(ctx, options.nccl_comm, nullptr) != 0)
+        fail("grmonty_b200_allreduce");
+    uint64_t counts[3];
+    grmonty_b200_stats st;
+    if (L.result(ctx, spectrum_.data(), counts, &stats_.max_tau_scatt, &st) != 0)
+        fail("grmonty_b200_result");
+    L.destroy(ctx);
+
+    stats_.created = counts[0];
+    stats_.scattered = counts[1];
+    stats_.recorded = counts[2];
+    stats_.kernel_ms = st.kernel_ms;
+    stats_.transport_ms = st.transport_ms;
+    stats_.n_tracked = st.n_tracked;
+    stats_.n_steps = st.n_steps;
+    stats_.n_push_attempts = st.n_push_attempts;
+    stats_.n_interactions = st.n_interactions;
+    stats_.n_scatter_events = st.n_scatter_events;
+    stats_.n_generations = st.n_generations;
+    stats_.n_kernel_launches = st.n_kernel_launches;
+    stats_.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    /* same final summary as the reference (harm_model.cpp:409-413) */
+    log_info("Final rate %.2f ph/s", stats_.created / stats_.seconds);
+    log_info("Super photons:");
+    log_info("\tcreated: %llu", (unsigned long long)stats_.created);
+    log_info("\tscattered: %llu", (unsigned long long)stats_.scattered);
+    log_info("\trecorded: %llu", (unsigned long long)stats_.recorded);
+}
+
+/* ---- spectrum file (reference report_spectrum :416-471, d_omega_func :532-536) ---------------------------- */
+double HARMModel::d_omega(double x2i, double x2f) const {
+    const double hs = header_.h_slope;
+    return 2.0 * pi *
+           (-std::cos(pi * x2f + 0.5 * (1.0 - hs) * std::sin(2 * pi * x2f)) +
+            std::cos(pi * x2i + 0.5 * (1.0 - hs) * std::sin(2 * pi * x2i)));
+}
+
+void HARMModel::report_spectrum(std::string filepath) {
+    const double dx2 = (header_.x_stop[2] - header_.x_start[2]) / (2 * kNThBins);
+    log_info("Writing spectrum to file %s", filepath.c_str());
+    std::ofstream out(filepath);
+    if (!out.is_open()) {
+        std::fprintf(stderr, "[error] Cannot open file %s\n", filepath.c_str());
+        return;
+    }
+    enum { DN_DLE = 0, DE_DLE = 1, X1I_AV = 4, X2I_SQ = 5, X3F_SQ = 6, TAU_ABS = 7, TAU_SCATT = 8 };
+    auto S = [&](int j, int i, int f) { return spectrum_[((size_t)j * kNEBins + i) * kSpecFields + f]; };
+    const double l_e_0 = std::log(1.0e-12);
+    double max_tau_scatt = 0.0, l = 0.0;
+    std::string line;
+    for (int i = 0; i < kNEBins; ++i) {
+        line.clear();
+        line += std::format("{:10.5g} ", (i * gm::kSpecDLE + l_e_0) / std::numbers::ln10);
+        for (int j = 0; j < kNThBins; ++j) {
+            const double d_om = 2.0 * d_omega(j * dx2, (j + 1) * dx2);
+            double nu_lnu = (gm::kME * gm::kCL * gm::kCL) * (4.0 * pi / d_om) * (1.0 / gm::kSpecDLE);
+            nu_lnu *= S(j, i, DE_DLE);
+            nu_lnu /= gm::kLSun;
+            const double dn = S(j, i, DN_DLE) + gm::kEps;
+            const double tau_scatt = S(j, i, TAU_SCATT) / dn;
+            line += std::format("{:10.5g} ", nu_lnu);
+            line += std::format("{:10.5g} ", S(j, i, TAU_ABS) / dn);
+            line += std::format("{:10.5g} ", tau_scatt);
+            line += std::format("{:10.5g} ", S(j, i, X1I_AV) / dn);
+            line += std::format("{:10.5g} ", std::sqrt(std::abs(S(j, i, X2I_SQ) / dn)));
+            line += std::format("{:10.5g} ", std::sqrt(std::abs(S(j, i, X3F_SQ) / dn)));
+            if (tau_scatt > max_tau_scatt)
+                max_tau_scatt = tau_scatt;
+            l += nu_lnu * d_om * gm::kSpecDLE;
+        }
+        out << line << '\n';
+    }
+    out.close();
+    luminosity_ = l;
+    max_tau_reported_ = max_tau_scatt;
+    log_info("Writing spectrum done");
+    log_info("\tlumosity: %g", l);
+    log_info("\tmax_tau_scatt: %g", max_tau_scatt);
+}
+
+} /* namespace harm */

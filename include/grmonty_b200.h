@@ -97,6 +97,8 @@ typedef struct grmonty_b200_config {
     int64_t queue_capacity; /* photon slots in the device queue */
     int64_t gen0;           /* positions in the first generation (default 32); doubles each generation ... */
     int64_t gen_cap;        /* ... up to this cap (default 2^22).  Bias statistics are frozen within a generation. */
+    int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over
+                               to the next one (default 256); bounds the tail of every generation */
 } grmonty_b200_config;
 
 /* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */

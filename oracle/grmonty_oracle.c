@@ -11,6 +11,7 @@
 #define _USE_MATH_DEFINES
 #include "grmonty_oracle.h"
 
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1159,45 +1160,85 @@ static void eval_opacities(const orc_model *m, const orc_photon *ph, const orc_f
     *alpha_abs = orc_alpha_inv_abs(m, nu, f->theta_e, f->n_e, f->b, theta);
 }
 
-void orc_track_super_photon(orc_model *m, orc_photon *ph) {
+/* Resumable form of track_super_photon.  The loop variables the reference keeps on the stack
+ * (alpha_scatti, alpha_absi, bi, the n_e > 0 latch, n_step) live in orc_track_state so that a photon can be
+ * SUSPENDED at a step boundary and continued later: the CUDA path bounds the tail of each generation by
+ * letting every photon lineage make at most `budget` push attempts per generation ("generation clock",
+ * DESIGN.md); a suspended photon continues in the next generation, with that generation's frozen bias
+ * statistics.  With budget = INT_MAX this is exactly the reference's control flow. */
+static void carry_push(orc_model *m, const orc_track_state *s) {
+    if (m->n_carry == m->cap_carry) {
+        m->cap_carry = m->cap_carry ? 2 * m->cap_carry : 1024;
+        m->carry = (orc_track_state *)realloc(m->carry, m->cap_carry * sizeof(orc_track_state));
+    }
+    m->carry[m->n_carry] = *s;
+    m->carry[m->n_carry].clock = 0;
+    m->n_carry++;
+}
+
+/* reference :894-917: validation and start-of-track quantities; returns 0 if the photon is invalid */
+static int track_begin(orc_model *m, const orc_photon *ph_in, int clock, orc_track_state *s) {
+    s->ph = *ph_in;
+    orc_photon *ph = &s->ph;
     for (int i = 0; i < 4; ++i) {
         if (isnan(ph->x[i]) || isnan(ph->k[i]))
-            return;
+            return 0;
     }
     if (ph->w == 0.0)
-        return;
+        return 0;
     m->n_tracked++;
-
     double gcov[4][4];
     orc_fluid f;
     orc_gcov(m, ph->x, gcov);
     orc_get_fluid_params(m, ph->x, gcov, &f);
-    double alpha_scatti = 0.0, alpha_absi = 0.0, bi = 0.0, nu = 0.0;
+    s->alpha_scatti = s->alpha_absi = s->bi = 0.0;
+    double nu = 0.0;
     if (f.n_e > 0.0) {
-        eval_opacities(m, ph, &f, &alpha_scatti, &alpha_absi, &nu);
-        bi = orc_bias_func(m, f.theta_e, ph->w);
+        eval_opacities(m, ph, &f, &s->alpha_scatti, &s->alpha_absi, &nu);
+        if (nu < 0.0 || isnan(nu)) /* unphysical wave-vector: the CUDA path defines alpha = 0 here */
+            s->alpha_scatti = s->alpha_absi = 0.0;
+        s->bi = orc_bias_func(m, f.theta_e, ph->w);
     }
     /* (photons are born/scattered inside the grid, so the reference's unguarded evaluation at :907-913
      *  always sees valid fluid data; outside we define alpha = 0.) */
+    s->ne_pos = f.n_e > 0.0;
     orc_init_dkdlam(m, ph->x, ph->k, ph->dkdlam);
-    int n_step = 0;
+    s->n_step = 0;
+    s->clock = clock;
+    return 1;
+}
 
-    while (!orc_stop_criterion(m, ph)) {
+/* reference :919-1068.  Returns 1 if the photon was suspended (it is then on m->carry), else 0. */
+static int track_loop(orc_model *m, orc_track_state *s) {
+    orc_photon *ph = &s->ph;
+    double gcov[4][4];
+    orc_fluid f;
+    double nu = 0.0;
+    for (;;) {
+        if (m->budget > 0 && s->clock >= m->budget) {
+            carry_push(m, s);
+            return 1;
+        }
+        if (orc_stop_criterion(m, ph))
+            break;
         double x2[4], k2[4], dk2[4], e0s2;
         memcpy(x2, ph->x, sizeof(x2));
         memcpy(k2, ph->k, sizeof(k2));
         memcpy(dk2, ph->dkdlam, sizeof(dk2));
         e0s2 = ph->e_0_s;
         double dl = orc_step_size(m, ph->x, ph->k);
+        uint64_t att0 = m->n_push_attempts;
         orc_push_photon(m, ph, dl, 0);
+        s->clock += (int)(m->n_push_attempts - att0);
         m->n_steps++;
         if (orc_stop_criterion(m, ph))
             break;
 
-        if (alpha_absi > 0.0 || alpha_scatti > 0.0 || f.n_e > 0.0) {
+        if (s->alpha_absi > 0.0 || s->alpha_scatti > 0.0 || s->ne_pos) {
             m->n_interactions++;
             orc_gcov(m, ph->x, gcov);
             orc_get_fluid_params(m, ph->x, gcov, &f);
+            s->ne_pos = f.n_e > 0.0;
             int bound_flag = (f.n_e == 0.0);
             double theta = 0.0;
             if (!bound_flag) {
@@ -1206,22 +1247,22 @@ void orc_track_super_photon(orc_model *m, orc_photon *ph) {
             }
             double d_tau_scatt, d_tau_abs, bias;
             if (bound_flag || nu < 0.0) {
-                d_tau_scatt = 0.5 * alpha_scatti * m->d_tau_k * dl;
-                d_tau_abs = 0.5 * alpha_absi * m->d_tau_k * dl;
-                alpha_scatti = 0.0;
-                alpha_absi = 0.0;
+                d_tau_scatt = 0.5 * s->alpha_scatti * m->d_tau_k * dl;
+                d_tau_abs = 0.5 * s->alpha_absi * m->d_tau_k * dl;
+                s->alpha_scatti = 0.0;
+                s->alpha_absi = 0.0;
                 bias = 0.0;
-                bi = 0.0;
+                s->bi = 0.0;
             } else {
                 double alpha_scattf = orc_alpha_inv_scatt(m, nu, f.theta_e, f.n_e);
-                d_tau_scatt = 0.5 * (alpha_scatti + alpha_scattf) * m->d_tau_k * dl;
-                alpha_scatti = alpha_scattf;
+                d_tau_scatt = 0.5 * (s->alpha_scatti + alpha_scattf) * m->d_tau_k * dl;
+                s->alpha_scatti = alpha_scattf;
                 double alpha_absf = orc_alpha_inv_abs(m, nu, f.theta_e, f.n_e, f.b, theta);
-                d_tau_abs = 0.5 * (alpha_absi + alpha_absf) * m->d_tau_k * dl;
-                alpha_absi = alpha_absf;
+                d_tau_abs = 0.5 * (s->alpha_absi + alpha_absf) * m->d_tau_k * dl;
+                s->alpha_absi = alpha_absf;
                 double bf = orc_bias_func(m, f.theta_e, ph->w);
-                bias = 0.5 * (bi + bf);
-                bi = bf;
+                bias = 0.5 * (s->bi + bf);
+                s->bi = bf;
             }
             double x1 = -log(orc_uniform(m, &ph->rng));
             orc_photon php;
@@ -1232,7 +1273,7 @@ void orc_track_super_photon(orc_model *m, orc_photon *ph) {
                 double frac = x1 / (bias * d_tau_scatt);
                 d_tau_abs *= frac;
                 if (d_tau_abs > 100)
-                    return; /* absorbed before scattering */
+                    return 0; /* absorbed before scattering */
                 d_tau_scatt *= frac;
                 double d_tau = d_tau_abs + d_tau_scatt;
                 if (d_tau_abs < 1.0e-3)
@@ -1244,36 +1285,43 @@ void orc_track_super_photon(orc_model *m, orc_photon *ph) {
                 memcpy(ph->k, k2, sizeof(k2));
                 memcpy(ph->dkdlam, dk2, sizeof(dk2));
                 ph->e_0_s = e0s2;
+                att0 = m->n_push_attempts;
                 orc_push_photon(m, ph, dl * frac, 0);
+                s->clock += (int)(m->n_push_attempts - att0);
                 orc_gcov(m, ph->x, gcov);
                 orc_get_fluid_params(m, ph->x, gcov, &f);
+                s->ne_pos = f.n_e > 0.0;
                 if (f.n_e > 0.0) {
                     m->n_scatter_events++;
                     int child_ok = orc_scatter_super_photon(m, ph, &php, &f, gcov);
                     if (ph->w < 1.0e-100)
-                        return;
-                    if (child_ok)
-                        orc_track_super_photon(m, &php);
+                        return 0;
+                    if (child_ok) {
+                        /* the child inherits its lineage's generation clock */
+                        orc_track_state cs;
+                        if (track_begin(m, &php, s->clock, &cs))
+                            track_loop(m, &cs);
+                    }
                     theta = orc_bk_angle(m, ph->k, f.u_cov, f.b_cov, f.b);
                     nu = orc_fluid_nu(ph->k, f.u_cov);
                     if (nu < 0.0) {
-                        alpha_scatti = 0.0;
-                        alpha_absi = 0.0;
+                        s->alpha_scatti = 0.0;
+                        s->alpha_absi = 0.0;
                     } else {
-                        alpha_scatti = orc_alpha_inv_scatt(m, nu, f.theta_e, f.n_e);
-                        alpha_absi = orc_alpha_inv_abs(m, nu, f.theta_e, f.n_e, f.b, theta);
+                        s->alpha_scatti = orc_alpha_inv_scatt(m, nu, f.theta_e, f.n_e);
+                        s->alpha_absi = orc_alpha_inv_abs(m, nu, f.theta_e, f.n_e, f.b, theta);
                     }
-                    bi = orc_bias_func(m, f.theta_e, ph->w);
+                    s->bi = orc_bias_func(m, f.theta_e, ph->w);
                 } else {
                     /* left the grid while backing up: the reference reads uninitialised fluid data here
                      * (Appendix A.15); we define alpha = 0, bias = 0 (the gate then latches off). */
-                    alpha_scatti = 0.0;
-                    alpha_absi = 0.0;
-                    bi = 0.0;
+                    s->alpha_scatti = 0.0;
+                    s->alpha_absi = 0.0;
+                    s->bi = 0.0;
                 }
             } else {
                 if (d_tau_abs > 100)
-                    return; /* absorbed */
+                    return 0; /* absorbed */
                 double d_tau = d_tau_abs + d_tau_scatt;
                 if (d_tau < 1.0e-3)
                     ph->w *= (1. - d_tau / 24. * (24. - d_tau * (12. - d_tau * (4. - d_tau))));
@@ -1283,12 +1331,35 @@ void orc_track_super_photon(orc_model *m, orc_photon *ph) {
             ph->tau_abs += d_tau_abs;
             ph->tau_scatt += d_tau_scatt;
         }
-        ++n_step;
-        if (n_step > C_MAX_N_STEP)
+        ++s->n_step;
+        if (s->n_step > C_MAX_N_STEP)
             break;
     }
-    if (ph->x[1] > c_x1_max() && n_step <= C_MAX_N_STEP)
+    if (ph->x[1] > c_x1_max() && s->n_step <= C_MAX_N_STEP)
         orc_record_super_photon(m, ph);
+    return 0;
+}
+
+/* track one photon (and all its descendants); photons that run out of attempts end up on m->carry */
+void orc_track_super_photon(orc_model *m, orc_photon *ph) {
+    orc_track_state s;
+    if (!track_begin(m, ph, 0, &s))
+        return;
+    track_loop(m, &s);
+    *ph = s.ph;
+}
+
+/* continue the photons suspended so far (they may be suspended again) */
+static void run_carried(orc_model *m) {
+    size_t n = m->n_carry;
+    if (!n)
+        return;
+    orc_track_state *list = (orc_track_state *)malloc(n * sizeof(orc_track_state));
+    memcpy(list, m->carry, n * sizeof(orc_track_state));
+    m->n_carry = 0;
+    for (size_t i = 0; i < n; ++i)
+        track_loop(m, &list[i]);
+    free(list);
 }
 
 /* ============================================================================================
@@ -1373,20 +1444,37 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
     const int64_t mult = orc_perm_multiplier((int64_t)total);
     /* generations partition the global index range [0,total); statistics freeze at generation starts */
     int64_t g_start = 0;
+    const int budget = m->budget > 0 ? m->budget : INT_MAX;
     for (int64_t g = 0; g_start < last; ++g) {
         int64_t g_end = g_start + orc_generation_size(g, gen0, gen_cap);
+        const int64_t lo = g_start > first ? g_start : first, hi = g_end < last ? g_end : last;
+        if (lo < hi) {
+            if (m->stats_mode == ORC_STATS_FROZEN) {
+                m->bias_max_tau_scatt = m->acc_max_tau_scatt;
+                m->bias_n_scatt = (double)m->acc_n_scatt;
+                m->bias_n_recorded = (double)m->acc_n_recorded;
+            }
+            m->budget = budget;
+            run_carried(m); /* photons suspended in the previous generation continue with this one's statistics */
+            for (int64_t j = lo; j < hi; ++j) {
+                if ((j % world) != rank)
+                    continue;
+                orc_run_primary(m, prefix, dn_max, m->zone_order ? j : orc_permute(j, mult, (int64_t)total));
+            }
+        }
+        g_start = g_end;
+    }
+    /* drain: photons still suspended after the last generation run to completion */
+    while (m->n_carry > 0) {
         if (m->stats_mode == ORC_STATS_FROZEN) {
             m->bias_max_tau_scatt = m->acc_max_tau_scatt;
             m->bias_n_scatt = (double)m->acc_n_scatt;
             m->bias_n_recorded = (double)m->acc_n_recorded;
         }
-        for (int64_t j = g_start; j < g_end && j < last; ++j) {
-            if (j < first || (j % world) != rank)
-                continue;
-            orc_run_primary(m, prefix, dn_max, m->zone_order ? j : orc_permute(j, mult, (int64_t)total));
-        }
-        g_start = g_end;
+        m->budget = INT_MAX;
+        run_carried(m);
     }
+    m->budget = budget == INT_MAX ? 0 : budget;
     free(num);
     free(prefix);
     free(dn_max);
@@ -1442,5 +1530,9 @@ void orc_photon_to_flat(const orc_photon *ph, double *p) {
     p[24] = ph->n_scatt;
 }
 orc_model *orc_model_alloc(void) { return (orc_model *)calloc(1, sizeof(orc_model)); }
-void orc_model_free(orc_model *m) { free(m); }
+void orc_model_free(orc_model *m) {
+    if (m)
+        free(m->carry);
+    free(m);
+}
 unsigned long orc_sizeof_model(void) { return (unsigned long)sizeof(orc_model); }

@@ -77,6 +77,11 @@ typedef struct orc_model {
     uint64_t acc_n_recorded;
     int stats_mode; /* ORC_STATS_LIVE: bias_* track acc_* after every record */
     int zone_order; /* 1: process primaries in zone order like the reference; 0: Weyl-permuted order (CUDA path) */
+    /* generation clock (CUDA path's tail bound): push attempts a photon lineage may make per
+     * generation before it is suspended and continued in the next one; <= 0: unlimited (the reference) */
+    int budget;
+    struct orc_track_state *carry; /* suspended photons (owned by the model) */
+    uint64_t n_carry, cap_carry;
     /* outputs */
     double spectrum[ORC_N_TH_BINS][ORC_N_E_BINS][ORC_SPEC_FIELDS]; /* field order of harm_data.hpp:129-143 */
     uint64_t n_created;
@@ -97,6 +102,13 @@ typedef struct orc_photon {
     int n_scatt;
     orc_rng rng;
 } orc_photon;
+
+/* loop state of track_super_photon, so that a photon can be suspended and resumed */
+typedef struct orc_track_state {
+    orc_photon ph;
+    double alpha_scatti, alpha_absi, bi;
+    int ne_pos, n_step, clock;
+} orc_track_state;
 
 typedef struct orc_fluid {
     double n_e, theta_e, b;

@@ -36,6 +36,7 @@ class OrcModel(C.Structure):
         ("bias_max_tau_scatt", C.c_double), ("bias_n_scatt", C.c_double), ("bias_n_recorded", C.c_double),
         ("acc_max_tau_scatt", C.c_double), ("acc_n_scatt", C.c_uint64), ("acc_n_recorded", C.c_uint64),
         ("stats_mode", C.c_int), ("zone_order", C.c_int),
+        ("budget", C.c_int), ("carry", C.c_void_p), ("n_carry", C.c_uint64), ("cap_carry", C.c_uint64),
         ("spectrum", C.c_double * (N_TH * N_E * N_F)),
         ("n_created", C.c_uint64),
         ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64), ("n_interactions", C.c_uint64),
@@ -250,5 +251,6 @@ class Model:
         self.L.orc_track_super_photon(self.ptr, C.byref(ph))
         return self.flat(ph)
 
-    def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22):
+    def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22, budget=256):
+        self.m.budget = budget if self.m.stats_mode == 0 else 0
         self.L.orc_run(self.ptr, first, last, rank, world, gen0, gen_cap)
