@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- superphotons/s of the B200 transport path (BASELINE.json metric), with the reference CPU build
+timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[1], the README benchmark shape -- synthetic dump019-shaped
+HARM dump (192x192, a = 0.9375, tools/make_harm_dump.py), mass_unit = 4e19, photon_n = 1e6 PER GPU (weak
+scaling: the job's photon_n is N x 1e6 and rank r tracks the primaries at positions j = r mod N).
+A "step" is one complete run_simulation: every primary superphoton of the rank's share is generated,
+transported (with all its scattered descendants) and recorded.
+
+    value      whole-job primaries/s with the model resident in HBM (context created once, reset per step)
+    e2e        the same through the HARMModel host API with HOST buffers: create (H2D of grid + tables) +
+               run + result (D2H of the spectrum) + destroy inside the timed region
+    roofline   FP64 pipe: algorithmic flops (650 per vacuum step, 1100 per in-fluid step, 3000 per
+               scattering, 628 per extra push attempt) / CUDA-event time of the transport kernels, against the
+               DFMA peak measured in the same process (MEASURED_PEAKS.json has no FP64 entry)
+    cpu_baseline  the UNMODIFIED reference CPU build (oracle/_ref/grmonty_ref) on all host cores, one
+               single-threaded process per core as in BASELINE.md section 3, on a bounded photon_n
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_VAC, FLOP_FLUID, FLOP_SCAT, FLOP_EXTRA = 650.0, 1100.0, 3000.0, 628.0
+
+
+def dump_path(n0: int, n1: int) -> str:
+    """synthetic dump, generated once per box (deterministic)"""
+    from tools import make_harm_dump
+    p = os.path.join(tempfile.gettempdir(), f"grmonty_b200_dump_{n0}x{n1}.txt")
+    if not os.path.exists(p):
+        header, table = make_harm_dump.make_dump(n0=n0, n1=n1)
+        tmp = p + f".{os.getpid()}.tmp"
+        make_harm_dump.write_dump(tmp, header, table)
+        os.replace(tmp, p)
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, device: int):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference_cpu(dump: str, photon_n: int, mass_unit: float, cores: int, seed0: int = 123) -> dict:
+    """`cores` concurrent single-threaded processes of the reference CPU build; rate = sum primaries / max wall of
+    run_simulation (table init excluded; the hot cross-section table is cached on disk by the harness)."""
+    from oracle import refharness as rh
+    if os.path.exists(rh.CLI_PATH):
+        procs = [subprocess.Popen([rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit",
+                                   repr(mass_unit), "--seed", str(seed0 + i), "--hotcross_cache", rh.HOTCROSS_CACHE],
+                                  stdout=subprocess.PIPE, text=True) for i in range(cores)]
+        outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+        created = sum(o["created"] for o in outs)
+        wall = max(o["run_s"] for o in outs)
+        return {"value": created / wall, "unit": "superphotons/s", "cores": cores, "kind": "reference",
+                "sample": f"{cores} processes x photon_n={photon_n} (reference CPU build, unmodified sources), "
+                          f"{created} primaries in {wall:.1f} s of run_simulation",
+                "recorded": sum(o["recorded"] for o in outs), "scattered": sum(o["scattered"] for o in outs),
+                "created": created, "seconds": wall}
+    # the reference build is not on this box: time the plain-C port instead (oracle/grmonty_oracle.c)
+    import multiprocessing as mp
+    with mp.Pool(cores) as pool:
+        res = pool.map(_oracle_port_run, [(dump, photon_n, mass_unit, seed0 + i) for i in range(cores)])
+    created = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {"value": created / wall, "unit": "superphotons/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} processes x photon_n={photon_n} (plain-C port of the reference algorithm)",
+            "created": created, "seconds": wall}
+
+
+def _oracle_port_run(args):
+    dump, photon_n, mass_unit, seed = args
+    import cuda_grmonty_b200 as gm
+    from oracle import orc
+    gm.build_host()
+    hm = gm.HarmModel(photon_n, mass_unit)
+    hm.read_file(dump)
+    hm.init(1)
+    M = orc.Model(hm.model_dict(), seed=seed, stats_mode=1, zone_order=1)
+    t0 = time.time()
+    M.run(budget=0)
+    return int(M.m.n_created), time.time() - t0
+
+
+def flops_of(stats: dict) -> float:
+    n_fluid = stats["n_interactions"]
+    n_vac = max(0, stats["n_steps"] - n_fluid)
+    n_extra = max(0, stats["n_push_attempts"] - stats["n_steps"] - stats["n_scatter_events"])
+    return (n_vac * FLOP_VAC + n_fluid * FLOP_FLUID + stats["n_scatter_events"] * FLOP_SCAT + n_extra * FLOP_EXTRA)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--photon_n", type=float, default=1.0e6, help="photon_n per GPU")
+    ap.add_argument("--mass_unit", type=float, default=4.0e19)
+    ap.add_argument("--n0", type=int, default=192)
+    ap.add_argument("--n1", type=int, default=192)
+    ap.add_argument("--ref_photon_n", type=int, default=4000, help="photon_n of each reference CPU process")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = (f"synthetic dump019-shaped HARM dump {args.n0}x{args.n1} (a=0.9375), mass_unit={args.mass_unit:g}, "
+                f"photon_n={args.photon_n:g} per GPU")
+    config = {"workload": workload, "photon_n_per_gpu": args.photon_n, "mass_unit": args.mass_unit,
+              "grid": [args.n0, args.n1], "sharding": f"photons x{world}, end-of-run allreduce",
+              "l2": "per-step working set (photon pool, ~250 B x millions of photons) exceeds L2; no flush needed"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dump = dump_path(args.n0, args.n1)
+        cores = os.cpu_count() or 1
+        for _ in range(min(args.warmup, 1)):
+            run_reference_cpu(dump, max(200, args.ref_photon_n // 10), args.mass_unit, cores)
+        t0 = time.time()
+        res = [run_reference_cpu(dump, args.ref_photon_n, args.mass_unit, cores, 123 + 1000 * s)
+               for s in range(args.steps)]
+        wall = time.time() - t0
+        value = sum(r["created"] for r in res) / sum(r["seconds"] for r in res)
+        cb = dict(res[-1])
+        cb["value"] = value
+        print(json.dumps({
+            "impl": "reference", "metric": "superphotons/sec", "value": value, "unit": "superphotons/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "superphotons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import cuda_grmonty_b200 as gm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the transport path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    photon_n_total = int(round(args.photon_n * world))
+
+    # untimed set-up: synthetic dump, host model (loader + tables), device context
+    if rank == 0:
+        dump = dump_path(args.n0, args.n1)
+    if dist:
+        dist.barrier()
+    dump = dump_path(args.n0, args.n1)
+    hm = gm.HarmModel(photon_n_total, args.mass_unit)
+    t0 = time.time()
+    hm.read_file(dump)
+    hm.init()
+    init_s = time.time() - t0
+    model = hm.model_dict()
+    ctx = gm.Context(model, seed=123, rank=rank, world=world, device=dev)
+    fp64_peak = ctx.fp64_peak()
+    sp_ptr, cnt_ptr, mt_ptr = ctx.device_accumulators()
+
+    class DevArr:
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+    if dist:
+        t_spec = torch.as_tensor(DevArr(sp_ptr, 6 * 200 * 13, "<f8"), device=f"cuda:{dev}")
+        t_cnt = torch.as_tensor(DevArr(cnt_ptr, 3, "<i8"), device=f"cuda:{dev}")
+        t_mt = torch.as_tensor(DevArr(mt_ptr, 1, "<i8"), device=f"cuda:{dev}")  # bit pattern of a double >= 0
+
+    def step():
+        ctx.reset()
+        ctx.run()
+        if dist:  # the path's only collective: end-of-run reduction of spectrum, counters and max tau
+            dist.all_reduce(t_spec, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_cnt, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t_mt, op=dist.ReduceOp.MAX)
+        return ctx.result()
+
+    def sync():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(dev) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    kernel_ms = transport_ms = 0.0
+    launches = 0
+    flops = 0.0
+    res = None
+    for _ in range(args.steps):
+        res = step()
+        kernel_ms += res["stats"]["kernel_ms"]
+        transport_ms += res["stats"]["transport_ms"]
+        launches += res["stats"]["n_kernel_launches"]
+        flops += flops_of(res["stats"])
+    ev1.record()
+    sync()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    local = torch.tensor([wall, kernel_ms, transport_ms, flops, float(launches)], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist:
+        mx = local.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = local.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall, kernel_ms, transport_ms = mx[0].item(), mx[1].item(), mx[2].item()
+        flops_all, launches_all = sm[3].item(), int(sm[4].item())
+    else:
+        flops_all, launches_all = flops, launches
+    total = ctx.total_primaries()  # primaries of the whole job (all ranks) per step
+    value = total * args.steps / wall
+
+    # ---- e2e: through the HARMModel host API with host buffers (create + H2D + run + D2H + destroy per step)
+    hm.set_options(seed=123, rank=rank, world=world, device=dev)
+    ctx.close()
+    hm.run_simulation()  # warm-up
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        hm.run_simulation()
+        if dist:
+            spec = torch.from_numpy(hm.spectrum()).to(f"cuda:{dev}")
+            dist.all_reduce(spec, op=dist.ReduceOp.SUM)
+            hm.set_spectrum(spec.cpu().numpy())
+    sync()
+    e2e_wall = time.perf_counter() - t0
+    if dist:
+        tw = torch.tensor([e2e_wall], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e_wall = tw.item()
+    nz = args.n0 * args.n1
+    h2d = 8 * (9 * nz + 221 * 81 + 3 * 201 + 2 * 20001)
+    d2h = 8 * (6 * 200 * 13 + 3 + 1 + 10)
+    e2e = {"value": total * args.steps / e2e_wall, "unit": "superphotons/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
+           "api": "HARMModel.run_simulation (create + run + result + destroy through the C ABI)"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    achieved = flops_all / world / (transport_ms * 1e-3) / 1e12  # per GPU
+    out = {
+        "metric": "superphotons/sec", "value": value, "unit": "superphotons/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_peak, "traffic": None,
+                     "peak_source": "DFMA micro-benchmark in this process (grmonty_b200_fp64_peak); "
+                                    "MEASURED_PEAKS.json has no FP64 entry",
+                     "kernel": "transport_kernel", "kernel_ms_per_step": transport_ms / args.steps},
+        "device_ms_per_step": kernel_ms / args.steps, "init_s": init_s,
+        "run": {"primaries_per_step": total, "recorded": res["recorded"], "scattered": res["scattered"],
+                "max_tau_scatt": res["max_tau_scatt"], **{k: res["stats"][k] for k in
+                ("n_tracked", "n_steps", "n_push_attempts", "n_interactions", "n_scatter_events", "n_generations",
+                 "n_live_iterations", "n_slot_iterations")}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        out["cpu_baseline"] = run_reference_cpu(dump, args.ref_photon_n, args.mass_unit, cores)
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,7 @@ class Stats(C.Structure):
     _fields_ = [("n_tracked", C.c_uint64), ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64),
                 ("n_interactions", C.c_uint64), ("n_scatter_events", C.c_uint64), ("n_generations", C.c_uint64),
                 ("n_kernel_launches", C.c_uint64), ("queue_high_water", C.c_uint64),
+                ("n_live_iterations", C.c_uint64), ("n_slot_iterations", C.c_uint64),
                 ("kernel_ms", C.c_double), ("transport_ms", C.c_double)]
 
     def as_dict(self):
@@ -353,3 +354,126 @@ class Context:
         self._ck(self.L.grmonty_b200_test_philox(self.h, C.c_int64(len(c)), _ptr(c, C.c_uint32),
                                                  _ptr(k, C.c_uint32), _ptr(out, C.c_uint32)))
         return out
+
+
+# ---- host library binding (libgrmonty_b200_host.so): the reference's HARMModel surface -------------------------
+_hlib = None
+
+
+def host_lib():
+    global _hlib
+    if _hlib is None:
+        if not os.path.exists(LIB_HOST):
+            raise GrmontyError(f"{LIB_HOST} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        H = C.CDLL(LIB_HOST)
+        H.gmh_last_error.restype = C.c_char_p
+        H.gmh_create.restype = C.c_void_p
+        H.gmh_create.argtypes = [C.c_int, C.c_double, C.c_int]
+        H.gmh_destroy.argtypes = [C.c_void_p]
+        H.gmh_read_file.argtypes = [C.c_void_p, C.c_char_p]
+        H.gmh_init.argtypes = [C.c_void_p, C.c_int]
+        H.gmh_init_stage.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        H.gmh_set_options.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                      C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_char_p]
+        H.gmh_run_simulation.argtypes = [C.c_void_p]
+        H.gmh_report_spectrum.argtypes = [C.c_void_p, C.c_char_p]
+        for n in ("gmh_get_header", "gmh_get_header_raw", "gmh_get_units", "gmh_get_scalars", "gmh_get_spectrum",
+                  "gmh_set_spectrum", "gmh_get_stats"):
+            getattr(H, n).argtypes = [C.c_void_p, dp]
+        H.gmh_get_grid.argtypes = [C.c_void_p, C.c_int, dp]
+        H.gmh_get_table.argtypes = [C.c_void_p, C.c_int, dp]
+        _hlib = H
+    return _hlib
+
+
+class HarmModel:
+    """Python face of the C++ host object (cuda-grmonty_b200/host/harm_model.hpp), same call order as the
+    reference main: HarmModel(photon_n, mass_unit) -> read_file -> init -> run_simulation -> report_spectrum."""
+
+    STATS = ["created", "scattered", "recorded", "max_tau_scatt", "seconds", "kernel_ms", "transport_ms",
+             "n_tracked", "n_steps", "n_push_attempts", "n_interactions", "n_scatter_events", "n_generations",
+             "n_kernel_launches", "luminosity", "max_tau_scatt_reported"]
+
+    def __init__(self, photon_n: int, mass_unit: float, verbosity: int = 6):
+        self.H = host_lib()
+        self.h = C.c_void_p(self.H.gmh_create(int(photon_n), float(mass_unit), verbosity))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GrmontyError(self.H.gmh_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.H.gmh_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def read_file(self, path: str):
+        self._ck(self.H.gmh_read_file(self.h, path.encode()))
+
+    def init(self, threads: int = 0):
+        self._ck(self.H.gmh_init(self.h, threads))
+
+    def init_stage(self, which: int, threads: int = 0):
+        self._ck(self.H.gmh_init_stage(self.h, which, threads))
+
+    def set_options(self, seed=123, rank=0, world=1, device=0, threads_per_block=0, blocks_per_sm=0,
+                    queue_capacity=0, gen0=0, gen_cap=0, gen_budget=0, nccl_comm=None, cuda_library=None):
+        lib_path = (cuda_library or LIB_CUDA).encode()
+        self.H.gmh_set_options(self.h, seed, rank, world, device, threads_per_block, blocks_per_sm, queue_capacity,
+                               gen0, gen_cap, gen_budget, nccl_comm, lib_path)
+
+    def run_simulation(self):
+        self._ck(self.H.gmh_run_simulation(self.h))
+
+    def report_spectrum(self, path: str):
+        self._ck(self.H.gmh_report_spectrum(self.h, path.encode()))
+
+    def header_raw(self):
+        a = np.zeros(26)
+        self.H.gmh_get_header_raw(self.h, _ptr(a))
+        return a
+
+    def spectrum(self):
+        a = np.zeros((N_TH, N_E, N_F))
+        self.H.gmh_get_spectrum(self.h, _ptr(a))
+        return a
+
+    def set_spectrum(self, spec):
+        a = _arr(spec).reshape(N_TH, N_E, N_F)
+        self.H.gmh_set_spectrum(self.h, _ptr(a))
+
+    def stats(self) -> dict:
+        a = np.zeros(16)
+        self.H.gmh_get_stats(self.h, _ptr(a))
+        return dict(zip(self.STATS, a.tolist()))
+
+    def model_dict(self) -> dict:
+        """Everything grmonty_b200_create needs, as numpy arrays (same keys as tests/golden model files)."""
+        h, u, s = np.zeros(13), np.zeros(8), np.zeros(3)
+        self.H.gmh_get_header(self.h, _ptr(h))
+        self.H.gmh_get_units(self.h, _ptr(u))
+        self.H.gmh_get_scalars(self.h, _ptr(s))
+        n0, n1 = int(h[0]), int(h[1])
+        d = dict(n0=n0, n1=n1, x_start1=h[2], x_start2=h[3], dx1=h[4], dx2=h[5], dx3=h[6], x_stop1=h[7],
+                 x_stop2=h[8], a=h[9], h_slope=h[10], r_0=h[11], gamma=h[12], mass_unit=u[0], l_unit=u[1],
+                 t_unit=u[2], rho_unit=u[3], u_unit=u[4], b_unit=u[5], theta_e_unit=u[6], n_e_unit=u[7],
+                 bias_norm=s[0], max_tau_scatt0=s[1], photon_n=s[2])
+        c_me, c_cl, c_hbar = 9.1093826e-28, 2.99792458e10, 6.6260693e-27 / (2.0 * np.pi)
+        d["d_tau_k"] = 2.0 * np.pi * d["l_unit"] / (c_me * c_cl * c_cl / c_hbar)
+        d["x1_min"] = float(np.log(1.0 + np.sqrt(max(0.0, 1.0 - d["a"] ** 2))))
+        for i, nm in enumerate(["k_rho", "u", "u_1", "u_2", "u_3", "b_1", "b_2", "b_3", "geom_det"]):
+            a = np.zeros((n0, n1))
+            if self.H.gmh_get_grid(self.h, i, _ptr(a)) == 0:
+                d[nm] = a
+        for i, (nm, n) in enumerate([("hotcross", 221 * 81), ("f", 201), ("k2", 201), ("weight", 201),
+                                     ("nint", 20001), ("dndlnu_max", 20001)]):
+            a = np.zeros(n)
+            self.H.gmh_get_table(self.h, i, _ptr(a))
+            d[nm] = a
+        return d

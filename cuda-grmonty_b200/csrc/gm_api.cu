@@ -665,6 +665,8 @@ int grmonty_b200_result(grmonty_b200_ctx *ctx, double *spectrum, uint64_t counts
         ctx->stats.n_push_attempts = w[2];
         ctx->stats.n_interactions = w[3];
         ctx->stats.n_scatter_events = w[4];
+        ctx->stats.n_live_iterations = w[5];
+        ctx->stats.n_slot_iterations = w[6];
         *stats = ctx->stats;
     }
     return GRMONTY_B200_OK;

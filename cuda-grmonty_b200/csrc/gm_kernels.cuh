@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
     Live L;
     bool has = false;
     long long ticket = -1; /* position in the ready queue this lane is entitled to (monotone queue, no wrap) */
-    Work wk = {0u, 0u, 0u, 0u, 0u};
+    Work wk = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
     unsigned int iter = 0, idle_spins = 0;
     bool was_idle = true;
 
@@ -359,7 +359,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
         idle_spins = 0;
         ++iter;
         /* ---- one flattened iteration for every live lane ---- */
+        ++wk.slot_iters;
         if (has) {
+            ++wk.live_iters;
             bool record;
             const StepResult r = advance(A, L, snap, BLOCK, wk, record);
             if (r == STEP_FINISHED) {
@@ -402,9 +404,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
         }
     }
     /* flush work counters: warp-reduce, one atomic per warp and counter */
-    unsigned int c[5] = {wk.tracked, wk.steps, wk.attempts, wk.interactions, wk.scatters};
+    unsigned int c[7] = {wk.tracked, wk.steps, wk.attempts, wk.interactions, wk.scatters, wk.live_iters, wk.slot_iters};
 #pragma unroll
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < 7; ++q) {
         unsigned long long v = c[q];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)

@@ -389,6 +389,7 @@ __device__ __forceinline__ void live_load(const TransportArgs &A, unsigned int s
 /* work counters kept per thread and flushed once */
 struct Work {
     unsigned int tracked, steps, attempts, interactions, scatters;
+    unsigned int live_iters, slot_iters; /* loop iterations with / regardless of a live photon in the lane */
 };
 
 enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_SUSPEND = 3 };

@@ -292,5 +292,35 @@ if __name__ == "__main__":
         gen_samplers()
     elif what == "spectrum":
         gen_spectrum()
+    elif what == "spectrum_file":
+        pass  # handled at the end of the file
     else:
         raise SystemExit(__doc__)
+
+
+def gen_spectrum_file():
+    """fixture for the spectrum-writer test: a Spectrum array and the bytes the reference writes for it"""
+    tmp = tempfile.mkdtemp()
+    dump = os.path.join(tmp, "dump48.txt")
+    small_dump(dump)
+    R = rh.Ref(dump, SMALL["photon_n"], SMALL["mass_unit"], seed=5)
+    R.L.ref_run_simulation()
+    spec = R.spectrum()
+    out = os.path.join(tmp, "spectrum.txt")
+    R.L.ref_report_spectrum(out.encode())
+    text = np.frombuffer(open(out, "rb").read(), dtype=np.uint8)
+    # luminosity as the reference logs it (harm_model.cpp:461)
+    lines = open(out).read().splitlines()
+    d = R.model_dict()
+    dx2 = (d["x_stop2"] - d["x_start2"]) / 12.0
+    lum = 0.0
+    for ln in lines:
+        v = [float(t) for t in ln.split()]
+        for j in range(6):
+            lum += v[1 + 6 * j] * 2.0 * R.L.ref_d_omega(j * dx2, (j + 1) * dx2) * 0.25
+    np.savez_compressed(os.path.join(GOLD, "spectrum_file.npz"), spectrum=spec, text=text, luminosity=np.array(lum))
+    print("wrote spectrum_file.npz", len(text), "bytes, L =", lum, file=sys.stderr)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_file":
+    gen_spectrum_file()

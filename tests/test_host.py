@@ -1,0 +1,157 @@
+"""CPU tests of the C++ host (cuda-grmonty_b200/host): the parts of the reference surface that are kept --
+HARM dump loader, table builders, spectrum file writer, CLI -- and the C-ABI library's exported symbols.
+
+The dump-format test mirrors the reference's own harm_model_test.cpp (ReadFileHeader / ReadFileData) with the
+same 2x3 fixture values (reference tests/harm_model_test.cpp:16-94, writers :224-262).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cuda_grmonty_b200 as gm
+from tools import make_harm_dump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    gm.build_host()
+
+
+def write_fixture(path):
+    """the reference test's sample header/data: header values 1, (2,3), 4, 5, 8, 9, 10 ... 28; data 111..823"""
+    hdr = "1 2 3 4 5 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 23 24 25 26 27 28"
+    lines = [hdr]
+    for i in range(2):
+        for j in range(3):
+            prims = " ".join(str(100 * v + 10 * (i + 1) + (j + 1)) for v in range(1, 9))
+            lines.append("0 0 0 0 " + prims + " 0 " + "0 0 0 0 0 0 0 0 " * 2 + "0 0 0 0 0")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+def test_read_file_header_and_data(tmp_path):
+    p = str(tmp_path / "harm_dump")
+    write_fixture(p)
+    m = gm.HarmModel(1000, 4e19)
+    m.read_file(p)
+    raw = m.header_raw()
+    want = [1, 2, 3, 4, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28]
+    assert np.array_equal(raw, np.array(want, dtype=float))
+    d = m.model_dict()
+    # derived header fields (reference harm_model.cpp:106-117)
+    assert d["x_stop1"] == 4.0 + 2 * 8.0 and d["x_stop2"] == 5.0 + 3 * 9.0 and d["dx3"] == 2.0 * np.pi
+    for v, nm in enumerate(["k_rho", "u", "u_1", "u_2", "u_3", "b_1", "b_2", "b_3"], start=1):
+        want = np.array([[100 * v + 10 * (i + 1) + (j + 1) for j in range(3)] for i in range(2)], dtype=float)
+        assert np.array_equal(d[nm], want), nm
+
+
+def test_read_file_missing_raises(tmp_path):
+    m = gm.HarmModel(1000, 4e19)
+    with pytest.raises(gm.GrmontyError, match="File does not exist"):
+        m.read_file(str(tmp_path / "nope"))
+
+
+@pytest.fixture(scope="module")
+def host48(tmp_path_factory):
+    """host model of the same 48x48 synthetic dump the golden vectors were generated from"""
+    p = str(tmp_path_factory.mktemp("dump") / "dump48.txt")
+    header, table = make_harm_dump.make_dump(n0=48, n1=48)
+    make_harm_dump.write_dump(p, header, table)
+    m = gm.HarmModel(2000, 4e19)
+    m.read_file(p)
+    m.init()
+    return m
+
+
+def test_units_scalars_and_grids_match_reference(host48, golden_model):
+    d = host48.model_dict()
+    for k in ["mass_unit", "l_unit", "t_unit", "rho_unit", "u_unit", "b_unit", "theta_e_unit", "n_e_unit",
+              "max_tau_scatt0", "d_tau_k", "x1_min", "x_start1", "dx1", "dx2", "x_stop1", "x_stop2", "a", "h_slope"]:
+        assert d[k] == pytest.approx(golden_model[k], rel=1e-15), k
+    assert d["bias_norm"] == pytest.approx(golden_model["bias_norm"], rel=1e-12)
+    for k in ["k_rho", "u", "u_1", "u_2", "u_3", "b_1", "b_2", "b_3"]:
+        # the dump text is regenerated here; values agree to the printed precision (%.15g)
+        assert np.allclose(d[k], golden_model[k], rtol=1e-13, atol=0), k
+    assert np.allclose(d["geom_det"], golden_model["geom_det"], rtol=1e-13)
+
+
+def test_tables_match_reference(host48, golden_model):
+    """table builders vs the reference's own tables (golden): hotcross and K2 restate the reference arithmetic
+    (agreement ~1e-13); F(K) uses a different quadrature than the reference's adaptive GK61 (eps_rel 1e-6)."""
+    d = host48.model_dict()
+    assert np.max(np.abs(d["hotcross"] - golden_model["hotcross"])) < 1e-12      # log10 sigma
+    assert np.max(np.abs(d["k2"] - golden_model["k2"])) < 1e-12                  # ln K2
+    assert np.max(np.abs(d["f"] - golden_model["f"])) < 3e-6                     # ln F
+    assert np.max(np.abs(d["weight"] - golden_model["weight"])) < 5e-6           # ln weight
+    ok = np.isfinite(golden_model["nint"])
+    assert np.array_equal(ok, np.isfinite(d["nint"]))
+    assert np.max(np.abs(d["nint"][ok] - golden_model["nint"][ok])) < 1e-5
+    ok = np.isfinite(golden_model["dndlnu_max"])
+    assert np.max(np.abs(d["dndlnu_max"][ok] - golden_model["dndlnu_max"][ok])) < 1e-5
+
+
+def test_tables_do_not_depend_on_thread_count(tmp_path):
+    p = str(tmp_path / "d.txt")
+    header, table = make_harm_dump.make_dump(n0=16, n1=16)
+    make_harm_dump.write_dump(p, header, table)
+    out = []
+    for threads in (1, 5):
+        m = gm.HarmModel(500, 4e19)
+        m.read_file(p)
+        for stage in (0, 2, 3, 4):  # skip the hot cross-section table (grid independent)
+            m.init_stage(stage, threads)
+        d = m.model_dict()
+        out.append(np.concatenate([d["geom_det"].ravel(), d["f"], d["k2"], d["weight"], d["nint"]]))
+    assert np.array_equal(out[0], out[1], equal_nan=True)
+
+
+def test_spectrum_file_is_byte_identical_to_the_reference(host48, tmp_path):
+    """report_spectrum on the same Spectrum array must produce the same bytes as the reference's
+    (fixture: tests/golden/spectrum_file.npz, written by oracle/make_golden.py from the reference build)"""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "spectrum_file.npz"))
+    host48.set_spectrum(fx["spectrum"])
+    out = str(tmp_path / "spectrum.txt")
+    host48.report_spectrum(out)
+    got = open(out, "rb").read()
+    assert got == fx["text"].tobytes()
+    st = host48.stats()
+    assert st["luminosity"] == pytest.approx(float(fx["luminosity"]), rel=1e-4)  # fixture value is from the 5-digit text
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """every function declared in include/grmonty_b200.h is exported by the CUDA library (no compute calls)"""
+    import ctypes
+    import re
+    hdr = open(os.path.join(ROOT, "include", "grmonty_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(grmonty_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    gm.build_cuda()
+    L = ctypes.CDLL(gm.LIB_CUDA)
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(gm.ABI_SYMBOLS) == declared
+
+
+def test_no_cpu_fallback(golden_model):
+    """without a CUDA device the product fails loudly instead of computing on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gm.GrmontyError, match="no CUDA device"):
+        gm.Context(golden_model)
+    m = gm.HarmModel(10, 4e19)
+    with pytest.raises(gm.GrmontyError):
+        m.set_options()
+        m.run_simulation()
+
+
+def test_cli_flags(tmp_path):
+    """the CLI accepts the reference's flag spellings; without a readable dump it exits non-zero"""
+    r = subprocess.run([gm.CLI, "--harm_dump_path", str(tmp_path / "missing"), "--spectrum_path",
+                        str(tmp_path / "s"), "-photon_n", "1000", "--mass_unit=4e19", "--verbosity", "error"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "File does not exist" in r.stderr
