@@ -6,6 +6,7 @@
  * on-device photon generation and one persistent kernel per generation.  No CPU fallback exists: every
  * entry point needs a CUDA device and fails with GRMONTY_B200_ECUDA otherwise.
  */
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -55,7 +56,7 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
-    long long gen0 = 32, gen_cap = 1 << 22;
+    long long gen0 = 32, gen_cap = 1 << 20;
     grmonty_b200_stats stats{};
     std::string err;
 };
@@ -270,7 +271,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         CK(cudaMemcpy(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice));
 
         /* ---- photon pool and stage queues ---- */
-        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 24);
+        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 22);
         if (cap > 0x3fffffffull)
             cap = 0x3fffffffull; /* slots are addressed with 32 bits */
         auto alloc_pool = [&](PhotonPool &pl, unsigned long long c) -> cudaError_t {
@@ -463,11 +464,25 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     long long blocks = std::min<long long>(ctx->grid_blocks,
                                            std::max<long long>(1, (n_start * 2 + ctx->threads - 1) / ctx->threads));
     blocks = std::max<long long>(blocks, std::min<long long>(ctx->grid_blocks, ctx->sm_count));
+    /* profiling hook: GRMONTY_B200_PROFILE_MIN_COUNT=n brackets the first transport launch that starts with at
+     * least n photons with cudaProfilerStart/Stop (use with `ncu --profile-from-start off`) */
+    static long long prof_min = -2;
+    if (prof_min == -2) {
+        const char *e = getenv("GRMONTY_B200_PROFILE_MIN_COUNT");
+        prof_min = e ? atoll(e) : -1;
+    }
+    const bool prof = prof_min >= 0 && n_start >= prof_min;
+    if (prof)
+        cudaProfilerStart();
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     v->fn<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
+    if (prof) {
+        cudaProfilerStop();
+        prof_min = -1;
+    }
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.kernel_ms += ms;
     ctx->stats.transport_ms += ms;

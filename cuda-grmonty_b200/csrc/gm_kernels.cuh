@@ -359,11 +359,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
         idle_spins = 0;
         ++iter;
         /* ---- one flattened iteration for every live lane ---- */
+        const unsigned int live_mask = __ballot_sync(0xffffffffu, has);
         ++wk.slot_iters;
         if (has) {
             ++wk.live_iters;
             bool record;
-            const StepResult r = advance(A, L, snap, BLOCK, wk, record);
+            const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
             if (r == STEP_FINISHED) {
                 if (record) {
                     record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);

@@ -395,7 +395,8 @@ struct Work {
 enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_SUSPEND = 3 };
 
 /* Interaction with the fluid after an accepted step (reference harm_model.cpp:936-1056).
- * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER). */
+ * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER).
+ * Single exit, no early returns: the lanes of a warp must leave this function together (see advance). */
 __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const GeoPoint &q,
                                                const double *snap, int snap_stride, Work &wk) {
     const GmParams &P = A.P;
@@ -411,8 +412,16 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         fluid_frame(P, L.k, f, e_fluid, mu);
         nu = e_fluid * kME * kCL * kCL / kHPL;
     }
+    const bool outside = bound || nu < 0.0;
+    /* evaluate the opacities for every lane (harmless dummy arguments outside the fluid) so that the warp
+     * stays converged through the expensive part */
+    const double nu_e = outside ? 1.0e12 : nu, te_e = outside ? 1.0 : f.theta_e, ne_e = outside ? 1.0 : f.n_e;
+    const double b_e = outside ? 1.0 : f.b;
+    const double a_sf = alpha_inv_scatt(P, nu_e, te_e, ne_e);
+    const double a_af = alpha_inv_abs_sin(P, nu_e, te_e, ne_e, b_e, sqrt(1.0 - mu * mu));
+    const double bf = bias_func(P, A.bias, te_e, L.w);
     double d_tau_scatt, d_tau_abs, bias;
-    if (bound || nu < 0.0) {
+    if (outside) {
         d_tau_scatt = 0.5 * L.alpha_scatt * P.d_tau_k * L.dl;
         d_tau_abs = 0.5 * L.alpha_abs * P.d_tau_k * L.dl;
         L.alpha_scatt = 0.0;
@@ -420,19 +429,17 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         bias = 0.0;
         L.bi = 0.0;
     } else {
-        const double a_sf = alpha_inv_scatt(P, nu, f.theta_e, f.n_e);
         d_tau_scatt = 0.5 * (L.alpha_scatt + a_sf) * P.d_tau_k * L.dl;
         L.alpha_scatt = a_sf;
-        const double a_af = alpha_inv_abs_sin(P, nu, f.theta_e, f.n_e, f.b, sqrt(1.0 - mu * mu));
         d_tau_abs = 0.5 * (L.alpha_abs + a_af) * P.d_tau_k * L.dl;
         L.alpha_abs = a_af;
-        const double bf = bias_func(P, A.bias, f.theta_e, L.w);
         bias = 0.5 * (L.bi + bf);
         L.bi = bf;
     }
     L.ne_pos = f.n_e > 0.0;
     const double x1r = -log(rng_uniform(P, L.rng));
     const double w_child = L.w / bias;
+    StepResult res = STEP_CONTINUE;
     if (bias * d_tau_scatt > x1r && w_child > kWeightMin) {
         /* ---- the photon scatters in this step (reference :985-1005): park it ---- */
         const Rng crng = rng_child(P, L.rng);
@@ -440,113 +447,131 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         d_tau_abs *= frac;
         if (d_tau_abs > 100) {
             L.status |= 4;
-            return STEP_FINISHED; /* absorbed before scattering */
-        }
-        d_tau_scatt *= frac;
-        L.w *= attenuation(d_tau_abs + d_tau_scatt, d_tau_abs < 1.0e-3);
-        const PhotonPool &pool = A.pool;
-        const unsigned int s = L.slot;
-        /* the scattering stage restarts from the pre-step snapshot and pushes it by dl * frac */
+            res = STEP_FINISHED; /* absorbed before scattering */
+        } else {
+            d_tau_scatt *= frac;
+            L.w *= attenuation(d_tau_abs + d_tau_scatt, d_tau_abs < 1.0e-3);
+            const PhotonPool &pool = A.pool;
+            const unsigned int s = L.slot;
+            /* the scattering stage restarts from the pre-step snapshot and pushes it by dl * frac */
 #pragma unroll
-        for (int i = 0; i < 12; ++i)
-            pstore(pool, P_X0 + i, s, snap[i * snap_stride]);
-        pstore(pool, P_E0S, s, snap[12 * snap_stride]);
-        pstore(pool, P_W, s, L.w);
-        pstore(pool, P_TAU_ABS, s, L.tau_abs + d_tau_abs);
-        pstore(pool, P_TAU_SCATT, s, L.tau_scatt + d_tau_scatt);
-        pstore(pool, P_ALPHA_SCATT, s, L.dl * frac);
-        pstore(pool, P_ALPHA_ABS, s, w_child);
-        __stcg(pool.rng + s, make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr));
-        __stcg(pool.crng + s, make_uint4(crng.id0, crng.id1, crng.id2, crng.ctr));
-        __stcg(pool.n_step + s, L.n_step);
-        __stcg(pool.gclock + s, L.clock);
-        queue_push(A, A.scatter, s);
-        return STEP_SCATTER;
-    }
-    if (d_tau_abs > 100) {
+            for (int i = 0; i < 12; ++i)
+                pstore(pool, P_X0 + i, s, snap[i * snap_stride]);
+            pstore(pool, P_E0S, s, snap[12 * snap_stride]);
+            pstore(pool, P_W, s, L.w);
+            pstore(pool, P_TAU_ABS, s, L.tau_abs + d_tau_abs);
+            pstore(pool, P_TAU_SCATT, s, L.tau_scatt + d_tau_scatt);
+            pstore(pool, P_ALPHA_SCATT, s, L.dl * frac);
+            pstore(pool, P_ALPHA_ABS, s, w_child);
+            __stcg(pool.rng + s, make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr));
+            __stcg(pool.crng + s, make_uint4(crng.id0, crng.id1, crng.id2, crng.ctr));
+            __stcg(pool.n_step + s, L.n_step);
+            __stcg(pool.gclock + s, L.clock);
+            queue_push(A, A.scatter, s);
+            res = STEP_SCATTER;
+        }
+    } else if (d_tau_abs > 100) {
         L.status |= 4;
-        return STEP_FINISHED; /* absorbed */
+        res = STEP_FINISHED; /* absorbed */
+    } else {
+        const double d_tau = d_tau_abs + d_tau_scatt;
+        L.w *= attenuation(d_tau, d_tau < 1.0e-3);
+        L.tau_abs += d_tau_abs;
+        L.tau_scatt += d_tau_scatt;
     }
-    const double d_tau = d_tau_abs + d_tau_scatt;
-    L.w *= attenuation(d_tau, d_tau < 1.0e-3);
-    L.tau_abs += d_tau_abs;
-    L.tau_scatt += d_tau_scatt;
-    return STEP_CONTINUE;
+    return res;
 }
 
-/* One iteration of the flattened per-photon loop: (step start bookkeeping) + one push attempt +
- * (step end: stop test, interaction).  `record` tells whether a finished photon escaped through r > r_max
- * (reference :1066-1068). */
-__device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, double *snap, int snap_stride,
-                                              Work &wk, bool &record) {
+/* One iteration of the flattened per-photon loop, in three phases that every live lane of the warp walks
+ * through together:  A  step-start bookkeeping (suspend / stop test, snapshot, step size);
+ *                    B  one push attempt;
+ *                    C  step end (stop test, interaction with the fluid).
+ * There are no early returns: each phase ends with __syncwarp(live) so that the lanes RECONVERGE before the
+ * next one.  (With early returns the compiler let the lanes that came through phase A and those that were in
+ * the middle of a halved step run phase B separately: ncu showed 15.6 of ~27 live threads per instruction.)
+ * `record` tells whether a finished photon escaped through r > r_max (reference :1066-1068). */
+__device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, unsigned int live, double *snap,
+                                              int snap_stride, Work &wk, bool &record) {
     const GmParams &P = A.P;
     record = false;
+    StepResult st = STEP_CONTINUE;
+    /* ---- phase A ---- */
     if (L.pos == 0 && L.level == 0) {
         /* out of attempts for this generation: continue in the next one.  Checked BEFORE the stop test so
          * that the test (and its roulette draw) runs exactly once per loop iteration, on resumption. */
-        if (L.clock >= A.budget)
-            return STEP_SUSPEND;
-        /* top of the while loop (:919) */
-        if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) {
+        if (L.clock >= A.budget) {
+            st = STEP_SUSPEND;
+        } else if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) { /* top of the while loop (:919) */
             record = L.x[1] > P.x1_max;
-            return STEP_FINISHED;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            snap[(0 + i) * snap_stride] = L.x[i];
-            snap[(4 + i) * snap_stride] = L.k[i];
-            snap[(8 + i) * snap_stride] = L.dk[i];
-        }
-        snap[12 * snap_stride] = L.e_0_s;
-        L.dl = step_size(P, L.x, L.k);
-    }
-    bool accept;
-    GeoPoint q;
-    if (L.x[1] < P.x_start1) {
-        accept = true; /* push_photon is a silent no-op below the grid's inner edge (:1218-1220) */
-        q = geo_point(P, L.x[1], L.x[2]);
-    } else {
-        double xn[4], kn[4], dkn[4], e1;
-        const bool fail = push_attempt(P, L.x, L.k, L.dk, ldexp(L.dl, -L.level), L.e_0_s, xn, kn, dkn, e1, q);
-        ++wk.attempts;
-        ++L.clock;
-        accept = !(fail && L.level < kMaxHalvings);
-        if (accept) {
+            st = STEP_FINISHED;
+        } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                L.x[i] = xn[i];
-                L.k[i] = kn[i];
-                L.dk[i] = dkn[i];
+                snap[(0 + i) * snap_stride] = L.x[i];
+                snap[(4 + i) * snap_stride] = L.k[i];
+                snap[(8 + i) * snap_stride] = L.dk[i];
             }
-            L.e_0_s = e1;
+            snap[12 * snap_stride] = L.e_0_s;
+            L.dl = step_size(P, L.x, L.k);
         }
     }
-    if (!accept) {
-        ++L.level;
-        return STEP_CONTINUE;
+    __syncwarp(live);
+    /* ---- phase B ---- */
+    bool step_done = false;
+    GeoPoint q;
+    if (st == STEP_CONTINUE) {
+        double xn[4], kn[4], dkn[4], e1;
+        /* below the grid's inner edge push_photon is a silent no-op (:1218-1220): the attempt is computed but
+         * discarded, so that the warp does not diverge (it happens only inside the horizon) */
+        const bool noop = L.x[1] < P.x_start1;
+        const bool fail = push_attempt(P, L.x, L.k, L.dk, ldexp(L.dl, -L.level), L.e_0_s, xn, kn, dkn, e1, q);
+        bool accept = true;
+        if (!noop) {
+            ++wk.attempts;
+            ++L.clock;
+            accept = !(fail && L.level < kMaxHalvings);
+            if (accept) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    L.x[i] = xn[i];
+                    L.k[i] = kn[i];
+                    L.dk[i] = dkn[i];
+                }
+                L.e_0_s = e1;
+            }
+        }
+        if (!accept) {
+            ++L.level;
+        } else {
+            L.pos += 128 >> L.level;
+            if (L.pos < 128) {
+                L.level = halving_next_level(L.pos);
+            } else {
+                L.pos = 0;
+                L.level = 0;
+                step_done = true;
+                ++wk.steps;
+            }
+        }
     }
-    L.pos += 128 >> L.level;
-    if (L.pos < 128) {
-        L.level = halving_next_level(L.pos);
-        return STEP_CONTINUE;
+    __syncwarp(live);
+    /* ---- phase C ---- */
+    if (step_done) {
+        if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) {
+            record = L.x[1] > P.x1_max;
+            st = STEP_FINISHED;
+        } else {
+            if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos)
+                st = interact(A, L, q, snap, snap_stride, wk);
+            if (st == STEP_CONTINUE) {
+                ++L.n_step;
+                if (L.n_step > kMaxNStep)
+                    st = STEP_FINISHED; /* step cap: not recorded (:1060-1066) */
+            }
+        }
     }
-    /* the step is complete */
-    L.pos = 0;
-    L.level = 0;
-    ++wk.steps;
-    if (stop_criterion_fast(A, L.x[1], L.w, L.rng)) {
-        record = L.x[1] > P.x1_max;
-        return STEP_FINISHED;
-    }
-    if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos) {
-        const StepResult r = interact(A, L, q, snap, snap_stride, wk);
-        if (r != STEP_CONTINUE)
-            return r;
-    }
-    ++L.n_step;
-    if (L.n_step > kMaxNStep)
-        return STEP_FINISHED; /* step cap: not recorded (:1060-1066) */
-    return STEP_CONTINUE;
+    __syncwarp(live);
+    return st;
 }
 
 /* write the start-of-track record of a photon (hot part); cold fields are written by the caller */

@@ -96,7 +96,7 @@ typedef struct grmonty_b200_config {
     int32_t blocks_per_sm;
     int64_t queue_capacity; /* photon slots in the device queue */
     int64_t gen0;           /* positions in the first generation (default 32); doubles each generation ... */
-    int64_t gen_cap;        /* ... up to this cap (default 2^22).  Bias statistics are frozen within a generation. */
+    int64_t gen_cap;        /* ... up to this cap (default 2^20).  Bias statistics are frozen within a generation. */
     int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over
                                to the next one (default 256); bounds the tail of every generation */
 } grmonty_b200_config;

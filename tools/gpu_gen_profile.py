@@ -5,13 +5,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cuda_grmonty_b200 as gm
-d = dict(np.load(os.path.join(ROOT, "tests/golden/functions_48.npz")))
-m = {k[6:]: (v.item() if v.ndim == 0 else v) for k, v in d.items() if k.startswith("model_")}
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 100.0
 budget = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-m["photon_n"] *= scale; m["weight"] = m["weight"] - np.log(scale)
-m["nint"] = m["nint"] + np.log(scale); m["dndlnu_max"] = m["dndlnu_max"] + np.log(scale)
-c = gm.Context(m, gen_budget=budget)
+grid = int(sys.argv[3]) if len(sys.argv) > 3 else 48
+tb = [int(v) for v in sys.argv[4].split("x")] if len(sys.argv) > 4 else [0, 0]
+if grid == 48:
+    d = dict(np.load(os.path.join(ROOT, "tests/golden/functions_48.npz")))
+    m = {k[6:]: (v.item() if v.ndim == 0 else v) for k, v in d.items() if k.startswith("model_")}
+    m["photon_n"] *= scale; m["weight"] = m["weight"] - np.log(scale)
+    m["nint"] = m["nint"] + np.log(scale); m["dndlnu_max"] = m["dndlnu_max"] + np.log(scale)
+else:
+    from tools import make_harm_dump
+    p = f"/tmp/gp_dump_{grid}.txt"
+    if not os.path.exists(p):
+        make_harm_dump.write_dump(p, *make_harm_dump.make_dump(n0=grid, n1=grid))
+    gm.build_host()
+    hm = gm.HarmModel(int(2000 * scale), 4e19); hm.read_file(p); hm.init(); m = hm.model_dict()
+c = gm.Context(m, gen_budget=budget, threads_per_block=tb[0], blocks_per_sm=tb[1])
 tot = c.total_primaries()
 c.run(0, 2000); c.reset()
 gs, g = 0, 0
