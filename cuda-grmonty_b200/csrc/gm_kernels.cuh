@@ -240,6 +240,11 @@ __device__ __noinline__ void record_call(const TransportArgs *Ag, unsigned int s
     record_super_photon(*Ag, slot, x2, x3, w, tau_abs, tau_scatt);
 }
 
+#ifndef GM_ITERS_PER_SYNC
+#define GM_ITERS_PER_SYNC 1
+#endif
+constexpr int kItersPerSync = GM_ITERS_PER_SYNC;
+
 template <int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const TransportArgs A) {
     /* Control words shared by the block.  The warps of a block run the loop in lockstep (one barrier per
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
     bool has = false;
     long long ticket = -1; /* position in the ready queue this lane is entitled to (monotone queue, no wrap) */
     Work wk = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    unsigned int iter = 0, idle_spins = 0;
+    unsigned int idle_spins = 0;
     bool was_idle = true;
 
     for (;;) {
@@ -263,19 +268,17 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
         /* ---- block control (one thread): claim parked photons for the scattering stage ---- */
         if (threadIdx.x == 0) {
             int cnt = 0;
-            if (was_idle || (iter & 3u) == 0u) {
-                const unsigned long long h = ld_volatile_u64(A.scatter.head);
-                unsigned long long t = ld_volatile_u64(A.scatter.tail);
-                t = t < A.scatter.capacity ? t : A.scatter.capacity;
-                const unsigned long long avail = t > h ? t - h : 0ull;
-                /* a full block-load of parked photons, or -- when the block has nothing else to do -- any */
-                if (avail >= (unsigned long long)BLOCK || (was_idle && avail > 0)) {
-                    cnt = avail < (unsigned long long)BLOCK ? (int)avail : BLOCK;
-                    if (atomicCAS(A.scatter.head, h, h + cnt) == h)
-                        s_base = h;
-                    else
-                        cnt = 0;
-                }
+            const unsigned long long h = ld_volatile_u64(A.scatter.head);
+            unsigned long long t = ld_volatile_u64(A.scatter.tail);
+            t = t < A.scatter.capacity ? t : A.scatter.capacity;
+            const unsigned long long avail = t > h ? t - h : 0ull;
+            /* a full block-load of parked photons, or -- when the block has nothing else to do -- any */
+            if (avail >= (unsigned long long)BLOCK || (was_idle && avail > 0)) {
+                cnt = avail < (unsigned long long)BLOCK ? (int)avail : BLOCK;
+                if (atomicCAS(A.scatter.head, h, h + cnt) == h)
+                    s_base = h;
+                else
+                    cnt = 0;
             }
             s_count = cnt;
         }
@@ -297,50 +300,97 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                     n_done += scatter_stage(A.self, v - 1u, wk.attempts, wk.scatters, wk.tracked);
             }
         }
-        /* ---- refill empty lanes from the ready queue: a ticket per empty lane (one atomicAdd per warp,
-         *      never fails), then loads only ---- */
-        {
-            const bool want = !has && ticket < 0;
-            const unsigned int need = __ballot_sync(0xffffffffu, want);
-            if (need) {
-                unsigned long long base = 0;
-                if (lane == 0)
-                    base = atomicAdd(A.ready.head, (unsigned long long)__popc(need));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (want)
-                    ticket = (long long)(base + __popc(need & ((1u << lane) - 1u)));
-            }
-            if (!has && ticket >= 0 && ticket < (long long)A.ready.capacity) {
-                const unsigned int v = ld_volatile_u32(A.ready.entries + ticket);
-                if (v) {
-                    __threadfence();
-                    const unsigned int slot = v - 1u;
-                    ticket = -1;
-                    live_load(A, slot, L);
-                    bool bad = (L.w == 0.0);
+        /* ---- kItersPerSync loop iterations per warp between two block barriers.  The barrier keeps the warps
+         *      of the block in the same code region (instruction cache); syncing only every few iterations
+         *      keeps one warp's rare slow paths (record, park, suspend) from stalling the other warps every
+         *      time ---- */
+#pragma unroll 1
+        for (int sub = 0; sub < kItersPerSync; ++sub) {
+            /* refill empty lanes from the ready queue: a ticket per empty lane (one atomicAdd per warp, never
+             * fails), then loads only */
+            {
+                const bool want = !has && ticket < 0;
+                const unsigned int need = __ballot_sync(0xffffffffu, want);
+                if (need) {
+                    unsigned long long base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(A.ready.head, (unsigned long long)__popc(need));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (want)
+                        ticket = (long long)(base + __popc(need & ((1u << lane) - 1u)));
+                }
+                if (!has && ticket >= 0 && ticket < (long long)A.ready.capacity) {
+                    const unsigned int v = ld_volatile_u32(A.ready.entries + ticket);
+                    if (v) {
+                        __threadfence();
+                        const unsigned int slot = v - 1u;
+                        ticket = -1;
+                        live_load(A, slot, L);
+                        bool bad = (L.w == 0.0);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
-                    if (bad) {
-                        ++n_done; /* invalid photon (reference :895-900): dropped */
-                        if (A.D.status && slot < A.D.n)
-                            atomicOr(A.D.status + slot, 4);
-                    } else {
-                        has = true;
+                        for (int i = 0; i < 4; ++i)
+                            bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
+                        if (bad) {
+                            ++n_done; /* invalid photon (reference :895-900): dropped */
+                            if (A.D.status && slot < A.D.n)
+                                atomicOr(A.D.status + slot, 4);
+                        } else {
+                            has = true;
+                        }
                     }
                 }
             }
+            const unsigned int live_mask = __ballot_sync(0xffffffffu, has);
+            if (!live_mask)
+                break; /* nothing to do in this warp: go to the barrier */
+            /* one flattened iteration for every live lane */
+            ++wk.slot_iters;
+            if (has) {
+                ++wk.live_iters;
+                bool record;
+                const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
+                if (r == STEP_FINISHED) {
+                    if (record) {
+                        record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
+                        L.status |= 1;
+                    }
+                    if (A.D.final_state && L.slot < A.D.n) {
+                        double *o = A.D.final_state + (size_t)L.slot * 12;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            o[i] = L.x[i];
+                            o[4 + i] = L.k[i];
+                        }
+                        o[8] = L.w;
+                        o[9] = L.tau_abs;
+                        o[10] = L.tau_scatt;
+                        o[11] = L.e_0_s;
+                        atomicOr(A.D.status + L.slot, L.status);
+                        A.pool.rng[L.slot] = make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr);
+                    }
+                    has = false;
+                    ++n_done;
+                } else if (r == STEP_SCATTER) {
+                    has = false; /* parked for the scattering stage */
+                } else if (r == STEP_SUSPEND) {
+                    suspend_photon(A.self, L.slot, L.x, L.k, L.dk, L.w, L.e_0_s, L.tau_abs, L.tau_scatt,
+                                   L.alpha_scatt, L.alpha_abs, L.bi, L.ne_pos, L.rng, L.n_step);
+                    has = false;
+                    ++n_done; /* done as far as this generation is concerned */
+                }
+            }
         }
-        /* ---- nothing to do in this block? ---- */
-        const int block_live = __syncthreads_or(has ? 1 : 0);
-        if (!block_live) {
+        /* ---- publish finished counts; is the whole block out of work? ---- */
+        {
             int s = n_done;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
                 s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0 && s)
                 atomicAdd(A.pool.finished, (unsigned long long)s);
-            __syncthreads(); /* all warps' finished counts are in before thread 0 looks */
+        }
+        const int block_live = __syncthreads_or(has ? 1 : 0);
+        if (!block_live) {
             if (threadIdx.x == 0) {
                 const unsigned long long fin = ld_volatile_u64(A.pool.finished);
                 __threadfence();
@@ -353,55 +403,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
             was_idle = true;
             if (++idle_spins > 2)
                 __nanosleep(1000);
-            continue;
-        }
-        was_idle = false;
-        idle_spins = 0;
-        ++iter;
-        /* ---- one flattened iteration for every live lane ---- */
-        const unsigned int live_mask = __ballot_sync(0xffffffffu, has);
-        ++wk.slot_iters;
-        if (has) {
-            ++wk.live_iters;
-            bool record;
-            const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
-            if (r == STEP_FINISHED) {
-                if (record) {
-                    record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
-                    L.status |= 1;
-                }
-                if (A.D.final_state && L.slot < A.D.n) {
-                    double *o = A.D.final_state + (size_t)L.slot * 12;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        o[i] = L.x[i];
-                        o[4 + i] = L.k[i];
-                    }
-                    o[8] = L.w;
-                    o[9] = L.tau_abs;
-                    o[10] = L.tau_scatt;
-                    o[11] = L.e_0_s;
-                    atomicOr(A.D.status + L.slot, L.status);
-                    A.pool.rng[L.slot] = make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr);
-                }
-                has = false;
-                ++n_done;
-            } else if (r == STEP_SCATTER) {
-                has = false; /* parked for the scattering stage */
-            } else if (r == STEP_SUSPEND) {
-                suspend_photon(A.self, L.slot, L.x, L.k, L.dk, L.w, L.e_0_s, L.tau_abs, L.tau_scatt, L.alpha_scatt,
-                               L.alpha_abs, L.bi, L.ne_pos, L.rng, L.n_step);
-                has = false;
-                ++n_done; /* done as far as this generation is concerned */
-            }
-        }
-        if (__ballot_sync(0xffffffffu, n_done != 0)) {
-            int s = n_done;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0)
-                atomicAdd(A.pool.finished, (unsigned long long)s);
+        } else {
+            was_idle = false;
+            idle_spins = 0;
         }
     }
     /* flush work counters: warp-reduce, one atomic per warp and counter */
