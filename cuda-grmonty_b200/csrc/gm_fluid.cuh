@@ -32,21 +32,21 @@ __device__ __forceinline__ void prims_to_fluid(const GmParams &P, const MetricCo
                                                double gcon01, const double v[4], const double bp[4], Fluid &f) {
     const double v_dot_v =
         g.g11 * v[1] * v[1] + 2.0 * g.g13 * v[1] * v[3] + g.g22 * v[2] * v[2] + g.g33 * v[3] * v[3];
-    const double v_fac = sqrt(-1.0 / gcon00 * (1.0 + fabs(v_dot_v)));
+    const double v_fac = fm::sqrt_(-fm::rcp(gcon00) * (1.0 + fabs(v_dot_v)));
     f.u_con[0] = -v_fac * gcon00;
     f.u_con[1] = v[1] - v_fac * gcon01;
     f.u_con[2] = v[2];
     f.u_con[3] = v[3];
     lower_sparse(g, f.u_con, f.u_cov);
     const double u_dot_bp = f.u_cov[1] * bp[1] + f.u_cov[2] * bp[2] + f.u_cov[3] * bp[3];
-    const double iu0 = 1.0 / f.u_con[0];
+    const double iu0 = fm::rcp(f.u_con[0]);
     f.b_con[0] = u_dot_bp;
     f.b_con[1] = (bp[1] + f.u_con[1] * u_dot_bp) * iu0;
     f.b_con[2] = (bp[2] + f.u_con[2] * u_dot_bp) * iu0;
     f.b_con[3] = (bp[3] + f.u_con[3] * u_dot_bp) * iu0;
     lower_sparse(g, f.b_con, f.b_cov);
-    f.b = sqrt(f.b_con[0] * f.b_cov[0] + f.b_con[1] * f.b_cov[1] + f.b_con[2] * f.b_cov[2] +
-               f.b_con[3] * f.b_cov[3]) *
+    f.b = fm::sqrt_(f.b_con[0] * f.b_cov[0] + f.b_con[1] * f.b_cov[1] + f.b_con[2] * f.b_cov[2] +
+                    f.b_con[3] * f.b_cov[3]) *
           P.b_unit;
 }
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         f.n_e = 0.0;
         return false;
     }
-    const double qi = (x1 - P.x_start1) / P.dx1, qj = (x2 - P.x_start2) / P.dx2;
+    const double qi = fm::div(x1 - P.x_start1, P.dx1), qj = fm::div(x2 - P.x_start2, P.dx2);
     int i = (int)(qi - 0.5 + 1000) - 1000;
     int j = (int)(qj - 0.5 + 1000) - 1000;
     double del_i, del_j;
@@ -69,7 +69,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         i = P.n0 - 2;
         del_i = 1.0;
     } else {
-        del_i = (x1 - ((i + 0.5) * P.dx1 + P.x_start1)) / P.dx1;
+        del_i = fm::div(x1 - ((i + 0.5) * P.dx1 + P.x_start1), P.dx1);
     }
     if (j < 0) {
         j = 0;
@@ -78,7 +78,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         j = P.n1 - 2;
         del_j = 1.0;
     } else {
-        del_j = (x2 - ((j + 0.5) * P.dx2 + P.x_start2)) / P.dx2;
+        del_j = fm::div(x2 - ((j + 0.5) * P.dx2 + P.x_start2), P.dx2);
     }
     const double c00 = (1.0 - del_i) * (1.0 - del_j), c01 = (1.0 - del_i) * del_j;
     const double c10 = del_i * (1.0 - del_j), c11 = del_i * del_j;
@@ -92,7 +92,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         pr[2 * v + 1] = a.y * c00 + b.y * c01 + c.y * c10 + d.y * c11;
     }
     f.n_e = pr[0] * P.n_e_unit;
-    f.theta_e = pr[1] / pr[0] * P.theta_e_unit;
+    f.theta_e = fm::div(pr[1], pr[0]) * P.theta_e_unit;
     const double v[4] = {0.0, pr[2], pr[3], pr[4]};
     const double bp[4] = {0.0, pr[5], pr[6], pr[7]};
     const MetricCon gc = metric_con(P, q);

@@ -14,6 +14,7 @@
  *     that every lane of a warp executes the same attempt code each iteration (see gm_transport.cuh).
  */
 #pragma once
+#include "gm_math.cuh"
 #include "gm_params.h"
 
 namespace gm {
@@ -28,12 +29,13 @@ struct GeoPoint {
 
 __device__ __forceinline__ GeoPoint geo_point(const GmParams &P, double x1, double x2) {
     GeoPoint g;
-    g.r = exp(x1);
+    /* branch-free evaluations (gm_math.cuh): exp and sincospi interleave, sincos follows */
+    g.r = fm::exp_(x1);
     g.rm = g.r + P.r_0;
-    sincospi(2.0 * x2, &g.sx, &g.cx);
+    fm::sincospi_(2.0 * x2, &g.sx, &g.cx);
     const double omh = 1.0 - P.h_slope;
     const double th = kPi * x2 + 0.5 * omh * g.sx;
-    sincos(th, &g.sth, &g.cth);
+    fm::sincos_(th, &g.sth, &g.cth);
     g.hfac = kPi * (1.0 + omh * g.cx);
     return g;
 }
@@ -50,7 +52,7 @@ __device__ __forceinline__ MetricCov metric_cov(const GmParams &P, const GeoPoin
     const double r = q.rm;
     const double rho2 = r * r + a * a * q.cth * q.cth;
     const double rfac = r - P.r_0;
-    const double tr = 2.0 * r / rho2;
+    const double tr = fm::div(2.0 * r, rho2);
     MetricCov m;
     m.g00 = -1.0 + tr;
     m.g01 = tr * rfac;
@@ -68,7 +70,7 @@ __device__ __forceinline__ void metric_cov_row0(const GmParams &P, const GeoPoin
     const double s = fabs(q.sth) + kEps;
     const double r = q.rm;
     const double rho2 = r * r + P.a * P.a * q.cth * q.cth;
-    const double tr = 2.0 * r / rho2;
+    const double tr = fm::div(2.0 * r, rho2);
     g00 = -1.0 + tr;
     g01 = tr * (r - P.r_0);
     g03 = -P.a * (s * s) * tr;
@@ -83,14 +85,14 @@ __device__ __forceinline__ MetricCon metric_con(const GmParams &P, const GeoPoin
     const double s = fabs(q.sth) + kEps;
     const double r = q.rm;
     const double a = P.a;
-    const double irho2 = 1.0 / (r * r + a * a * q.cth * q.cth);
+    const double irho2 = fm::rcp(r * r + a * a * q.cth * q.cth);
     MetricCon m;
     m.g00 = -1.0 - 2.0 * r * irho2;
     m.g01 = 2.0 * irho2;
-    m.g11 = irho2 * (r * (r - 2.0) + a * a) / (r * r);
-    m.g13 = a * irho2 / r;
-    m.g22 = irho2 / (q.hfac * q.hfac);
-    m.g33 = irho2 / (s * s);
+    m.g11 = fm::div(irho2 * (r * (r - 2.0) + a * a), r * r);
+    m.g13 = fm::div(a * irho2, r);
+    m.g22 = fm::div(irho2, q.hfac * q.hfac);
+    m.g33 = fm::div(irho2, s * s);
     return m;
 }
 
@@ -120,11 +122,11 @@ __device__ __forceinline__ void connection_eval(const GmParams &P, const GeoPoin
     const double a2sth2 = a2 * sth2, a2cth2 = a2 * cth2, a4cth4 = a4 * cth4;
     const double rho2 = r2 + a2cth2;
     const double rho22 = rho2 * rho2, rho23 = rho22 * rho2;
-    const double irho2 = 1.0 / rho2;
+    const double irho2 = fm::rcp(rho2);
     const double irho22 = irho2 * irho2, irho23 = irho22 * irho2;
-    const double idth = 1.0 / dth;
-    const double ir1 = 1.0 / r1;
-    const double isth = 1.0 / sth;
+    const double idth = fm::rcp(dth);
+    const double ir1 = fm::rcp(r1);
+    const double isth = fm::rcp(sth);
     const double irho23_dth = irho23 * idth;
     const double fac1 = r2 - a2cth2;
     const double fac1_rho23 = fac1 * irho23;
@@ -212,10 +214,10 @@ __device__ __forceinline__ double step_size(const GmParams &P, const double x[4]
     const double a1 = fabs(kStepEps * x[1]);
     const double a2 = fabs(kStepEps * fmin(x[2], P.x_stop2 - x[2]));
     const double a3 = kStepEps;
-    const double i1 = b1 / (a1 + kEps * b1);
-    const double i2 = b2 / (a2 + kEps * b2);
-    const double i3 = b3 / (a3 + kEps * b3);
-    return 1.0 / (i1 + i2 + i3);
+    const double i1 = fm::div(b1, a1 + kEps * b1);
+    const double i2 = fm::div(b2, a2 + kEps * b2);
+    const double i3 = fm::div(b3, a3 + kEps * b3);
+    return fm::rcp(i1 + i2 + i3);
 }
 
 /* |a - b| / |b + eps| for the fixed-point convergence test.  The quotient only feeds the thresholds e_tol = 1e-3
@@ -229,7 +231,7 @@ __device__ __forceinline__ double rel_change(double a, double b) {
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b + kEps));
     return fabs((a - b) * r);
 #else
-    return fabs((a - b) / (b + kEps));
+    return fabs(fm::div(a - b, b + kEps));
 #endif
 }
 
@@ -276,7 +278,7 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
     double g00, g01, g03;
     metric_cov_row0(P, q, g00, g01, g03);
     e1 = -(kn[0] * g00 + kn[1] * g01 + kn[3] * g03);
-    const double err_e = fabs((e1 - e_0_s) / e_0_s);
+    const double err_e = fabs(fm::div(e1 - e_0_s, e_0_s));
     /* !(err <= tol) also catches NaN; isinf(err) > tol anyway (reference :1279) */
     return (err_e > 1.0e-4) || !(err <= kETol);
 }

@@ -296,8 +296,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                     }
                 }
                 __threadfence();
-                if (v)
-                    n_done += scatter_stage(A.self, v - 1u, wk.attempts, wk.scatters, wk.tracked);
+                if (v) {
+                    const ScatterStageResult sr = scatter_stage(A.self, v - 1u);
+                    n_done += sr.done;
+                    wk.attempts += sr.attempts;
+                    wk.scatters += sr.scatters;
+                    wk.tracked += sr.children;
+                }
             }
         }
         /* ---- kItersPerSync loop iterations per warp between two block barriers.  The barrier keeps the warps
@@ -373,8 +378,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                 } else if (r == STEP_SCATTER) {
                     has = false; /* parked for the scattering stage */
                 } else if (r == STEP_SUSPEND) {
-                    suspend_photon(A.self, L.slot, L.x, L.k, L.dk, L.w, L.e_0_s, L.tau_abs, L.tau_scatt,
-                                   L.alpha_scatt, L.alpha_abs, L.bi, L.ne_pos, L.rng, L.n_step);
+                    suspend_photon(A.self, L.slot, L.x[0], L.x[1], L.x[2], L.x[3], L.k[0], L.k[1], L.k[2], L.k[3],
+                                   L.dk[0], L.dk[1], L.dk[2], L.dk[3], L.w, L.e_0_s, L.tau_abs, L.tau_scatt,
+                                   L.alpha_scatt, L.alpha_abs, L.bi, L.ne_pos, L.rng.id0, L.rng.id1, L.rng.id2,
+                                   L.rng.ctr, L.n_step);
                     has = false;
                     ++n_done; /* done as far as this generation is concerned */
                 }

@@ -18,19 +18,21 @@ namespace gm {
 /* exp of a linear interpolation in a 201-entry log table (reference jnu_mixed.cpp:150-168;
  * upper index clamped) */
 __device__ __forceinline__ double interp_exp_table(const double *tab, double lx, double l_min, double d_l) {
-    double d_i = (lx - l_min) / d_l;
+    double d_i = fm::div(lx - l_min, d_l);
     int i = (int)d_i;
-    i = min(i, kNESamp - 1);
+    i = max(0, min(i, kNESamp - 1));
     d_i -= i;
-    return exp((1.0 - d_i) * __ldg(tab + i) + d_i * __ldg(tab + i + 1));
+    return fm::exp_((1.0 - d_i) * __ldg(tab + i) + d_i * __ldg(tab + i + 1));
 }
 
+/* K2(1/theta_e) given l_theta = ln(theta_e) (reference jnu_mixed::k2_eval, jnu_mixed.cpp:102-111); selects only */
+__device__ __forceinline__ double k2_eval_l(const GmParams &P, double theta_e, double l_theta) {
+    const double tab = interp_exp_table(P.k2, l_theta, P.jnu_l_min_t, P.jnu_d_l_t);
+    const double v = theta_e > kJnuMaxT ? 2.0 * theta_e * theta_e : tab;
+    return theta_e < kThetaEMin ? 0.0 : v;
+}
 __device__ __forceinline__ double k2_eval(const GmParams &P, double theta_e) {
-    if (theta_e < kThetaEMin)
-        return 0.0;
-    if (theta_e > kJnuMaxT)
-        return 2.0 * theta_e * theta_e;
-    return interp_exp_table(P.k2, log(theta_e), P.jnu_l_min_t, P.jnu_d_l_t);
+    return k2_eval_l(P, theta_e, fm::log_(fmax(theta_e, 1.0e-300)));
 }
 
 __device__ __forceinline__ double f_eval(const GmParams &P, double theta_e, double b_mag, double nu) {
@@ -44,21 +46,27 @@ __device__ __forceinline__ double f_eval(const GmParams &P, double theta_e, doub
     return interp_exp_table(P.f, log(k), P.jnu_l_min_k, P.jnu_d_l_k);
 }
 
-/* thermal synchrotron emissivity given sin(theta) (reference synch, jnu_mixed.cpp:75-100) */
+/* thermal synchrotron emissivity given sin(theta) and ln(theta_e) (reference synch, jnu_mixed.cpp:75-100).
+ * Branch-free: the two "return 0" conditions of the reference are applied as selects at the end, the arithmetic
+ * in between runs on guarded arguments. */
+__device__ __forceinline__ double synch_sin_l(const GmParams &P, double nu, double n_e, double theta_e, double b,
+                                              double sin_th, double l_theta) {
+    const double k2 = k2_eval_l(P, theta_e, l_theta);
+    const double nu_c = fm::div(kEE * b, 2.0 * kPi * kME * kCL);
+    const double nu_s = (2.0 / 9.0) * nu_c * theta_e * theta_e * sin_th;
+    const bool zero = (theta_e < kThetaEMin) || (nu > 1.0e12 * nu_s) || !(nu_s > 0.0);
+    const double nu_s_g = zero ? 1.0 : nu_s, nu_g = zero ? 1.0 : nu, k2_g = zero ? 1.0 : k2;
+    const double x = fm::div(nu_g, nu_s_g);
+    const double xp = fm::cbrt_(x);
+    const double xx = fm::sqrt_(x) + kJnuCst * fm::sqrt_(xp);
+    const double f = xx * xx;
+    const double j = fm::div(1.41421356237309504880 * kPi * kEE * kEE * n_e * nu_s_g, 3.0 * kCL * k2_g) * f *
+                     fm::exp_(-xp);
+    return zero ? 0.0 : j;
+}
 __device__ __forceinline__ double synch_sin(const GmParams &P, double nu, double n_e, double theta_e, double b,
                                             double sin_th) {
-    if (theta_e < kThetaEMin)
-        return 0.0;
-    const double k2 = k2_eval(P, theta_e);
-    const double nu_c = kEE * b / (2.0 * kPi * kME * kCL);
-    const double nu_s = (2.0 / 9.0) * nu_c * theta_e * theta_e * sin_th;
-    if (nu > 1.0e12 * nu_s)
-        return 0.0;
-    const double x = nu / nu_s;
-    const double xp = cbrt(x);
-    const double xx = sqrt(x) + kJnuCst * sqrt(xp);
-    const double f = xx * xx;
-    return (1.41421356237309504880 * kPi * kEE * kEE * n_e * nu_s / (3.0 * kCL * k2)) * f * exp(-xp);
+    return synch_sin_l(P, nu, n_e, theta_e, b, sin_th, fm::log_(fmax(theta_e, 1.0e-300)));
 }
 
 /* Klein-Nishina total cross-section / sigma_T (reference hotcross.cpp:144-152) */
@@ -113,22 +121,38 @@ __device__ __noinline__ double hotcross_num(double w, double theta_e) {
     return cross * kSigmaThomson;
 }
 
-/* reference total_compton_cross_lkup, hotcross.cpp:81-106 */
-__device__ __forceinline__ double hotcross_lkup(const GmParams &P, double w, double theta_e) {
-    if (w * theta_e < 1.0e-6)
-        return kSigmaThomson;
+/* the rare regimes of total_compton_cross_lkup that are not a table look-up (reference hotcross.cpp:86-93) */
+__device__ __noinline__ double hotcross_cold(double w, double theta_e) {
     if (theta_e < kHcMinT)
         return hc_klein_nishina(w) * kSigmaThomson;
-    if (w <= kHcMinW || w >= kHcMaxW || theta_e <= kHcMinT || theta_e >= kHcMaxT)
-        return hotcross_num(w, theta_e);
-    const double qw = (log10(w) - P.hc_l_min_w) / P.hc_d_l_w;
-    const double qt = (log10(theta_e) - P.hc_l_min_t) / P.hc_d_l_t;
+    return hotcross_num(w, theta_e);
+}
+
+/* reference total_compton_cross_lkup, hotcross.cpp:81-106, given l_w = ln(w) and l_theta = ln(theta_e).
+ * The table look-up runs for every lane on clamped coordinates (its loads and exp10 cost the same for one lane
+ * as for 32); the Thomson regime is a select, the out-of-table regimes a rarely taken call. */
+__device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, double theta_e, double l_w,
+                                                  double l_theta) {
+    const bool thomson = w * theta_e < 1.0e-6;
+    const bool in_table = !(w <= kHcMinW || w >= kHcMaxW || theta_e <= kHcMinT || theta_e >= kHcMaxT);
+    const double kLog10E = 0.43429448190325182765;
+    double qw = fm::div(l_w * kLog10E - P.hc_l_min_w, P.hc_d_l_w);
+    double qt = fm::div(l_theta * kLog10E - P.hc_l_min_t, P.hc_d_l_t);
+    qw = fmin(fmax(qw, 0.0), (double)kHcNW - 1.0e-6);
+    qt = fmin(fmax(qt, 0.0), (double)kHcNT - 1.0e-6);
     const int i = (int)qw, j = (int)qt;
     const double d_i = qw - i, d_j = qt - j;
     const double *t = P.hotcross + i * (kHcNT + 1) + j;
     const double l_cross = (1.0 - d_i) * (1.0 - d_j) * __ldg(t) + d_i * (1.0 - d_j) * __ldg(t + kHcNT + 1) +
                            (1.0 - d_i) * d_j * __ldg(t + 1) + d_i * d_j * __ldg(t + kHcNT + 2);
-    return exp10(l_cross);
+    double sigma = fm::exp10_(l_cross);
+    sigma = thomson ? kSigmaThomson : sigma;
+    if (!thomson && !in_table)
+        sigma = hotcross_cold(w, theta_e);
+    return sigma;
+}
+__device__ __forceinline__ double hotcross_lkup(const GmParams &P, double w, double theta_e) {
+    return hotcross_lkup_l(P, w, theta_e, fm::log_(fmax(w, 1.0e-300)), fm::log_(fmax(theta_e, 1.0e-300)));
 }
 
 /* fluid-frame photon energy (units of m_e c^2) and cosine of the angle between k and b
@@ -137,47 +161,55 @@ __device__ __forceinline__ void fluid_frame(const GmParams &P, const double k[4]
                                             double &mu) {
     const double ku = k[0] * f.u_cov[0] + k[1] * f.u_cov[1] + k[2] * f.u_cov[2] + k[3] * f.u_cov[3];
     e_fluid = -ku;
-    if (f.b == 0.0) {
-        mu = 0.0; /* theta = pi/2 */
-    } else {
-        const double kb = k[0] * f.b_cov[0] + k[1] * f.b_cov[1] + k[2] * f.b_cov[2] + k[3] * f.b_cov[3];
-        mu = kb / (fabs(ku) * f.b / P.b_unit);
-        mu = fmin(fmax(mu, -1.0), 1.0);
-    }
+    const double kb = k[0] * f.b_cov[0] + k[1] * f.b_cov[1] + k[2] * f.b_cov[2] + k[3] * f.b_cov[3];
+    const bool no_b = (f.b == 0.0);
+    const double den = fm::div(fabs(ku) * (no_b ? 1.0 : f.b), P.b_unit);
+    mu = fm::div(kb, den);
+    mu = fmin(fmax(mu, -1.0), 1.0);
+    mu = no_b ? 0.0 : mu; /* theta = pi/2 */
 }
 
 /* invariant scattering opacity nu * sigma_hot * n_e (reference alpha_inv_scatt / kappa_es,
  * radiation.cpp:103-107,142-146; the m_p factors cancel) */
+__device__ __forceinline__ double alpha_inv_scatt_l(const GmParams &P, double nu, double theta_e, double n_e,
+                                                    double l_nu, double l_theta) {
+    const double e_g = fm::div(kHPL * nu, kME * kCL * kCL);
+    const double kLnHOverMc2 = -46.263250426746548; /* ln(h / (m_e c^2)) in cgs: ln(e_g) = ln(nu) + this */
+    return nu * hotcross_lkup_l(P, e_g, theta_e, l_nu + kLnHOverMc2, l_theta) * n_e;
+}
 __device__ __forceinline__ double alpha_inv_scatt(const GmParams &P, double nu, double theta_e, double n_e) {
-    const double e_g = kHPL * nu / (kME * kCL * kCL);
-    return nu * hotcross_lkup(P, e_g, theta_e) * n_e;
+    return alpha_inv_scatt_l(P, nu, theta_e, n_e, fm::log_(fmax(nu, 1.0e-300)), fm::log_(fmax(theta_e, 1.0e-300)));
 }
 
-/* reference b_nu_inv, radiation.cpp:120-128 */
+/* reference b_nu_inv, radiation.cpp:120-128 (series below x = 1e-3), as a select between the two forms */
 __device__ __forceinline__ double b_nu_inv(double nu, double theta_e) {
-    const double x = kHPL * nu / (kME * kCL * kCL * theta_e);
+    const double x = fm::div(kHPL * nu, kME * kCL * kCL * theta_e);
     const double c = 2.0 * kHPL / (kCL * kCL);
-    if (x < 1.0e-3)
-        return c / (x / 24.0 * (24.0 + x * (12.0 + x * (4.0 + x))));
-    return c / (exp(x) - 1.0);
+    const double series = x * (1.0 / 24.0) * (24.0 + x * (12.0 + x * (4.0 + x)));
+    const double em1 = fm::exp_(fmin(x, 700.0)) - 1.0;
+    return fm::div(c, x < 1.0e-3 ? series : em1);
 }
 
-/* invariant absorption opacity by Kirchhoff's law (reference alpha_inv_abs, radiation.cpp:109-118) */
+/* invariant absorption opacity by Kirchhoff's law (reference alpha_inv_abs, radiation.cpp:109-118):
+ * (j / nu^2) / (B + 1e-100) evaluated as j / (nu^2 (B + 1e-100)): one division, no denormal intermediate */
+__device__ __forceinline__ double alpha_inv_abs_sin_l(const GmParams &P, double nu, double theta_e, double n_e,
+                                                      double b, double sin_th, double l_theta) {
+    const double j = synch_sin_l(P, nu, n_e, theta_e, b, sin_th, l_theta);
+    return fm::div(j, nu * nu * (b_nu_inv(nu, theta_e) + 1.0e-100));
+}
 __device__ __forceinline__ double alpha_inv_abs_sin(const GmParams &P, double nu, double theta_e, double n_e,
                                                     double b, double sin_th) {
-    const double j = synch_sin(P, nu, n_e, theta_e, b, sin_th) / (nu * nu);
-    return j / (b_nu_inv(nu, theta_e) + 1.0e-100);
+    return alpha_inv_abs_sin_l(P, nu, theta_e, n_e, b, sin_th, fm::log_(fmax(theta_e, 1.0e-300)));
 }
 
 /* reference bias_func, harm_model.cpp:1391-1404, with the generation's frozen statistics */
 __device__ __forceinline__ double bias_func(const GmParams &P, const GmBiasStats &s, double theta_e, double w) {
-    const double mx = 0.5 * w / kWeightMin;
-    const double avg_num_scatt = s.n_scatt / (1.0 * s.n_recorded + 1.0);
-    double bias = 100.0 * theta_e * theta_e / (P.bias_norm * s.max_tau_scatt * (avg_num_scatt + 2.0));
+    const double mx = fm::div(0.5 * w, kWeightMin);
+    const double avg_num_scatt = fm::div(s.n_scatt, 1.0 * s.n_recorded + 1.0);
+    double bias = fm::div(100.0 * theta_e * theta_e, P.bias_norm * s.max_tau_scatt * (avg_num_scatt + 2.0));
     bias = fmax(bias, kTpOverTe);
-    if (bias > mx)
-        bias = mx;
-    return bias / kTpOverTe;
+    bias = fmin(bias, mx);
+    return bias * (1.0 / kTpOverTe);
 }
 
 /* both opacities at once for a photon with wave-vector k in fluid f */
@@ -185,14 +217,15 @@ __device__ __forceinline__ void opacities(const GmParams &P, const double k[4], 
                                           double &alpha_scatt, double &alpha_abs) {
     double e_fluid, mu;
     fluid_frame(P, k, f, e_fluid, mu);
-    nu = e_fluid * kME * kCL * kCL / kHPL;
+    nu = fm::div(e_fluid * kME * kCL * kCL, kHPL);
     if (nu < 0.0 || isnan(nu)) {
         alpha_scatt = 0.0;
         alpha_abs = 0.0;
         return;
     }
-    alpha_scatt = alpha_inv_scatt(P, nu, f.theta_e, f.n_e);
-    alpha_abs = alpha_inv_abs_sin(P, nu, f.theta_e, f.n_e, f.b, sqrt(1.0 - mu * mu));
+    const double l_nu = fm::log_(nu), l_theta = fm::log_(f.theta_e);
+    alpha_scatt = alpha_inv_scatt_l(P, nu, f.theta_e, f.n_e, l_nu, l_theta);
+    alpha_abs = alpha_inv_abs_sin_l(P, nu, f.theta_e, f.n_e, f.b, fm::sqrt_(1.0 - mu * mu), l_theta);
 }
 
 } /* namespace gm */

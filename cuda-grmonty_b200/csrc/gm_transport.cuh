@@ -186,29 +186,43 @@ __device__ __forceinline__ bool queue_pop_warp(const TransportArgs &A, const Slo
 
 /* ---- small physics helpers ----------------------------------------------------------------------------------- */
 /* reference stop_criterion, harm_model.cpp:1589-1616 */
-__device__ __noinline__ bool stop_criterion_roulette(const GmParams *Pg, double x1, double &w, Rng &rng) {
-    /* cold part of stop_criterion: Russian roulette for light photons (draws from the photon's stream) */
+/* cold part of stop_criterion: Russian roulette for light photons (draws from the photon's stream).  Everything is
+ * passed and returned BY VALUE: a reference parameter of a non-inlined function would force the caller's live
+ * photon state (weight, RNG counter) into local memory for the whole loop. */
+struct RouletteResult {
+    double w;
+    uint32_t ctr;
+    int stop;
+};
+__device__ __noinline__ RouletteResult stop_criterion_roulette(const GmParams *Pg, double x1, double w, uint32_t id0,
+                                                               uint32_t id1, uint32_t id2, uint32_t ctr) {
     const GmParams &P = *Pg;
+    Rng rng = {id0, id1, id2, ctr};
+    RouletteResult r;
+    const double u = rng_uniform(P, rng);
+    r.ctr = rng.ctr;
     if (x1 > P.x1_max) {
-        if (rng_uniform(P, rng) <= 1.0 / kRoulette)
-            w *= kRoulette;
-        else
-            w = 0.0;
-        return true;
+        r.w = (u <= 1.0 / kRoulette) ? w * kRoulette : 0.0;
+        r.stop = 1;
+    } else if (u <= 1.0 / kRoulette) {
+        r.w = w * kRoulette;
+        r.stop = 0;
+    } else {
+        r.w = 0.0;
+        r.stop = 1;
     }
-    if (rng_uniform(P, rng) <= 1.0 / kRoulette) {
-        w *= kRoulette;
-        return false;
-    }
-    w = 0.0;
-    return true;
+    return r;
 }
 
 __device__ __forceinline__ bool stop_criterion_fast(const TransportArgs &A, double x1, double &w, Rng &rng) {
     if (x1 < A.P.x1_min)
         return true;
-    if (w < kWeightMin)
-        return stop_criterion_roulette(&A.self->P, x1, w, rng);
+    if (w < kWeightMin) {
+        const RouletteResult r = stop_criterion_roulette(&A.self->P, x1, w, rng.id0, rng.id1, rng.id2, rng.ctr);
+        w = r.w;
+        rng.ctr = r.ctr;
+        return r.stop != 0;
+    }
     return x1 > A.P.x1_max;
 }
 
@@ -237,9 +251,8 @@ __device__ __forceinline__ bool stop_criterion(const GmParams &P, double x1, dou
 
 /* exp(-dtau) with the reference's 4th-order series below 1e-3 (harm_model.cpp:998-1002, :1047-1051) */
 __device__ __forceinline__ double attenuation(double d_tau, bool use_series) {
-    if (use_series)
-        return 1.0 - d_tau / 24.0 * (24.0 - d_tau * (12.0 - d_tau * (4.0 - d_tau)));
-    return exp(-d_tau);
+    const double series = 1.0 - d_tau * (1.0 / 24.0) * (24.0 - d_tau * (12.0 - d_tau * (4.0 - d_tau)));
+    return use_series ? series : fm::exp_(-d_tau);
 }
 
 /* start-of-track quantities at a position where geometry and fluid are known
@@ -406,19 +419,20 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
     Fluid f;
     fluid_params(P, L.x[1], L.x[2], g, q, f);
     const bool bound = (f.n_e == 0.0);
-    double nu = 0.0, mu = 0.0;
-    if (!bound) {
-        double e_fluid;
+    double e_fluid = 0.0, mu = 0.0;
+    if (!bound)
         fluid_frame(P, L.k, f, e_fluid, mu);
-        nu = e_fluid * kME * kCL * kCL / kHPL;
-    }
+    const double nu = bound ? 0.0 : fm::div(e_fluid * kME * kCL * kCL, kHPL);
     const bool outside = bound || nu < 0.0;
     /* evaluate the opacities for every lane (harmless dummy arguments outside the fluid) so that the warp
-     * stays converged through the expensive part */
-    const double nu_e = outside ? 1.0e12 : nu, te_e = outside ? 1.0 : f.theta_e, ne_e = outside ? 1.0 : f.n_e;
+     * stays converged through the expensive part; the three logarithms (nu, theta_e, and the interaction
+     * draw below) are independent and interleave */
+    const double nu_e = (outside || !(nu > 0.0)) ? 1.0e12 : nu;
+    const double te_e = outside ? 1.0 : f.theta_e, ne_e = outside ? 1.0 : f.n_e;
     const double b_e = outside ? 1.0 : f.b;
-    const double a_sf = alpha_inv_scatt(P, nu_e, te_e, ne_e);
-    const double a_af = alpha_inv_abs_sin(P, nu_e, te_e, ne_e, b_e, sqrt(1.0 - mu * mu));
+    const double l_nu = fm::log_(nu_e), l_theta = fm::log_(te_e);
+    const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta);
+    const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta);
     const double bf = bias_func(P, A.bias, te_e, L.w);
     double d_tau_scatt, d_tau_abs, bias;
     if (outside) {
@@ -437,13 +451,14 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         L.bi = bf;
     }
     L.ne_pos = f.n_e > 0.0;
-    const double x1r = -log(rng_uniform(P, L.rng));
-    const double w_child = L.w / bias;
+    const double x1r = -fm::log_(rng_uniform(P, L.rng));
+    /* w / bias; bias == 0 gives +inf in the reference (Appendix A.3), which the scatter test below rejects */
+    const double w_child = bias > 0.0 ? fm::div(L.w, bias) : fm::from_bits(0x7ff0000000000000ull);
     StepResult res = STEP_CONTINUE;
     if (bias * d_tau_scatt > x1r && w_child > kWeightMin) {
         /* ---- the photon scatters in this step (reference :985-1005): park it ---- */
         const Rng crng = rng_child(P, L.rng);
-        const double frac = x1r / (bias * d_tau_scatt);
+        const double frac = fm::div(x1r, bias * d_tau_scatt);
         d_tau_abs *= frac;
         if (d_tau_abs > 100) {
             L.status |= 4;
@@ -524,7 +539,9 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, u
         /* below the grid's inner edge push_photon is a silent no-op (:1218-1220): the attempt is computed but
          * discarded, so that the warp does not diverge (it happens only inside the horizon) */
         const bool noop = L.x[1] < P.x_start1;
-        const bool fail = push_attempt(P, L.x, L.k, L.dk, ldexp(L.dl, -L.level), L.e_0_s, xn, kn, dkn, e1, q);
+        /* dl / 2^level: an exact scaling */
+        const double dl_now = L.dl * fm::from_bits((uint64_t)(1023 - L.level) << 52);
+        const bool fail = push_attempt(P, L.x, L.k, L.dk, dl_now, L.e_0_s, xn, kn, dkn, e1, q);
         bool accept = true;
         if (!noop) {
             ++wk.attempts;
@@ -598,26 +615,35 @@ __device__ __forceinline__ void pool_store_hot(const PhotonPool &pool, unsigned 
 
 /* Suspend a live photon at a step boundary: its complete hot state goes back to its pool record and the record
  * is put on the carry queue; the host moves carried records into the next generation's batch. */
-__device__ __noinline__ void suspend_photon(const TransportArgs *Ag, unsigned int slot, const double *x,
-                                            const double *k, const double *dk, double w, double e_0_s,
+__device__ __noinline__ void suspend_photon(const TransportArgs *Ag, unsigned int slot, double x0, double x1,
+                                            double x2, double x3, double k0, double k1, double k2, double k3,
+                                            double dk0, double dk1, double dk2, double dk3, double w, double e_0_s,
                                             double tau_abs, double tau_scatt, double alpha_scatt, double alpha_abs,
-                                            double bi, bool ne_pos, Rng rng, int n_step) {
+                                            double bi, bool ne_pos, uint32_t id0, uint32_t id1, uint32_t id2,
+                                            uint32_t ctr, int n_step) {
+    /* all arguments by value (see stop_criterion_roulette) */
     const TransportArgs &A = *Ag;
     TrackInit t;
     t.alpha_scatt = alpha_scatt;
     t.alpha_abs = alpha_abs;
     t.bi = bi;
     t.ne_pos = ne_pos;
+    const double x[4] = {x0, x1, x2, x3}, k[4] = {k0, k1, k2, k3}, dk[4] = {dk0, dk1, dk2, dk3};
+    const Rng rng = {id0, id1, id2, ctr};
     pool_store_hot(A.pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, t, rng, n_step);
     __stcg(A.pool.gclock + slot, 0);
     queue_push(A, A.carry, slot);
 }
 
 /* The scattering stage for one parked photon (reference harm_model.cpp:1005-1039 + scatter_super_photon).
- * Called with all lanes of a warp holding a parked photon (or idle).  Returns the number of photons whose
- * life ended here (0 or 1); the parent and the child that continue are pushed on the ready queue. */
-__device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int slot, unsigned int &n_attempts,
-                                          unsigned int &n_scatters, unsigned int &n_children) {
+ * Called with all lanes of a warp holding a parked photon (or idle).  The parent and the child that continue
+ * are pushed on the ready queue. */
+struct ScatterStageResult {
+    int done;                                  /* photons whose life ended here (0 or 1) */
+    unsigned int attempts, scatters, children; /* work counters, returned by value (see stop_criterion_roulette) */
+};
+__device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag, unsigned int slot) {
+    unsigned int n_attempts = 0, n_scatters = 0, n_children = 0;
     const TransportArgs &A = *Ag;
     const GmParams &P = A.P;
     const PhotonPool &pool = A.pool;
@@ -656,7 +682,8 @@ __device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int 
         if (w < 1.0e-100) {
             if (A.D.status && slot < A.D.n)
                 A.D.status[slot] = 4 | 2;
-            return 1; /* k could not be put back on the light cone (:1018-1021): dropped */
+            return ScatterStageResult{1, n_attempts, n_scatters, n_children}; /* k could not be put back on the light
+                                                                                * cone (:1018-1021): dropped */
         }
         if (child_ok) {
             unsigned int cs;
@@ -697,12 +724,12 @@ __device__ __noinline__ int scatter_stage(const TransportArgs *Ag, unsigned int 
     if (n_step > kMaxNStep) {
         if (A.D.status && slot < A.D.n)
             atomicOr(A.D.status + slot, 4);
-        return 1;
+        return ScatterStageResult{1, n_attempts, n_scatters, n_children};
     }
     pool_store_hot(pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, ti, rng, n_step);
     __stcg(pool.gclock + slot, clock);
     queue_push(A, A.ready, slot);
-    return 0;
+    return ScatterStageResult{0, n_attempts, n_scatters, n_children};
 }
 
 } /* namespace gm */

@@ -253,14 +253,17 @@ def gen_samplers():
     print("wrote samplers.npz", file=sys.stderr)
 
 
-def gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e19,)):
+def gen_spectrum(photon_n=100000, seeds=8, mass_units=(4e19,), first_seed=0, merge=False):
+    """`seeds` runs of the reference CLI (seed 123 + first_seed + s), each a complete run at `photon_n`
+    (BASELINE.json configs[0]); merge=True appends to the existing fixture (more seeds = less Monte Carlo
+    noise in the reference ensemble)."""
     tmp = tempfile.mkdtemp()
     dump = os.path.join(tmp, "dump192.txt")
     header, table = make_harm_dump.make_dump()
     make_harm_dump.write_dump(dump, header, table)
     for mu in mass_units:
         procs = []
-        for s in range(seeds):
+        for s in range(first_seed, first_seed + seeds):
             sb = os.path.join(tmp, f"spec_{s}.bin")
             cmd = [rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit", repr(mu),
                    "--seed", str(123 + s), "--hotcross_cache", rh.HOTCROSS_CACHE, "--spectrum_bin", sb]
@@ -271,7 +274,7 @@ def gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e19,)):
             metas.append(json.loads(o.strip().splitlines()[-1]))
             specs.append(np.fromfile(sb).reshape(6, 200, 13))
         specs = np.array(specs)
-        out = dict(photon_n=np.array(photon_n), mass_unit=np.array(mu), seeds=np.array(seeds),
+        out = dict(photon_n=np.array(photon_n), mass_unit=np.array(mu), seeds=np.array(first_seed + seeds),
                    created=np.array([m["created"] for m in metas]),
                    scattered=np.array([m["scattered"] for m in metas]),
                    recorded=np.array([m["recorded"] for m in metas]),
@@ -280,6 +283,11 @@ def gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e19,)):
                    # per-seed: dn_dle, de_dle, nph, nscatt, tau_abs, tau_scatt (fields 0,1,2,3,7,8)
                    spec=specs[:, :, :, [0, 1, 2, 3, 7, 8]].astype(np.float64))
         name = f"spectrum_192_{mu:.0e}.npz".replace("+", "")
+        if merge and os.path.exists(os.path.join(GOLD, name)):
+            old = dict(np.load(os.path.join(GOLD, name)))
+            assert int(old["photon_n"]) == photon_n and int(old["seeds"]) == first_seed
+            for k in ("created", "scattered", "recorded", "run_s", "max_tau_scatt", "spec"):
+                out[k] = np.concatenate([old[k], out[k]])
         np.savez_compressed(os.path.join(GOLD, name), **out)
         print("wrote", name, "rates", out["created"] / out["run_s"], file=sys.stderr)
 
@@ -292,6 +300,9 @@ if __name__ == "__main__":
         gen_samplers()
     elif what == "spectrum":
         gen_spectrum()
+    elif what == "spectrum_more":  # spectrum_more <first_seed> <n> [mass_unit]
+        gen_spectrum(first_seed=int(sys.argv[2]), seeds=int(sys.argv[3]), merge=True,
+                     mass_units=(float(sys.argv[4]),) if len(sys.argv) > 4 else (4e19,))
     elif what == "spectrum_file":
         pass  # handled at the end of the file
     else:

@@ -113,7 +113,13 @@ def test_radiation(ctx, golden):
     for col, key in enumerate(["rad_alpha_scatt", "rad_alpha_abs", "rad_synch", "rad_k2", "rad_f"]):
         want = golden[key]
         nz = want != 0
-        assert np.all(got[~nz, col] == 0.0), key
+        # where the reference returns exactly 0 so do we -- except that alpha_abs is evaluated here as
+        # j / (nu^2 (B + 1e-100)) and does not underflow where the reference's intermediate j / nu^2 does
+        assert np.all(np.abs(got[~nz, col]) < (1e-200 if key == "rad_alpha_abs" else 1e-320)), key
+        if key == "rad_alpha_abs":
+            # ... and where that intermediate is denormal (2 of the 230 non-zero vectors: 5e-319, 3e-316) the
+            # reference's own value has lost up to 16 bits; compare where it is a normal number
+            nz &= golden["rad_synch"] / golden["rad_args"][:, 0] ** 2 > 2.3e-308
         assert np.max(np.abs(got[nz, col] / want[nz] - 1)) < 1e-11, key
     hc = ctx.t_hotcross(golden["hc_args"])
     assert np.max(np.abs(hc / golden["hc_lkup"] - 1)) < 1e-12
