@@ -99,6 +99,7 @@ class Config(C.Structure):
         ("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32),
         ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
         ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64), ("gen_budget", C.c_int64),
+        ("gen_fine_from", C.c_int64), ("gen_fine_div", C.c_int64),
     ]
 
 
@@ -175,10 +176,10 @@ class Context:
 
     def __init__(self, model: dict, seed: int = 123, rank: int = 0, world: int = 1, device: int = 0,
                  threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
-                 gen_cap: int = 0, gen_budget: int = 0):
+                 gen_cap: int = 0, gen_budget: int = 0, gen_fine_from: int = 0, gen_fine_div: int = 0):
         self.L = lib()
         cfg = Config()
-        cfg.abi_version = 1
+        cfg.abi_version = 2
         cfg.struct_size = C.sizeof(Config)
         cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
         for k in self.SCALARS:
@@ -198,6 +199,7 @@ class Context:
         cfg.seed, cfg.rank, cfg.world, cfg.device = seed, rank, world, device
         cfg.threads_per_block, cfg.blocks_per_sm = threads_per_block, blocks_per_sm
         cfg.queue_capacity, cfg.gen0, cfg.gen_cap, cfg.gen_budget = queue_capacity, gen0, gen_cap, gen_budget
+        cfg.gen_fine_from, cfg.gen_fine_div = gen_fine_from, gen_fine_div
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))
@@ -374,7 +376,7 @@ def host_lib():
         H.gmh_init.argtypes = [C.c_void_p, C.c_int]
         H.gmh_init_stage.argtypes = [C.c_void_p, C.c_int, C.c_int]
         H.gmh_set_options.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
-                                      C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_char_p]
+                                      C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_char_p]
         H.gmh_run_simulation.argtypes = [C.c_void_p]
         H.gmh_report_spectrum.argtypes = [C.c_void_p, C.c_char_p]
         for n in ("gmh_get_header", "gmh_get_header_raw", "gmh_get_units", "gmh_get_scalars", "gmh_get_spectrum",
@@ -423,10 +425,11 @@ class HarmModel:
         self._ck(self.H.gmh_init_stage(self.h, which, threads))
 
     def set_options(self, seed=123, rank=0, world=1, device=0, threads_per_block=0, blocks_per_sm=0,
-                    queue_capacity=0, gen0=0, gen_cap=0, gen_budget=0, nccl_comm=None, cuda_library=None):
+                    queue_capacity=0, gen0=0, gen_cap=0, gen_budget=0, gen_fine_from=0, gen_fine_div=0,
+                    nccl_comm=None, cuda_library=None):
         lib_path = (cuda_library or LIB_CUDA).encode()
         self.H.gmh_set_options(self.h, seed, rank, world, device, threads_per_block, blocks_per_sm, queue_capacity,
-                               gen0, gen_cap, gen_budget, nccl_comm, lib_path)
+                               gen0, gen_cap, gen_budget, gen_fine_from, gen_fine_div, nccl_comm, lib_path)
 
     def run_simulation(self):
         self._ck(self.H.gmh_run_simulation(self.h))

@@ -56,7 +56,7 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
-    long long gen0 = 32, gen_cap = 1 << 20;
+    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 4;
     grmonty_b200_stats stats{};
     std::string err;
 };
@@ -99,7 +99,8 @@ struct Variant {
 };
 static const Variant kVariants[] = {
     {128, 2, transport_kernel<128, 2>}, {128, 3, transport_kernel<128, 3>}, {128, 4, transport_kernel<128, 4>},
-    {256, 1, transport_kernel<256, 1>}, {64, 4, transport_kernel<64, 4>},
+    {256, 1, transport_kernel<256, 1>}, {64, 4, transport_kernel<64, 4>},   {384, 1, transport_kernel<384, 1>},
+    {512, 1, transport_kernel<512, 1>}, {192, 2, transport_kernel<192, 2>},
 };
 static const Variant *find_variant(int block, int min_blocks) {
     for (const Variant &v : kVariants)
@@ -341,6 +342,10 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             ctx->gen0 = cfg->gen0;
         if (cfg->gen_cap > 0)
             ctx->gen_cap = cfg->gen_cap;
+        if (cfg->gen_fine_from > 0)
+            ctx->gen_fine_from = cfg->gen_fine_from;
+        if (cfg->gen_fine_div != 0)
+            ctx->gen_fine_div = cfg->gen_fine_div;
         return GRMONTY_B200_OK;
     }();
     if (rc != GRMONTY_B200_OK) {
@@ -383,10 +388,18 @@ int grmonty_b200_total_primaries(grmonty_b200_ctx *ctx, int64_t *total) {
     return GRMONTY_B200_OK;
 }
 
-static long long generation_size(long long g, long long gen0, long long cap) {
-    long long s = gen0;
-    for (long long i = 0; i < g && s < cap; ++i)
-        s *= 2;
+/* size of the generation starting at run position g_start (same rule as the oracle's orc_generation_size;
+ * documented at grmonty_b200_config::gen0) */
+static long long generation_size(long long g_start, long long gen0, long long cap, long long fine_from,
+                                 long long fine_div) {
+    long long s;
+    if (g_start < gen0)
+        s = gen0;
+    else if (g_start < fine_from || fine_div <= 1)
+        s = g_start;
+    else
+        s = g_start / fine_div;
+    s = std::max(s, gen0);
     return std::min(s, cap);
 }
 
@@ -553,7 +566,8 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
     unsigned long long created = 0;
     GmBiasStats bias;
     for (long long g = 0; g_start < last; ++g) {
-        const long long g_end = g_start + generation_size(g, ctx->gen0, ctx->gen_cap);
+        const long long g_end =
+            g_start + generation_size(g_start, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from, ctx->gen_fine_div);
         const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
         if (lo < hi) {
             long long f0 = lo + ((rank - lo % world) % world + world) % world; /* first index >= lo, = rank mod world */

@@ -51,7 +51,7 @@ int gmh_init_stage(void *h, int which, int threads) {
 }
 int gmh_set_options(void *h, uint64_t seed, int rank, int world, int device, int threads_per_block,
                     int blocks_per_sm, int64_t queue_capacity, int64_t gen0, int64_t gen_cap, int64_t gen_budget,
-                    void *nccl_comm,
+                    int64_t gen_fine_from, int64_t gen_fine_div, void *nccl_comm,
                     const char *cuda_library) {
     auto &o = static_cast<HARMModel *>(h)->options;
     o.seed = seed;
@@ -64,6 +64,8 @@ int gmh_set_options(void *h, uint64_t seed, int rank, int world, int device, int
     o.gen0 = gen0;
     o.gen_cap = gen_cap;
     o.gen_budget = gen_budget;
+    o.gen_fine_from = gen_fine_from;
+    o.gen_fine_div = gen_fine_div;
     o.nccl_comm = nccl_comm;
     o.cuda_library = cuda_library ? cuda_library : "";
     return 0;

@@ -637,6 +637,8 @@ void HARMModel::run_simulation() {
     cfg.gen0 = options.gen0;
     cfg.gen_cap = options.gen_cap;
     cfg.gen_budget = options.gen_budget;
+    cfg.gen_fine_from = options.gen_fine_from;
+    cfg.gen_fine_div = options.gen_fine_div;
 
     grmonty_b200_ctx *ctx = nullptr;
     if (L.create(&ctx, &cfg) != 0)

@@ -57,7 +57,7 @@ struct RunOptions {
     uint64_t seed = 123; /* reference consts::rng_seed, main.cpp:49 */
     int rank = 0, world = 1, device = 0;
     int threads_per_block = 0, blocks_per_sm = 0;
-    int64_t queue_capacity = 0, gen0 = 0, gen_cap = 0, gen_budget = 0;
+    int64_t queue_capacity = 0, gen0 = 0, gen_cap = 0, gen_budget = 0, gen_fine_from = 0, gen_fine_div = 0;
     void *nccl_comm = nullptr; /* ncclComm_t for world > 1 (optional: the caller may reduce by other means) */
     std::string cuda_library;  /* path of libgrmonty_b200.so; empty: $GRMONTY_B200_LIB or next to this library */
 };

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRMONTY_B200_ABI_VERSION 1
+#define GRMONTY_B200_ABI_VERSION 2
 
 #define GRMONTY_B200_N_TH_BINS 6     /* reference consts.hpp:26 */
 #define GRMONTY_B200_N_E_BINS 200    /* reference consts.hpp:25 */
@@ -95,10 +95,18 @@ typedef struct grmonty_b200_config {
     int32_t threads_per_block;
     int32_t blocks_per_sm;
     int64_t queue_capacity; /* photon slots in the device queue */
-    int64_t gen0;           /* positions in the first generation (default 32); doubles each generation ... */
-    int64_t gen_cap;        /* ... up to this cap (default 2^20).  Bias statistics are frozen within a generation. */
+    /* Generation schedule.  The scattering-bias statistics are frozen within a generation, so the generations
+     * must stay short relative to the run so far (the reference updates its statistics after every photon):
+     * the generation starting at run position s holds gen0 positions if s < gen0, s positions (the cumulative
+     * count doubles) while s < gen_fine_from, then s / gen_fine_div positions, and never more than gen_cap. */
+    int64_t gen0;           /* default 32 */
+    int64_t gen_cap;        /* default 2^20 */
     int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over
                                to the next one (default 256); bounds the tail of every generation */
+    int64_t gen_fine_from;  /* default 16384 */
+    int64_t gen_fine_div;   /* default 4 (each generation adds 25 % to the run so far); <= 1: keep doubling.
+                               Measured at configs[0] against 20 reference runs (profiles/r1_bias_schedule.txt):
+                               doubling gives +5.8 % scattered / +2.5 % recorded counts, div 4 +0.3 % / -0.05 %. */
 } grmonty_b200_config;
 
 /* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */
