@@ -117,7 +117,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = [
     "grmonty_b200_create", "grmonty_b200_total_primaries", "grmonty_b200_run_range", "grmonty_b200_run",
     "grmonty_b200_allreduce", "grmonty_b200_device_accumulators", "grmonty_b200_result", "grmonty_b200_reset",
-    "grmonty_b200_destroy", "grmonty_b200_last_error", "grmonty_b200_fp64_peak",
+    "grmonty_b200_destroy", "grmonty_b200_trim_cache", "grmonty_b200_last_error", "grmonty_b200_fp64_peak",
     "grmonty_b200_test_geometry", "grmonty_b200_test_dkdlam_step", "grmonty_b200_test_push_photon",
     "grmonty_b200_test_trajectory", "grmonty_b200_test_fluid_params", "grmonty_b200_test_radiation",
     "grmonty_b200_test_hotcross", "grmonty_b200_test_angles", "grmonty_b200_test_tetrad",

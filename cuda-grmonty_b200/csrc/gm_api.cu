@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,19 @@
 #include "gm_kernels.cuh"
 
 using namespace gm;
+
+/* Device memory of a destroyed context, kept for the next context on the same device.  Every device buffer of a
+ * context is carved out of ONE cudaMalloc block; cudaFree costs 10 - 100 ms per call on the B200 boxes and 0.2 - 1.4 s
+ * for the photon pool (measured, profiles/r1_e2e_split.txt) -- more than the whole transport of 16 M superphotons --
+ * so destroy parks the block here (one per device) and create reuses it when it is large enough.
+ * grmonty_b200_trim_cache() really frees it. */
+struct DeviceArena {
+    int device = -1;
+    char *base = nullptr;
+    size_t bytes = 0;
+};
+static std::mutex g_arena_mutex;
+static std::vector<DeviceArena> g_arena_cache;
 
 struct grmonty_b200_ctx {
     grmonty_b200_config cfg;
@@ -42,6 +56,8 @@ struct grmonty_b200_ctx {
     SlotQueue carry{};
     PhotonPool stage{}; /* staging pool: suspended photons between two batches */
     unsigned long long n_carry = 0; /* records in `stage` waiting for the next batch */
+    DeviceArena arena;     /* the one device allocation all buffers below live in */
+    size_t arena_used = 0;
     int budget = 256;               /* attempts a lineage may make per generation */
     unsigned long long *d_qctr = nullptr; /* n_alloc, finished, ready head/tail, scatter head/tail, carry head/tail */
     unsigned long long used_ready = 0, used_scatter = 0, used_carry = 0; /* entries to clear before the next batch */
@@ -84,11 +100,23 @@ static int fail(grmonty_b200_ctx *c, int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                                  \
     } while (0)
 
-template <typename T> static cudaError_t upload(T **dst, const T *src, size_t n) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dst), n * sizeof(T));
+/* bump allocation inside the context's arena (256-byte aligned); sizes are summed by arena_bytes_needed() first */
+static void *arena_take(grmonty_b200_ctx *ctx, size_t bytes) {
+    const size_t off = (ctx->arena_used + 255) & ~(size_t)255;
+    if (off + bytes > ctx->arena.bytes)
+        return nullptr;
+    ctx->arena_used = off + bytes;
+    return ctx->arena.base + off;
+}
+template <typename T> static cudaError_t arena_alloc(grmonty_b200_ctx *ctx, T **dst, size_t n) {
+    *dst = static_cast<T *>(arena_take(ctx, n * sizeof(T)));
+    return *dst ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+template <typename T> static cudaError_t upload(grmonty_b200_ctx *ctx, T **dst, const T *src, size_t n) {
+    cudaError_t e = arena_alloc(ctx, dst, n);
     if (e != cudaSuccess)
         return e;
-    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
 }
 
 /* ---- kernel dispatch over the compiled (block, min-blocks) variants ------------------------------------- */
@@ -190,23 +218,61 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         P.spec_l_e_0 = std::log(1.0e-12);
         P.nz_max = cfg->photon_n * std::log(kNuMax / kNuMin);
 
-        /* ---- model upload: primitives interleaved [n0][n1][8] ---- */
+        /* ---- one device arena for everything (reused from the cache when possible) ---- */
         const size_t nz = (size_t)cfg->n0 * cfg->n1;
+        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 22);
+        if (cap > 0x3fffffffull)
+            cap = 0x3fffffffull; /* slots are addressed with 32 bits */
+        const unsigned long long stage_cap = std::max<unsigned long long>(1024, cap / 2);
+        ctx->ready.capacity = (unsigned int)std::min<unsigned long long>(2 * cap, 0x7fffffffull);
+        ctx->scatter.capacity = (unsigned int)cap;
+        ctx->carry.capacity = (unsigned int)stage_cap;
+        {
+            const size_t per_slot = (size_t)P_NFIELDS * sizeof(double) + 2 * sizeof(uint4) + 3 * sizeof(int);
+            size_t need = nz * (8 + 1 + 1) * sizeof(double) + nz * sizeof(ZoneData) + (2 * nz + 1) * sizeof(long long) +
+                          (size_t)(GRMONTY_B200_HOTCROSS_N + 3 * GRMONTY_B200_TABLE_N + 2 * GRMONTY_B200_NINT_N) *
+                              sizeof(double) +
+                          per_slot * (cap + stage_cap) +
+                          ((size_t)ctx->ready.capacity + ctx->scatter.capacity + ctx->carry.capacity) *
+                              sizeof(unsigned int) +
+                          (size_t)kNThBins * kNEBins * kSpecFields * sizeof(double) + sizeof(TransportArgs) + 4096;
+            need += 64 * 256; /* alignment padding of the ~40 sub-allocations */
+            {
+                std::lock_guard<std::mutex> lock(g_arena_mutex);
+                for (size_t i = 0; i < g_arena_cache.size(); ++i)
+                    if (g_arena_cache[i].device == ctx->device && g_arena_cache[i].bytes >= need &&
+                        g_arena_cache[i].bytes <= need + need / 2) {
+                        ctx->arena = g_arena_cache[i];
+                        g_arena_cache.erase(g_arena_cache.begin() + i);
+                        break;
+                    }
+            }
+            if (!ctx->arena.base) {
+                void *b = nullptr;
+                CK(cudaMalloc(&b, need));
+                ctx->arena.device = ctx->device;
+                ctx->arena.base = static_cast<char *>(b);
+                ctx->arena.bytes = need;
+            }
+            ctx->arena_used = 0;
+        }
+
+        /* ---- model upload: primitives interleaved [n0][n1][8] ---- */
         {
             std::vector<double> inter(nz * 8);
             const double *src[8] = {cfg->k_rho, cfg->u, cfg->u_1, cfg->u_2, cfg->u_3, cfg->b_1, cfg->b_2, cfg->b_3};
             for (size_t z = 0; z < nz; ++z)
                 for (int v = 0; v < 8; ++v)
                     inter[z * 8 + v] = src[v][z];
-            CK(upload(&ctx->d_grid, inter.data(), nz * 8));
+            CK(upload(ctx, &ctx->d_grid, inter.data(), nz * 8));
         }
-        CK(upload(&ctx->d_det, cfg->geom_det, nz));
-        CK(upload(&ctx->d_hotcross, cfg->hotcross, (size_t)GRMONTY_B200_HOTCROSS_N));
-        CK(upload(&ctx->d_f, cfg->f, (size_t)GRMONTY_B200_TABLE_N));
-        CK(upload(&ctx->d_k2, cfg->k2, (size_t)GRMONTY_B200_TABLE_N));
-        CK(upload(&ctx->d_weight, cfg->weight, (size_t)GRMONTY_B200_TABLE_N));
-        CK(upload(&ctx->d_nint, cfg->nint, (size_t)GRMONTY_B200_NINT_N));
-        CK(upload(&ctx->d_dnmax, cfg->dndlnu_max, (size_t)GRMONTY_B200_NINT_N));
+        CK(upload(ctx, &ctx->d_det, cfg->geom_det, nz));
+        CK(upload(ctx, &ctx->d_hotcross, cfg->hotcross, (size_t)GRMONTY_B200_HOTCROSS_N));
+        CK(upload(ctx, &ctx->d_f, cfg->f, (size_t)GRMONTY_B200_TABLE_N));
+        CK(upload(ctx, &ctx->d_k2, cfg->k2, (size_t)GRMONTY_B200_TABLE_N));
+        CK(upload(ctx, &ctx->d_weight, cfg->weight, (size_t)GRMONTY_B200_TABLE_N));
+        CK(upload(ctx, &ctx->d_nint, cfg->nint, (size_t)GRMONTY_B200_NINT_N));
+        CK(upload(ctx, &ctx->d_dnmax, cfg->dndlnu_max, (size_t)GRMONTY_B200_NINT_N));
         P.grid = ctx->d_grid;
         P.geom_det = ctx->d_det;
         P.hotcross = ctx->d_hotcross;
@@ -238,10 +304,10 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         }
 
         /* ---- per-zone emission data and the zone -> primary index prefix ---- */
-        CK(cudaMalloc(&ctx->d_zones, nz * sizeof(ZoneData)));
-        CK(cudaMalloc(&ctx->d_num, nz * sizeof(long long)));
-        CK(cudaMalloc(&ctx->d_nz, nz * sizeof(double)));
-        CK(cudaMalloc(&ctx->d_prefix, (nz + 1) * sizeof(long long)));
+        CK(arena_alloc(ctx, &ctx->d_zones, nz));
+        CK(arena_alloc(ctx, &ctx->d_num, nz));
+        CK(arena_alloc(ctx, &ctx->d_nz, nz));
+        CK(arena_alloc(ctx, &ctx->d_prefix, nz + 1));
         zone_kernel<<<(unsigned)((nz + 127) / 128), 128, 0, ctx->stream>>>(P, ctx->d_zones, ctx->d_nz, ctx->d_num);
         CK(cudaGetLastError());
         std::vector<long long> num(nz);
@@ -272,32 +338,26 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         CK(cudaMemcpy(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice));
 
         /* ---- photon pool and stage queues ---- */
-        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 22);
-        if (cap > 0x3fffffffull)
-            cap = 0x3fffffffull; /* slots are addressed with 32 bits */
         auto alloc_pool = [&](PhotonPool &pl, unsigned long long c) -> cudaError_t {
             pl.capacity = (unsigned int)c;
             cudaError_t e;
-            if ((e = cudaMalloc(&pl.f, (size_t)P_NFIELDS * c * sizeof(double))) != cudaSuccess) return e;
-            if ((e = cudaMalloc(&pl.rng, c * sizeof(uint4))) != cudaSuccess) return e;
-            if ((e = cudaMalloc(&pl.crng, c * sizeof(uint4))) != cudaSuccess) return e;
-            if ((e = cudaMalloc(&pl.n_scatt, c * sizeof(int))) != cudaSuccess) return e;
-            if ((e = cudaMalloc(&pl.n_step, c * sizeof(int))) != cudaSuccess) return e;
-            return cudaMalloc(&pl.gclock, c * sizeof(int));
+            if ((e = arena_alloc(ctx, &pl.f, (size_t)P_NFIELDS * c)) != cudaSuccess) return e;
+            if ((e = arena_alloc(ctx, &pl.rng, c)) != cudaSuccess) return e;
+            if ((e = arena_alloc(ctx, &pl.crng, c)) != cudaSuccess) return e;
+            if ((e = arena_alloc(ctx, &pl.n_scatt, c)) != cudaSuccess) return e;
+            if ((e = arena_alloc(ctx, &pl.n_step, c)) != cudaSuccess) return e;
+            return arena_alloc(ctx, &pl.gclock, c);
         };
         CK(alloc_pool(ctx->pool, cap));
-        CK(alloc_pool(ctx->stage, std::max<unsigned long long>(1024, cap / 2)));
-        ctx->ready.capacity = (unsigned int)std::min<unsigned long long>(2 * cap, 0x7fffffffull);
-        ctx->scatter.capacity = (unsigned int)cap;
-        ctx->carry.capacity = ctx->stage.capacity;
-        CK(cudaMalloc(&ctx->ready.entries, (size_t)ctx->ready.capacity * sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->scatter.entries, (size_t)ctx->scatter.capacity * sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->carry.entries, (size_t)ctx->carry.capacity * sizeof(unsigned int)));
-        CK(cudaMemset(ctx->ready.entries, 0, (size_t)ctx->ready.capacity * sizeof(unsigned int)));
-        CK(cudaMemset(ctx->scatter.entries, 0, (size_t)ctx->scatter.capacity * sizeof(unsigned int)));
-        CK(cudaMemset(ctx->carry.entries, 0, (size_t)ctx->carry.capacity * sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->d_qctr, 8 * sizeof(unsigned long long)));
-        CK(cudaMemset(ctx->d_qctr, 0, 8 * sizeof(unsigned long long)));
+        CK(alloc_pool(ctx->stage, stage_cap));
+        CK(arena_alloc(ctx, &ctx->ready.entries, (size_t)ctx->ready.capacity));
+        CK(arena_alloc(ctx, &ctx->scatter.entries, (size_t)ctx->scatter.capacity));
+        CK(arena_alloc(ctx, &ctx->carry.entries, (size_t)ctx->carry.capacity));
+        CK(cudaMemsetAsync(ctx->ready.entries, 0, (size_t)ctx->ready.capacity * sizeof(unsigned int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->scatter.entries, 0, (size_t)ctx->scatter.capacity * sizeof(unsigned int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->carry.entries, 0, (size_t)ctx->carry.capacity * sizeof(unsigned int), ctx->stream));
+        CK(arena_alloc(ctx, &ctx->d_qctr, 8));
+        CK(cudaMemsetAsync(ctx->d_qctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
         ctx->pool.n_alloc = ctx->d_qctr;
         ctx->pool.finished = ctx->d_qctr + 1;
         ctx->ready.head = ctx->d_qctr + 2;
@@ -311,12 +371,12 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
 
         /* ---- accumulators ---- */
         const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
-        CK(cudaMalloc(&ctx->d_spectrum, nspec * sizeof(double)));
-        CK(cudaMalloc(&ctx->d_counters, 3 * sizeof(unsigned long long)));
-        CK(cudaMalloc(&ctx->d_maxtau, sizeof(unsigned long long)));
-        CK(cudaMalloc(&ctx->d_work, 8 * sizeof(unsigned long long)));
-        CK(cudaMalloc(&ctx->d_error, sizeof(unsigned int)));
-        CK(cudaMalloc(&ctx->d_args, sizeof(TransportArgs)));
+        CK(arena_alloc(ctx, &ctx->d_spectrum, nspec));
+        CK(arena_alloc(ctx, &ctx->d_counters, 3));
+        CK(arena_alloc(ctx, &ctx->d_maxtau, 1));
+        CK(arena_alloc(ctx, &ctx->d_work, 8));
+        CK(arena_alloc(ctx, &ctx->d_error, 1));
+        CK(arena_alloc(ctx, &ctx->d_args, 1));
         ctx->A.spectrum = ctx->d_spectrum;
         ctx->A.counters = ctx->d_counters;
         ctx->A.max_tau_bits = ctx->d_maxtau;
@@ -705,15 +765,20 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
     if (!ctx)
         return;
     cudaSetDevice(ctx->device);
-    void *bufs[] = {ctx->d_grid,  ctx->d_det,    ctx->d_hotcross, ctx->d_f,        ctx->d_k2,      ctx->d_weight,
-                    ctx->d_nint,  ctx->d_dnmax,  ctx->d_zones,    ctx->d_num,      ctx->d_prefix,  ctx->d_nz,
-                    ctx->pool.f,  ctx->pool.rng, ctx->pool.crng,  ctx->pool.n_scatt, ctx->pool.n_step, ctx->pool.gclock,
-                    ctx->stage.f, ctx->stage.rng, ctx->stage.crng, ctx->stage.n_scatt, ctx->stage.n_step, ctx->stage.gclock,
-                    ctx->ready.entries, ctx->scatter.entries, ctx->carry.entries, ctx->d_qctr, ctx->d_spectrum,
-                    ctx->d_counters, ctx->d_maxtau, ctx->d_work,  ctx->d_error, ctx->d_args};
-    for (void *b : bufs)
-        if (b)
-            cudaFree(b);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena.base) {
+        /* park the device block for the next context on this device (see DeviceArena): one block per device */
+        std::lock_guard<std::mutex> lock(g_arena_mutex);
+        for (size_t i = 0; i < g_arena_cache.size(); ++i)
+            if (g_arena_cache[i].device == ctx->arena.device) {
+                cudaFree(g_arena_cache[i].base);
+                g_arena_cache.erase(g_arena_cache.begin() + i);
+                break;
+            }
+        g_arena_cache.push_back(ctx->arena);
+        ctx->arena = DeviceArena{};
+    }
     if (ctx->ev0)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
@@ -721,6 +786,15 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+void grmonty_b200_trim_cache(void) {
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    for (DeviceArena &a : g_arena_cache) {
+        cudaSetDevice(a.device);
+        cudaFree(a.base);
+    }
+    g_arena_cache.clear();
 }
 
 int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops) {

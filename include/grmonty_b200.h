@@ -161,7 +161,11 @@ int grmonty_b200_result(grmonty_b200_ctx *ctx, double *spectrum, uint64_t counts
 /* Zero the accumulators and counters so the same context can run again. */
 int grmonty_b200_reset(grmonty_b200_ctx *ctx);
 
+/* Frees the context.  The photon pool (the bulk of the device memory, ~1.7 GB at the default capacity) is parked in a
+ * per-device cache and reused by the next grmonty_b200_create with the same queue_capacity: cudaFree of it costs
+ * more than a whole run.  grmonty_b200_trim_cache() returns the cached memory to the driver. */
 void grmonty_b200_destroy(grmonty_b200_ctx *ctx);
+void grmonty_b200_trim_cache(void);
 
 /* Message of the last error on this context (ctx == NULL: of the last failed create on this thread). */
 const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx);
