@@ -72,7 +72,7 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
-    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 4;
+    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 4, gen_ramp = 8;
     grmonty_b200_stats stats{};
     std::string err;
 };
@@ -217,6 +217,12 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         P.jnu_d_l_t = std::log(kJnuMaxT / kThetaEMin) / kNESamp;
         P.spec_l_e_0 = std::log(1.0e-12);
         P.nz_max = cfg->photon_n * std::log(kNuMax / kNuMin);
+        P.inv_dx1 = 1.0 / P.dx1;
+        P.inv_dx2 = 1.0 / P.dx2;
+        P.inv_b_unit = 1.0 / P.b_unit;
+        P.inv_hc_d_l_w = 1.0 / P.hc_d_l_w;
+        P.inv_hc_d_l_t = 1.0 / P.hc_d_l_t;
+        P.inv_jnu_d_l_t = 1.0 / P.jnu_d_l_t;
 
         /* ---- one device arena for everything (reused from the cache when possible) ---- */
         const size_t nz = (size_t)cfg->n0 * cfg->n1;
@@ -406,6 +412,8 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             ctx->gen_fine_from = cfg->gen_fine_from;
         if (cfg->gen_fine_div != 0)
             ctx->gen_fine_div = cfg->gen_fine_div;
+        if (cfg->gen_ramp > 1)
+            ctx->gen_ramp = cfg->gen_ramp;
         return GRMONTY_B200_OK;
     }();
     if (rc != GRMONTY_B200_OK) {
@@ -451,12 +459,12 @@ int grmonty_b200_total_primaries(grmonty_b200_ctx *ctx, int64_t *total) {
 /* size of the generation starting at run position g_start (same rule as the oracle's orc_generation_size;
  * documented at grmonty_b200_config::gen0) */
 static long long generation_size(long long g_start, long long gen0, long long cap, long long fine_from,
-                                 long long fine_div) {
+                                 long long fine_div, long long ramp) {
     long long s;
     if (g_start < gen0)
         s = gen0;
     else if (g_start < fine_from || fine_div <= 1)
-        s = g_start;
+        s = g_start * (std::max<long long>(ramp, 2) - 1);
     else
         s = g_start / fine_div;
     s = std::max(s, gen0);
@@ -603,9 +611,7 @@ static int read_bias_stats(grmonty_b200_ctx *ctx, GmBiasStats *b) {
     CK(cudaStreamSynchronize(ctx->stream));
     double mt;
     memcpy(&mt, &bits, sizeof(mt));
-    b->max_tau_scatt = mt;
-    b->n_scatt = (double)c[1];
-    b->n_recorded = (double)c[2];
+    *b = make_bias_stats(ctx->P.bias_norm, mt, (double)c[1], (double)c[2]);
     return GRMONTY_B200_OK;
 }
 
@@ -627,7 +633,7 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
     GmBiasStats bias;
     for (long long g = 0; g_start < last; ++g) {
         const long long g_end =
-            g_start + generation_size(g_start, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from, ctx->gen_fine_div);
+            g_start + generation_size(g_start, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from, ctx->gen_fine_div, ctx->gen_ramp);
         const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
         if (lo < hi) {
             long long f0 = lo + ((rank - lo % world) % world + world) % world; /* first index >= lo, = rank mod world */

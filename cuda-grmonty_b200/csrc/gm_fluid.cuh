@@ -58,7 +58,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         f.n_e = 0.0;
         return false;
     }
-    const double qi = fm::div(x1 - P.x_start1, P.dx1), qj = fm::div(x2 - P.x_start2, P.dx2);
+    const double qi = (x1 - P.x_start1) * P.inv_dx1, qj = (x2 - P.x_start2) * P.inv_dx2;
     int i = (int)(qi - 0.5 + 1000) - 1000;
     int j = (int)(qj - 0.5 + 1000) - 1000;
     double del_i, del_j;
@@ -69,7 +69,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         i = P.n0 - 2;
         del_i = 1.0;
     } else {
-        del_i = fm::div(x1 - ((i + 0.5) * P.dx1 + P.x_start1), P.dx1);
+        del_i = (x1 - ((i + 0.5) * P.dx1 + P.x_start1)) * P.inv_dx1;
     }
     if (j < 0) {
         j = 0;
@@ -78,7 +78,7 @@ __device__ __forceinline__ bool fluid_params(const GmParams &P, double x1, doubl
         j = P.n1 - 2;
         del_j = 1.0;
     } else {
-        del_j = fm::div(x2 - ((j + 0.5) * P.dx2 + P.x_start2), P.dx2);
+        del_j = (x2 - ((j + 0.5) * P.dx2 + P.x_start2)) * P.inv_dx2;
     }
     const double c00 = (1.0 - del_i) * (1.0 - del_j), c01 = (1.0 - del_i) * del_j;
     const double c10 = del_i * (1.0 - del_j), c11 = del_i * del_j;

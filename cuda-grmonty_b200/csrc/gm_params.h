@@ -86,6 +86,8 @@ struct GmParams {
     double jnu_l_min_k, jnu_d_l_k, jnu_l_min_t, jnu_d_l_t; /* consts.hpp:125-137 */
     double spec_l_e_0;                /* consts.hpp:156 */
     double nz_max;                    /* photon_n * ln(nu_max/nu_min), harm_model.cpp:1384 */
+    /* reciprocals of run constants the hot loop divides by (x * (1/c) instead of x / c: <= 1 ulp apart) */
+    double inv_dx1, inv_dx2, inv_b_unit, inv_hc_d_l_w, inv_hc_d_l_t, inv_jnu_d_l_t;
     /* device pointers */
     const double *grid;     /* interleaved primitives [n0][n1][8]: k_rho u u_1 u_2 u_3 b_1 b_2 b_3 */
     const double *geom_det; /* [n0][n1] */
@@ -99,6 +101,19 @@ struct GmBiasStats {
     double max_tau_scatt;
     double n_scatt;
     double n_recorded;
+    /* bias_norm * max_tau_scatt * (n_scatt / (n_recorded + 1) + 2): the denominator of bias_func, the same for
+     * every photon of the generation (computed on the host with the reference's operation order) */
+    double bias_den;
 };
+
+inline GmBiasStats make_bias_stats(double bias_norm, double max_tau_scatt, double n_scatt, double n_recorded) {
+    GmBiasStats s;
+    s.max_tau_scatt = max_tau_scatt;
+    s.n_scatt = n_scatt;
+    s.n_recorded = n_recorded;
+    const double avg_num_scatt = n_scatt / (1.0 * n_recorded + 1.0);
+    s.bias_den = bias_norm * max_tau_scatt * (avg_num_scatt + 2.0);
+    return s;
+}
 
 } /* namespace gm */

@@ -27,7 +27,11 @@ __device__ __forceinline__ double interp_exp_table(const double *tab, double lx,
 
 /* K2(1/theta_e) given l_theta = ln(theta_e) (reference jnu_mixed::k2_eval, jnu_mixed.cpp:102-111); selects only */
 __device__ __forceinline__ double k2_eval_l(const GmParams &P, double theta_e, double l_theta) {
-    const double tab = interp_exp_table(P.k2, l_theta, P.jnu_l_min_t, P.jnu_d_l_t);
+    double d_i = (l_theta - P.jnu_l_min_t) * P.inv_jnu_d_l_t;
+    int i = (int)d_i;
+    i = max(0, min(i, kNESamp - 1));
+    d_i -= i;
+    const double tab = fm::exp_((1.0 - d_i) * __ldg(P.k2 + i) + d_i * __ldg(P.k2 + i + 1));
     const double v = theta_e > kJnuMaxT ? 2.0 * theta_e * theta_e : tab;
     return theta_e < kThetaEMin ? 0.0 : v;
 }
@@ -52,7 +56,7 @@ __device__ __forceinline__ double f_eval(const GmParams &P, double theta_e, doub
 __device__ __forceinline__ double synch_sin_l(const GmParams &P, double nu, double n_e, double theta_e, double b,
                                               double sin_th, double l_theta) {
     const double k2 = k2_eval_l(P, theta_e, l_theta);
-    const double nu_c = fm::div(kEE * b, 2.0 * kPi * kME * kCL);
+    const double nu_c = b * (kEE / (2.0 * kPi * kME * kCL));
     const double nu_s = (2.0 / 9.0) * nu_c * theta_e * theta_e * sin_th;
     const bool zero = (theta_e < kThetaEMin) || (nu > 1.0e12 * nu_s) || !(nu_s > 0.0);
     const double nu_s_g = zero ? 1.0 : nu_s, nu_g = zero ? 1.0 : nu, k2_g = zero ? 1.0 : k2;
@@ -136,8 +140,8 @@ __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, d
     const bool thomson = w * theta_e < 1.0e-6;
     const bool in_table = !(w <= kHcMinW || w >= kHcMaxW || theta_e <= kHcMinT || theta_e >= kHcMaxT);
     const double kLog10E = 0.43429448190325182765;
-    double qw = fm::div(l_w * kLog10E - P.hc_l_min_w, P.hc_d_l_w);
-    double qt = fm::div(l_theta * kLog10E - P.hc_l_min_t, P.hc_d_l_t);
+    double qw = (l_w * kLog10E - P.hc_l_min_w) * P.inv_hc_d_l_w;
+    double qt = (l_theta * kLog10E - P.hc_l_min_t) * P.inv_hc_d_l_t;
     qw = fmin(fmax(qw, 0.0), (double)kHcNW - 1.0e-6);
     qt = fmin(fmax(qt, 0.0), (double)kHcNT - 1.0e-6);
     const int i = (int)qw, j = (int)qt;
@@ -163,7 +167,7 @@ __device__ __forceinline__ void fluid_frame(const GmParams &P, const double k[4]
     e_fluid = -ku;
     const double kb = k[0] * f.b_cov[0] + k[1] * f.b_cov[1] + k[2] * f.b_cov[2] + k[3] * f.b_cov[3];
     const bool no_b = (f.b == 0.0);
-    const double den = fm::div(fabs(ku) * (no_b ? 1.0 : f.b), P.b_unit);
+    const double den = fabs(ku) * (no_b ? 1.0 : f.b) * P.inv_b_unit;
     mu = fm::div(kb, den);
     mu = fmin(fmax(mu, -1.0), 1.0);
     mu = no_b ? 0.0 : mu; /* theta = pi/2 */
@@ -173,7 +177,7 @@ __device__ __forceinline__ void fluid_frame(const GmParams &P, const double k[4]
  * radiation.cpp:103-107,142-146; the m_p factors cancel) */
 __device__ __forceinline__ double alpha_inv_scatt_l(const GmParams &P, double nu, double theta_e, double n_e,
                                                     double l_nu, double l_theta) {
-    const double e_g = fm::div(kHPL * nu, kME * kCL * kCL);
+    const double e_g = nu * (kHPL / (kME * kCL * kCL));
     const double kLnHOverMc2 = -46.263250426746548; /* ln(h / (m_e c^2)) in cgs: ln(e_g) = ln(nu) + this */
     return nu * hotcross_lkup_l(P, e_g, theta_e, l_nu + kLnHOverMc2, l_theta) * n_e;
 }
@@ -183,7 +187,7 @@ __device__ __forceinline__ double alpha_inv_scatt(const GmParams &P, double nu, 
 
 /* reference b_nu_inv, radiation.cpp:120-128 (series below x = 1e-3), as a select between the two forms */
 __device__ __forceinline__ double b_nu_inv(double nu, double theta_e) {
-    const double x = fm::div(kHPL * nu, kME * kCL * kCL * theta_e);
+    const double x = fm::div(nu * (kHPL / (kME * kCL * kCL)), theta_e);
     const double c = 2.0 * kHPL / (kCL * kCL);
     const double series = x * (1.0 / 24.0) * (24.0 + x * (12.0 + x * (4.0 + x)));
     const double em1 = fm::exp_(fmin(x, 700.0)) - 1.0;
@@ -204,9 +208,8 @@ __device__ __forceinline__ double alpha_inv_abs_sin(const GmParams &P, double nu
 
 /* reference bias_func, harm_model.cpp:1391-1404, with the generation's frozen statistics */
 __device__ __forceinline__ double bias_func(const GmParams &P, const GmBiasStats &s, double theta_e, double w) {
-    const double mx = fm::div(0.5 * w, kWeightMin);
-    const double avg_num_scatt = fm::div(s.n_scatt, 1.0 * s.n_recorded + 1.0);
-    double bias = fm::div(100.0 * theta_e * theta_e, P.bias_norm * s.max_tau_scatt * (avg_num_scatt + 2.0));
+    const double mx = w * (0.5 / kWeightMin);
+    double bias = fm::div(100.0 * theta_e * theta_e, s.bias_den);
     bias = fmax(bias, kTpOverTe);
     bias = fmin(bias, mx);
     return bias * (1.0 / kTpOverTe);
@@ -217,7 +220,7 @@ __device__ __forceinline__ void opacities(const GmParams &P, const double k[4], 
                                           double &alpha_scatt, double &alpha_abs) {
     double e_fluid, mu;
     fluid_frame(P, k, f, e_fluid, mu);
-    nu = fm::div(e_fluid * kME * kCL * kCL, kHPL);
+    nu = e_fluid * (kME * kCL * kCL / kHPL);
     if (nu < 0.0 || isnan(nu)) {
         alpha_scatt = 0.0;
         alpha_abs = 0.0;

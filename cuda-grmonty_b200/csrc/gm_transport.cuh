@@ -422,7 +422,7 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
     double e_fluid = 0.0, mu = 0.0;
     if (!bound)
         fluid_frame(P, L.k, f, e_fluid, mu);
-    const double nu = bound ? 0.0 : fm::div(e_fluid * kME * kCL * kCL, kHPL);
+    const double nu = bound ? 0.0 : e_fluid * (kME * kCL * kCL / kHPL);
     const bool outside = bound || nu < 0.0;
     /* evaluate the opacities for every lane (harmless dummy arguments outside the fluid) so that the warp
      * stays converged through the expensive part; the three logarithms (nu, theta_e, and the interaction

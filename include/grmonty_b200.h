@@ -97,13 +97,15 @@ typedef struct grmonty_b200_config {
     int64_t queue_capacity; /* photon slots in the device queue */
     /* Generation schedule.  The scattering-bias statistics are frozen within a generation, so the generations
      * must stay short relative to the run so far (the reference updates its statistics after every photon):
-     * the generation starting at run position s holds gen0 positions if s < gen0, s positions (the cumulative
-     * count doubles) while s < gen_fine_from, then s / gen_fine_div positions, and never more than gen_cap. */
+     * the generation starting at run position s holds gen0 positions if s < gen0, (gen_ramp - 1) s positions (the
+     * cumulative count grows gen_ramp-fold) while s < gen_fine_from, then s / gen_fine_div positions, and never
+     * more than gen_cap. */
     int64_t gen0;           /* default 32 */
     int64_t gen_cap;        /* default 2^20 */
     int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over
                                to the next one (default 256); bounds the tail of every generation */
     int64_t gen_fine_from;  /* default 16384 */
+    int64_t gen_ramp;       /* default 8 */
     int64_t gen_fine_div;   /* default 4 (each generation adds 25 % to the run so far); <= 1: keep doubling.
                                Measured at configs[0] against 20 reference runs (profiles/r1_bias_schedule.txt):
                                doubling gives +5.8 % scattered / +2.5 % recorded counts, div 4 +0.3 % / -0.05 %. */

@@ -1365,15 +1365,16 @@ static void run_carried(orc_model *m) {
 /* ============================================================================================
  * Driver: generations of primaries (shared schedule with the CUDA path)
  * ============================================================================================ */
-int64_t orc_generation_size(int64_t g_start, int64_t gen0, int64_t gen_cap, int64_t fine_from, int64_t fine_div) {
-    /* size of the generation that starts at run position g_start: gen0 first, then as many positions as have
-     * been started so far (the cumulative count doubles) until fine_from, then 1/fine_div of the cumulative count
+int64_t orc_generation_size(int64_t g_start, int64_t gen0, int64_t gen_cap, int64_t fine_from, int64_t fine_div,
+                            int64_t ramp) {
+    /* size of the generation that starts at run position g_start: gen0 first, then (ramp - 1) times the positions
+     * started so far (the cumulative count grows ramp-fold) until fine_from, then 1/fine_div of the cumulative count
      * (growth factor 1 + 1/fine_div per generation), never more than gen_cap */
     int64_t s;
     if (g_start < gen0)
         s = gen0;
     else if (g_start < fine_from || fine_div <= 1)
-        s = g_start;
+        s = g_start * ((ramp > 2 ? ramp : 2) - 1);
     else
         s = g_start / fine_div;
     if (s < gen0)
@@ -1455,7 +1456,7 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
     int64_t g_start = 0;
     const int budget = m->budget > 0 ? m->budget : INT_MAX;
     for (int64_t g = 0; g_start < last; ++g) {
-        int64_t g_end = g_start + orc_generation_size(g_start, gen0, gen_cap, m->gen_fine_from, m->gen_fine_div);
+        int64_t g_end = g_start + orc_generation_size(g_start, gen0, gen_cap, m->gen_fine_from, m->gen_fine_div, m->gen_ramp);
         const int64_t lo = g_start > first ? g_start : first, hi = g_end < last ? g_end : last;
         if (lo < hi) {
             if (m->stats_mode == ORC_STATS_FROZEN) {

@@ -81,7 +81,7 @@ typedef struct orc_model {
      * generation before it is suspended and continued in the next one; <= 0: unlimited (the reference) */
     int budget;
     /* generation schedule (shared with the CUDA path, see orc_generation_size) */
-    int64_t gen_fine_from, gen_fine_div;
+    int64_t gen_fine_from, gen_fine_div, gen_ramp;
     struct orc_track_state *carry; /* suspended photons (owned by the model) */
     uint64_t n_carry, cap_carry;
     /* outputs */
@@ -167,7 +167,8 @@ void orc_sample_zone_photon(const orc_model *m, int i, int j, double dn_max, orc
 void orc_track_super_photon(orc_model *m, orc_photon *ph);
 void orc_record_super_photon(orc_model *m, const orc_photon *ph);
 /* Generation schedule shared with the CUDA path: size of the generation starting at position g_start. */
-int64_t orc_generation_size(int64_t g_start, int64_t gen0, int64_t gen_cap, int64_t fine_from, int64_t fine_div);
+int64_t orc_generation_size(int64_t g_start, int64_t gen0, int64_t gen_cap, int64_t fine_from, int64_t fine_div,
+                            int64_t ramp);
 /* Run positions [first,last) of the processing sequence that satisfy j % world == rank; position j handles
  * primary orc_permute(j) (or j itself when m->zone_order). */
 int64_t orc_perm_multiplier(int64_t total);

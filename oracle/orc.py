@@ -36,7 +36,7 @@ class OrcModel(C.Structure):
         ("bias_max_tau_scatt", C.c_double), ("bias_n_scatt", C.c_double), ("bias_n_recorded", C.c_double),
         ("acc_max_tau_scatt", C.c_double), ("acc_n_scatt", C.c_uint64), ("acc_n_recorded", C.c_uint64),
         ("stats_mode", C.c_int), ("zone_order", C.c_int),
-        ("budget", C.c_int), ("gen_fine_from", C.c_int64), ("gen_fine_div", C.c_int64), ("carry", C.c_void_p), ("n_carry", C.c_uint64), ("cap_carry", C.c_uint64),
+        ("budget", C.c_int), ("gen_fine_from", C.c_int64), ("gen_fine_div", C.c_int64), ("gen_ramp", C.c_int64), ("carry", C.c_void_p), ("n_carry", C.c_uint64), ("cap_carry", C.c_uint64),
         ("spectrum", C.c_double * (N_TH * N_E * N_F)),
         ("n_created", C.c_uint64),
         ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64), ("n_interactions", C.c_uint64),
@@ -89,7 +89,7 @@ def lib():
             getattr(L, name).restype = C.c_double
         L.orc_zone_counts.restype = C.c_uint64
         L.orc_generation_size.restype = C.c_int64
-        L.orc_generation_size.argtypes = [C.c_int64] * 5
+        L.orc_generation_size.argtypes = [C.c_int64] * 6
         L.orc_perm_multiplier.restype = C.c_int64
         L.orc_perm_multiplier.argtypes = [C.c_int64]
         L.orc_permute.restype = C.c_int64
@@ -252,7 +252,7 @@ class Model:
         return self.flat(ph)
 
     def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22, budget=256, fine_from=16384,
-            fine_div=4):
+            fine_div=4, ramp=8):
         self.m.budget = budget if self.m.stats_mode == 0 else 0
-        self.m.gen_fine_from, self.m.gen_fine_div = fine_from, fine_div
+        self.m.gen_fine_from, self.m.gen_fine_div, self.m.gen_ramp = fine_from, fine_div, ramp
         self.L.orc_run(self.ptr, first, last, rank, world, gen0, gen_cap)

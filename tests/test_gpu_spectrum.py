@@ -21,6 +21,18 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_GPU_SEEDS = 24
+
+
+def report(section, values):
+    """measured parity numbers -> gpurun_out/parity_report.json (copied to profiles/ for the record)"""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(out):
+        return
+    path = os.path.join(out, "parity_report.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[section] = values
+    json.dump(data, open(path, "w"), indent=1)
 FIELDS = [0, 1, 2, 3, 7, 8]  # dn_dle de_dle nph nscatt tau_abs tau_scatt: the fields stored in the fixture
 
 
@@ -58,13 +70,15 @@ def test_counts_and_luminosity_within_1pct(ref, gpu_runs):
     r_lum = ref["spec"][..., 1].sum(axis=(1, 2))
     # primaries: the per-zone expectation is the same number in both codes (stochastic rounding only)
     assert abs(g_created.mean() / r_created.mean() - 1) < 1e-3
-    report = {}
+    rep = {}
     for name, g, r in (("luminosity", g_lum, r_lum), ("recorded", g_rec, r_rec), ("scattered", g_scat, r_scat)):
         d = g.mean() / r.mean() - 1
         se = np.hypot(g.std(ddof=1) / np.sqrt(len(g)) / g.mean(), r.std(ddof=1) / np.sqrt(len(r)) / r.mean())
-        report[name] = (d, se)
-    print("relative difference of ensemble means (difference, standard error):", report)
-    for name, (d, se) in report.items():
+        rep[name] = (d, se)
+    print("relative difference of ensemble means (difference, standard error):", rep)
+    report("counts_configs0", {k: {"rel_diff": float(v[0]), "std_err": float(v[1])} for k, v in rep.items()} |
+           {"n_gpu_seeds": len(gpu_runs), "n_ref_seeds": int(len(r_rec))})
+    for name, (d, se) in rep.items():
         assert abs(d) < 0.01 + 2 * se, (name, d, se)
 
 
@@ -84,6 +98,8 @@ def test_spectrum_chi_square_and_l1(ref, gpu_runs):
     l1_floor = float(np.abs(a.mean(0) - b.mean(0))[mask].sum() / rm[mask].sum())
     print(f"bins {int(mask.sum())}  chi2/bin {chi2:.3f}  L1 {l1:.4f}  (reference half-vs-half L1 {l1_floor:.4f})  "
           f"max |z| {np.abs(z).max():.2f}")
+    report("spectrum_configs0", {"bins": int(mask.sum()), "chi2_per_bin": chi2, "l1": l1, "l1_ref_half_vs_half": l1_floor,
+                                 "max_abs_z": float(np.abs(z).max())})
     # variances estimated from ~8-24 samples make z Student-t like: E[z^2] ~ 1.1-1.4 for identical distributions
     assert chi2 < 1.6, chi2
     assert np.abs(z).max() < 6.0
