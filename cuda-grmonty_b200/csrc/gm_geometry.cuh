@@ -253,8 +253,12 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
     q = geo_point(P, xn[1], xn[2]);
     Connection c;
     connection_eval(P, q, c);
-    double err;
-    {
+    /* <= kMaxIter = 2 fixed-point iterations (reference :1247-1267) as a real loop: one copy of the contraction and
+     * of the error norm in the instruction stream (the loop body is the largest piece of the hot code, which
+     * competes for the 32 KB instruction cache) */
+    double err = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < kMaxIter; ++it) {
         geodesic_rhs(c, kp, dkn);
         err = 0.0;
 #pragma unroll
@@ -262,18 +266,11 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
             kn[i] = kh[i] + dl_2 * dkn[i];
             err += rel_change(kp[i], kn[i]);
         }
-    }
-    if (err > kETol) { /* second (last) fixed-point iteration, kMaxIter = 2 */
+        if (!(err > kETol))
+            break;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             kp[i] = kn[i];
-        geodesic_rhs(c, kp, dkn);
-        err = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            kn[i] = kh[i] + dl_2 * dkn[i];
-            err += rel_change(kp[i], kn[i]);
-        }
     }
     double g00, g01, g03;
     metric_cov_row0(P, q, g00, g01, g03);

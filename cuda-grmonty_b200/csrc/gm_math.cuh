@@ -54,6 +54,88 @@ GM_HD double with_hi(double d, int hi) {
     return from_bits((to_bits(d) & 0xffffffffull) | ((uint64_t)(uint32_t)hi << 32));
 }
 
+/* Polynomial coefficients and reduction constants.  On the device they live in constant memory: a DFMA takes a
+ * constant-bank operand directly, while a 64-bit literal costs two extra instructions (IMAD.MOV / UMOV pairs were
+ * 15 % of all executed instructions of the transport kernel with literals).  The host build uses the same table. */
+#define GM_MATH_CONSTANTS(X) \
+    X(E3, 1.6666666666666666e-01) \
+    X(E5, 8.3333333333333332e-03) \
+    X(E4, 4.1666666666666664e-02) \
+    X(E7, 1.9841269841269841e-04) \
+    X(E6, 1.3888888888888889e-03) \
+    X(E9, 2.7557319223985893e-06) \
+    X(E8, 2.4801587301587302e-05) \
+    X(E11, 2.5052108385441720e-08) \
+    X(E10, 2.7557319223985888e-07) \
+    X(E13, 1.6059043836821613e-10) \
+    X(E12, 2.0876756987868100e-09) \
+    X(LOG2E, 1.4426950408889634) \
+    X(MAGIC, 6755399441055744.0) \
+    X(LN2_HI, 6.93147180369123816490e-01) \
+    X(LN2_LO, 1.90821492927058770002e-10) \
+    X(LOG2_10, 3.3219280948873622) \
+    X(LG2_HI, 3.01029995663611771306e-01) \
+    X(LG2_LO, 3.69423907715893078616e-13) \
+    X(LN10_HI, 2.30258509299404590109e+00) \
+    X(LN10_LO_NEG, 2.17071551782250736e-16) \
+    X(L5, 4.0000000000000000e-01) \
+    X(L3, 6.6666666666666663e-01) \
+    X(L9, 2.2222222222222221e-01) \
+    X(L7, 2.8571428571428570e-01) \
+    X(L13, 1.5384615384615385e-01) \
+    X(L11, 1.8181818181818182e-01) \
+    X(L17, 1.1764705882352941e-01) \
+    X(L15, 1.3333333333333333e-01) \
+    X(L21, 9.5238095238095233e-02) \
+    X(L19, 1.0526315789473684e-01) \
+    X(PI_HI, 3.14159265358979311600e+00) \
+    X(PI_LO, 1.22464679914735317723e-16) \
+    X(S2, 8.33333333332248946124e-03) \
+    X(S1_NEG, 1.66666666666666324348e-01) \
+    X(S4, 2.75573137070700676789e-06) \
+    X(S3_NEG, 1.98412698298579493134e-04) \
+    X(S6, 1.58969099521155010221e-10) \
+    X(S5_NEG, 2.50507602534068634195e-08) \
+    X(C2_NEG, 1.38888888888741095749e-03) \
+    X(C1, 4.16666666666666019037e-02) \
+    X(C4_NEG, 2.75573143513906633035e-07) \
+    X(C3, 2.48015872894767294178e-05) \
+    X(C6_NEG, 1.13596475577881948265e-11) \
+    X(C5, 2.08757232129817482790e-09) \
+    X(TWO_OVER_PI, 6.36619772367581382433e-01) \
+    X(PIO2_1, 1.57079632673412561417e+00) \
+    X(PIO2_2, 6.07710050630396597660e-11) \
+    X(PIO2_2T, 2.02226624879595063154e-21) \
+    X(CB4_NEG, 3.47020774e-04) \
+    X(CB3, 7.96603547e-03) \
+    X(CB2_NEG, 7.33267142e-02) \
+    X(CB1, 4.22924391e-01) \
+    X(CB0, 6.48113736e-01)
+
+enum MathConstant {
+#define X(n, v) K_##n,
+    GM_MATH_CONSTANTS(X)
+#undef X
+        K_COUNT
+};
+#ifdef __CUDACC__
+__constant__ double gm_math_k[K_COUNT] = {
+#define X(n, v) v,
+    GM_MATH_CONSTANTS(X)
+#undef X
+};
+#endif
+static const double gm_math_k_host[K_COUNT] = {
+#define X(n, v) v,
+    GM_MATH_CONSTANTS(X)
+#undef X
+};
+#ifdef __CUDA_ARCH__
+#define C_(n) gm_math_k[K_##n]
+#else
+#define C_(n) gm_math_k_host[K_##n]
+#endif
+
 /* ~2^-23 reciprocal / reciprocal square root seeds (MUFU.RCP64H / MUFU.RSQ64H) */
 GM_HD double rcp_seed(double b) {
 #ifdef __CUDA_ARCH__
@@ -114,12 +196,12 @@ GM_HD double exp_core(double r, double n) {
     /* exp(r) on |r| <= 0.3466, degree-11 minimax-like Taylor (|r|^12/12! < 7e-15 relative to 1: the last
      * coefficients are the classic fdlibm-style 1/k!), Estrin */
     const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double p23 = fma(r, 1.6666666666666666e-01, 0.5);
-    const double p45 = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
-    const double p67 = fma(r, 1.9841269841269841e-04, 1.3888888888888889e-03);
-    const double p89 = fma(r, 2.7557319223985893e-06, 2.4801587301587302e-05);
-    const double pab = fma(r, 2.5052108385441720e-08, 2.7557319223985888e-07);
-    const double pcd = fma(r, 1.6059043836821613e-10, 2.0876756987868100e-09);
+    const double p23 = fma(r, C_(E3), 0.5);
+    const double p45 = fma(r, C_(E5), C_(E4));
+    const double p67 = fma(r, C_(E7), C_(E6));
+    const double p89 = fma(r, C_(E9), C_(E8));
+    const double pab = fma(r, C_(E11), C_(E10));
+    const double pcd = fma(r, C_(E13), C_(E12));
     const double q0 = fma(r2, p23, r);
     const double q1 = fma(r2, p67, p45);
     const double q2 = fma(r2, pab, p89);
@@ -133,10 +215,10 @@ GM_HD double exp_core(double r, double n) {
 
 GM_HD double exp_(double x) {
     const double xc = fmin(fmax(x, -708.0), 709.0);
-    const double t = fma(xc, 1.4426950408889634, 6755399441055744.0);
-    const double n = t - 6755399441055744.0;
-    double r = fma(n, -6.93147180369123816490e-01, xc);
-    r = fma(n, -1.90821492927058770002e-10, r);
+    const double t = fma(xc, C_(LOG2E), C_(MAGIC));
+    const double n = t - C_(MAGIC);
+    double r = fma(n, -C_(LN2_HI), xc);
+    r = fma(n, -C_(LN2_LO), r);
     double v = exp_core(r, n);
     v = x < -708.0 ? 0.0 : v;
     v = x > 709.78 ? from_bits(0x7ff0000000000000ull) : v;
@@ -146,14 +228,14 @@ GM_HD double exp_(double x) {
 /* 10^x */
 GM_HD double exp10_(double x) {
     const double xc = fmin(fmax(x, -307.0), 308.0);
-    const double t = fma(xc, 3.3219280948873622, 6755399441055744.0);
-    const double n = t - 6755399441055744.0;
+    const double t = fma(xc, C_(LOG2_10), C_(MAGIC));
+    const double n = t - C_(MAGIC);
     /* x - n log10(2) in two parts, then to the natural base */
-    double r = fma(n, -3.01029995663611771306e-01, xc);
-    r = fma(n, -3.69423907715893078616e-13, r);
-    const double rh = r * 2.30258509299404590109e+00;
-    const double rl = fma(r, 2.30258509299404590109e+00, -rh);
-    const double rr = rh + fma(r, -2.17071551782250736e-16, rl);
+    double r = fma(n, -C_(LG2_HI), xc);
+    r = fma(n, -C_(LG2_LO), r);
+    const double rh = r * C_(LN10_HI);
+    const double rl = fma(r, C_(LN10_HI), -rh);
+    const double rr = rh + fma(r, -C_(LN10_LO_NEG), rl);
     double v = exp_core(rr, n);
     v = x < -307.0 ? 0.0 : v;
     v = x > 308.25 ? from_bits(0x7ff0000000000000ull) : v;
@@ -176,18 +258,18 @@ GM_HD double log_(double x) {
     const double v = s * s;
     /* 2 atanh(s) = 2 s + s^3 (2/3 + 2/5 v + ... + 2/21 v^9), Estrin in v; |s| <= 0.1716 */
     const double v2 = v * v, v4 = v2 * v2, v8 = v4 * v4;
-    const double a01 = fma(v, 4.0000000000000000e-01, 6.6666666666666663e-01);
-    const double a23 = fma(v, 2.2222222222222221e-01, 2.8571428571428570e-01);
-    const double a45 = fma(v, 1.5384615384615385e-01, 1.8181818181818182e-01);
-    const double a67 = fma(v, 1.1764705882352941e-01, 1.3333333333333333e-01);
-    const double a89 = fma(v, 9.5238095238095233e-02, 1.0526315789473684e-01);
+    const double a01 = fma(v, C_(L5), C_(L3));
+    const double a23 = fma(v, C_(L9), C_(L7));
+    const double a45 = fma(v, C_(L13), C_(L11));
+    const double a67 = fma(v, C_(L17), C_(L15));
+    const double a89 = fma(v, C_(L21), C_(L19));
     const double b0 = fma(v2, a23, a01);
     const double b1 = fma(v2, a67, a45);
     const double c0 = fma(v4, b1, b0);
     const double poly = fma(v8, a89, c0);
     const double ed = (double)e;
-    const double hi_part = fma(ed, 6.93147180369123816490e-01, 2.0 * s);
-    const double lo_part = fma(ed, 1.90821492927058770002e-10, fma(s * v, poly, 2.0 * sl));
+    const double hi_part = fma(ed, C_(LN2_HI), 2.0 * s);
+    const double lo_part = fma(ed, C_(LN2_LO), fma(s * v, poly, 2.0 * sl));
     return hi_part + lo_part;
 }
 
@@ -196,19 +278,19 @@ GM_HD void sincospi_(double t, double *sp, double *cp) {
     const double q = rint(t + t);           /* nearest half-integer count */
     const double r = fma(q, -0.5, t);       /* |r| <= 1/4, exact */
     const int qi = (int)q;
-    const double x = r * 3.14159265358979311600e+00;
-    const double xl = fma(r, 3.14159265358979311600e+00, -x);
-    const double xr = x + fma(r, 1.22464679914735317723e-16, xl); /* pi r, |.| <= pi/4 */
+    const double x = r * C_(PI_HI);
+    const double xl = fma(r, C_(PI_HI), -x);
+    const double xr = x + fma(r, C_(PI_LO), xl); /* pi r, |.| <= pi/4 */
     const double z = xr * xr, z2 = z * z, z4 = z2 * z2;
     /* sin(x) = x + x z (S1 + S2 z + ... + S6 z^5), cos(x) = 1 - z/2 + z^2 (C1 + ... + C6 z^5): fdlibm kernels */
-    const double s12 = fma(z, 8.33333333332248946124e-03, -1.66666666666666324348e-01);
-    const double s34 = fma(z, 2.75573137070700676789e-06, -1.98412698298579493134e-04);
-    const double s56 = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    const double s12 = fma(z, C_(S2), -C_(S1_NEG));
+    const double s34 = fma(z, C_(S4), -C_(S3_NEG));
+    const double s56 = fma(z, C_(S6), -C_(S5_NEG));
     const double sp_ = fma(z4, s56, fma(z2, s34, s12));
     const double sn = fma(xr * z, sp_, xr);
-    const double c12 = fma(z, -1.38888888888741095749e-03, 4.16666666666666019037e-02);
-    const double c34 = fma(z, -2.75573143513906633035e-07, 2.48015872894767294178e-05);
-    const double c56 = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    const double c12 = fma(z, -C_(C2_NEG), C_(C1));
+    const double c34 = fma(z, -C_(C4_NEG), C_(C3));
+    const double c56 = fma(z, -C_(C6_NEG), C_(C5));
     const double cp_ = fma(z4, c56, fma(z2, c34, c12));
     const double cs = fma(z2, cp_, fma(z, -0.5, 1.0));
     /* quadrant */
@@ -222,22 +304,22 @@ GM_HD void sincospi_(double t, double *sp, double *cp) {
 
 /* sin and cos of x for |x| < 1e5 (three-part Cody-Waite reduction by pi/2) */
 GM_HD void sincos_(double x, double *sp, double *cp) {
-    const double t = fma(x, 6.36619772367581382433e-01, 6755399441055744.0);
-    const double q = t - 6755399441055744.0;
+    const double t = fma(x, C_(TWO_OVER_PI), C_(MAGIC));
+    const double q = t - C_(MAGIC);
     const int qi = (int)q;
-    double r = fma(q, -1.57079632673412561417e+00, x);
-    r = fma(q, -6.07710050630396597660e-11, r);
-    const double rl = q * 2.02226624879595063154e-21;
+    double r = fma(q, -C_(PIO2_1), x);
+    r = fma(q, -C_(PIO2_2), r);
+    const double rl = q * C_(PIO2_2T);
     const double xr = r - rl;
     const double z = xr * xr, z2 = z * z, z4 = z2 * z2;
-    const double s12 = fma(z, 8.33333333332248946124e-03, -1.66666666666666324348e-01);
-    const double s34 = fma(z, 2.75573137070700676789e-06, -1.98412698298579493134e-04);
-    const double s56 = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    const double s12 = fma(z, C_(S2), -C_(S1_NEG));
+    const double s34 = fma(z, C_(S4), -C_(S3_NEG));
+    const double s56 = fma(z, C_(S6), -C_(S5_NEG));
     const double sp_ = fma(z4, s56, fma(z2, s34, s12));
     const double sn = fma(xr * z, sp_, xr);
-    const double c12 = fma(z, -1.38888888888741095749e-03, 4.16666666666666019037e-02);
-    const double c34 = fma(z, -2.75573143513906633035e-07, 2.48015872894767294178e-05);
-    const double c56 = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    const double c12 = fma(z, -C_(C2_NEG), C_(C1));
+    const double c34 = fma(z, -C_(C4_NEG), C_(C3));
+    const double c56 = fma(z, -C_(C6_NEG), C_(C5));
     const double cp_ = fma(z4, c56, fma(z2, c34, c12));
     const double cs = fma(z2, cp_, fma(z, -0.5, 1.0));
     const bool swap = (qi & 1) != 0;
@@ -257,8 +339,8 @@ GM_HD double cbrt_(double x) {
     const int rem = e - 3 * q;
     const double m = with_hi(x, (hi & 0x000fffff) | ((1023 + rem) << 20)); /* [1, 8) */
     /* seed: least-squares fit of m^(1/3) on [1,8) (relative error), degree 4: 5.4e-3 */
-    double y = fma(m, fma(m, fma(m, fma(m, -3.47020774e-04, 7.96603547e-03), -7.33267142e-02), 4.22924391e-01),
-                   6.48113736e-01);
+    double y = fma(m, fma(m, fma(m, fma(m, -C_(CB4_NEG), C_(CB3)), -C_(CB2_NEG)), C_(CB1)),
+                   C_(CB0));
     /* Halley: y <- y (y^3 + 2 m) / (2 y^3 + m), cubic convergence: 5e-3 -> 1e-7 -> 1e-21 */
     double y3 = y * y * y;
     y = y * div(y3 + 2.0 * m, fma(2.0, y3, m));

@@ -189,9 +189,12 @@ __device__ __forceinline__ double alpha_inv_scatt(const GmParams &P, double nu, 
 __device__ __forceinline__ double b_nu_inv(double nu, double theta_e) {
     const double x = fm::div(nu * (kHPL / (kME * kCL * kCL)), theta_e);
     const double c = 2.0 * kHPL / (kCL * kCL);
-    const double series = x * (1.0 / 24.0) * (24.0 + x * (12.0 + x * (4.0 + x)));
-    const double em1 = fm::exp_(fmin(x, 700.0)) - 1.0;
-    return fm::div(c, x < 1.0e-3 ? series : em1);
+    double den = x * (1.0 / 24.0) * (24.0 + x * (12.0 + x * (4.0 + x)));
+    /* x >= 1e-3 means h nu >= 1e-3 k T_e: only up-scattered X-ray photons get here, so the exponential is a
+     * rarely taken branch instead of a select that every lane pays for */
+    if (!(x < 1.0e-3))
+        den = fm::exp_(fmin(x, 700.0)) - 1.0;
+    return fm::div(c, den);
 }
 
 /* invariant absorption opacity by Kirchhoff's law (reference alpha_inv_abs, radiation.cpp:109-118):

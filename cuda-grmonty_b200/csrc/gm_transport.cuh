@@ -251,8 +251,10 @@ __device__ __forceinline__ bool stop_criterion(const GmParams &P, double x1, dou
 
 /* exp(-dtau) with the reference's 4th-order series below 1e-3 (harm_model.cpp:998-1002, :1047-1051) */
 __device__ __forceinline__ double attenuation(double d_tau, bool use_series) {
-    const double series = 1.0 - d_tau * (1.0 / 24.0) * (24.0 - d_tau * (12.0 - d_tau * (4.0 - d_tau)));
-    return use_series ? series : fm::exp_(-d_tau);
+    double att = 1.0 - d_tau * (1.0 / 24.0) * (24.0 - d_tau * (12.0 - d_tau * (4.0 - d_tau)));
+    if (!use_series) /* optical depth >= 1e-3 over one step: rare */
+        att = fm::exp_(-d_tau);
+    return att;
 }
 
 /* start-of-track quantities at a position where geometry and fluid are known
