@@ -181,6 +181,9 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import cuda_grmonty_b200 as gm
     if not torch.cuda.is_available():
@@ -272,12 +275,17 @@ def main():
     hm.run_simulation()  # warm-up
     sync()
     t0 = time.perf_counter()
+    t_run = t_red = 0.0
     for _ in range(args.steps):
+        ta = time.perf_counter()
         hm.run_simulation()
+        tb = time.perf_counter()
         if dist:
             spec = torch.from_numpy(hm.spectrum()).to(f"cuda:{dev}")
             dist.all_reduce(spec, op=dist.ReduceOp.SUM)
             hm.set_spectrum(spec.cpu().numpy())
+        t_run += tb - ta
+        t_red += time.perf_counter() - tb
     sync()
     e2e_wall = time.perf_counter() - t0
     if dist:
@@ -289,6 +297,7 @@ def main():
     d2h = 8 * (6 * 200 * 13 + 3 + 1 + 10)
     e2e = {"value": total * args.steps / e2e_wall, "unit": "superphotons/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
+           "rank0_run_ms": 1e3 * t_run / args.steps, "rank0_reduce_ms": 1e3 * t_red / args.steps,
            "api": "HARMModel.run_simulation (create + run + result + destroy through the C ABI)"}
 
     if rank != 0:
@@ -315,7 +324,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         out["cpu_baseline"] = run_reference_cpu(dump, args.ref_photon_n, args.mass_unit, cores)
-    print(json.dumps(out))
+    json_out.write(json.dumps(out) + "\n")
+    json_out.flush()
     if dist:
         dist.destroy_process_group()
 

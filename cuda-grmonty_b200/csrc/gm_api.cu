@@ -295,7 +295,18 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
             if (max_persist > 0 && max_window > 0) {
-                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(bytes, (size_t)max_persist));
+                /* the persisting-L2 carve-out is a device-wide limit (and setting it synchronises the device):
+                 * once per process and device, and only ever grown */
+                static std::mutex limit_mutex;
+                static size_t limit_set[64] = {0};
+                {
+                    std::lock_guard<std::mutex> lock(limit_mutex);
+                    const size_t want = std::min(bytes, (size_t)max_persist);
+                    if (ctx->device < 64 && limit_set[ctx->device] < want) {
+                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                        limit_set[ctx->device] = want;
+                    }
+                }
                 cudaStreamAttrValue attr;
                 memset(&attr, 0, sizeof(attr));
                 attr.accessPolicyWindow.base_ptr = ctx->d_grid;

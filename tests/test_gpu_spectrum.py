@@ -33,6 +33,8 @@ def report(section, values):
     data = json.load(open(path)) if os.path.exists(path) else {}
     data[section] = values
     json.dump(data, open(path, "w"), indent=1)
+
+
 FIELDS = [0, 1, 2, 3, 7, 8]  # dn_dle de_dle nph nscatt tau_abs tau_scatt: the fields stored in the fixture
 
 
