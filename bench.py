@@ -112,6 +112,26 @@ def run_reference_cpu(dump: str, photon_n: int, mass_unit: float, cores: int, se
             "created": created, "seconds": wall}
 
 
+def run_reference_gpu(dump: str, photon_n: int, mass_unit: float) -> dict | None:
+    """The reference's OWN GPU path (oracle/_ref/grmonty_ref_gpu: its unmodified .cu/.cpp sources compiled for
+    sm_100a by `make -C oracle refgpu`) on the same dump, same photon_n, same box: SURVEY 8(f) N2.  A performance
+    comparator only (float RNG, half-step bug, racy bias statistics: not an oracle)."""
+    from oracle import refharness as rh
+    exe = os.path.join(os.path.dirname(rh.CLI_PATH), "grmonty_ref_gpu")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "--harm_dump_path", dump, "--photon_n", str(int(photon_n)), "--mass_unit",
+                              repr(mass_unit), "--hotcross_cache", rh.HOTCROSS_CACHE], capture_output=True, text=True,
+                             timeout=600)
+        o = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 -- a comparator that fails to run is reported, not fatal
+        return {"error": str(e)[:200]}
+    return {"value": o["created"] / o["run_s"], "unit": "superphotons/s", "kind": "reference GPU build (unmodified "
+            "super_photon.cu, sm_100a) on this GPU", "created": o["created"], "recorded": o["recorded"],
+            "scattered": o["scattered"], "seconds": o["run_s"], "photon_n": int(photon_n)}
+
+
 def _oracle_port_run(args):
     dump, photon_n, mass_unit, seed = args
     import cuda_grmonty_b200 as gm
@@ -143,7 +163,7 @@ def main():
     ap.add_argument("--mass_unit", type=float, default=4.0e19)
     ap.add_argument("--n0", type=int, default=192)
     ap.add_argument("--n1", type=int, default=192)
-    ap.add_argument("--ref_photon_n", type=int, default=4000, help="photon_n of each reference CPU process")
+    ap.add_argument("--ref_photon_n", type=int, default=12000, help="photon_n of each reference CPU process")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
 
@@ -324,6 +344,9 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         out["cpu_baseline"] = run_reference_cpu(dump, args.ref_photon_n, args.mass_unit, cores)
+        ctx_gpu = run_reference_gpu(dump, args.photon_n, args.mass_unit)
+        if ctx_gpu:
+            out["ref_gpu_baseline"] = ctx_gpu
     json_out.write(json.dumps(out) + "\n")
     json_out.flush()
     if dist:
