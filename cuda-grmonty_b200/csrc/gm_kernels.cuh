@@ -241,7 +241,7 @@ __device__ __noinline__ void record_call(const TransportArgs *Ag, unsigned int s
 }
 
 #ifndef GM_ITERS_PER_SYNC
-#define GM_ITERS_PER_SYNC 4
+#define GM_ITERS_PER_SYNC 16
 #endif
 constexpr int kItersPerSync = GM_ITERS_PER_SYNC;
 

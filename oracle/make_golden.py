@@ -300,6 +300,8 @@ if __name__ == "__main__":
         gen_samplers()
     elif what == "spectrum":
         gen_spectrum()
+    elif what == "spectrum_1e6":
+        pass  # handled at the end of the file
     elif what == "spectrum_4e20":  # configs[3]: Compton-dominated regime, 8 seeds at photon_n = 2e4
         gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e20,))
     elif what == "spectrum_more":  # spectrum_more <first_seed> <n> [mass_unit]
@@ -309,6 +311,32 @@ if __name__ == "__main__":
         pass  # handled at the end of the file
     else:
         raise SystemExit(__doc__)
+
+
+def gen_spectrum_big(photon_n=1000000, seeds=6, mu=4e19):
+    """configs[1]: complete reference runs at the bench's photon_n (about 40 minutes per run on one core);
+    only counters and theta-summed spectra are kept (small fixture)."""
+    tmp = tempfile.mkdtemp()
+    dump = os.path.join(tmp, "dump192.txt")
+    make_harm_dump.write_dump(dump, *make_harm_dump.make_dump())
+    procs = []
+    for s in range(seeds):
+        sb = os.path.join(tmp, f"spec_{s}.bin")
+        cmd = [rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit", repr(mu),
+               "--seed", str(500 + s), "--hotcross_cache", rh.HOTCROSS_CACHE, "--spectrum_bin", sb]
+        procs.append((subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True), sb))
+    metas, specs = [], []
+    for p, sb in procs:
+        o, _ = p.communicate()
+        metas.append(json.loads(o.strip().splitlines()[-1]))
+        specs.append(np.fromfile(sb).reshape(6, 200, 13)[:, :, [0, 1, 2, 3]])
+    np.savez_compressed(os.path.join(GOLD, "spectrum_192_4e19_1e6.npz"), photon_n=np.array(photon_n),
+                        mass_unit=np.array(mu), created=np.array([m["created"] for m in metas]),
+                        scattered=np.array([m["scattered"] for m in metas]),
+                        recorded=np.array([m["recorded"] for m in metas]),
+                        max_tau_scatt=np.array([m["max_tau_scatt"] for m in metas]),
+                        run_s=np.array([m["run_s"] for m in metas]), spec=np.array(specs))
+    print("wrote spectrum_192_4e19_1e6.npz", [m["run_s"] for m in metas], file=sys.stderr)
 
 
 def gen_spectrum_file():
@@ -337,3 +365,5 @@ def gen_spectrum_file():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_file":
     gen_spectrum_file()
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6":
+    gen_spectrum_big()  # configs[1] (the bench workload): 6 complete reference runs at photon_n = 1e6
