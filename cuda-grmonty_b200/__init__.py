@@ -117,7 +117,7 @@ class Stats(C.Structure):
 ABI_SYMBOLS = [
     "grmonty_b200_create", "grmonty_b200_total_primaries", "grmonty_b200_run_range", "grmonty_b200_run",
     "grmonty_b200_allreduce", "grmonty_b200_device_accumulators", "grmonty_b200_result", "grmonty_b200_reset",
-    "grmonty_b200_destroy", "grmonty_b200_trim_cache", "grmonty_b200_last_error", "grmonty_b200_fp64_peak",
+    "grmonty_b200_destroy", "grmonty_b200_trim_cache", "grmonty_b200_last_error", "grmonty_b200_fp64_peak", "grmonty_b200_hotcross_table",
     "grmonty_b200_test_geometry", "grmonty_b200_test_dkdlam_step", "grmonty_b200_test_push_photon",
     "grmonty_b200_test_trajectory", "grmonty_b200_test_fluid_params", "grmonty_b200_test_radiation",
     "grmonty_b200_test_hotcross", "grmonty_b200_test_angles", "grmonty_b200_test_tetrad",
@@ -152,6 +152,7 @@ def lib():
         L.grmonty_b200_device_accumulators.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3
         L.grmonty_b200_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.grmonty_b200_fp64_peak.argtypes = [C.c_void_p, dp]
+        L.grmonty_b200_hotcross_table.argtypes = [C.c_int, dp]
         _lib = L
     return _lib
 
@@ -357,6 +358,15 @@ class Context:
         self._ck(self.L.grmonty_b200_test_philox(self.h, C.c_int64(len(c)), _ptr(c, C.c_uint32),
                                                  _ptr(k, C.c_uint32), _ptr(out, C.c_uint32)))
         return out
+
+
+def hotcross_table(device: int = 0) -> np.ndarray:
+    """[221][81] log10 hot cross-section table built on the GPU (grmonty_b200_hotcross_table)"""
+    t = np.zeros((221, 81))
+    rc = lib().grmonty_b200_hotcross_table(device, _ptr(t))
+    if rc != 0:
+        raise GrmontyError(f"grmonty_b200_hotcross_table failed ({rc}): {lib().grmonty_b200_last_error(None).decode()}")
+    return t
 
 
 # ---- host library binding (libgrmonty_b200_host.so): the reference's HARMModel surface -------------------------

@@ -805,6 +805,37 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
     delete ctx;
 }
 
+int grmonty_b200_hotcross_table(int device, double *table) {
+    grmonty_b200_ctx *ctx = nullptr; /* for the CK macro: errors go to the thread's create-error slot */
+    if (!table)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "null table");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, GRMONTY_B200_ECUDA, "no such CUDA device %d (there is no CPU fallback)", device);
+    CK(cudaSetDevice(device));
+    const int n = GRMONTY_B200_HOTCROSS_N;
+    const double l_min_w = std::log10(kHcMinW), l_min_t = std::log10(kHcMinT);
+    const double d_l_w = std::log10(kHcMaxW / kHcMinW) / kHcNW, d_l_t = std::log10(kHcMaxT / kHcMinT) / kHcNT;
+    std::vector<double> axes(kHcNW + 1 + kHcNT + 1);
+    for (int i = 0; i <= kHcNW; ++i)
+        axes[i] = std::pow(10.0, l_min_w + i * d_l_w);
+    for (int j = 0; j <= kHcNT; ++j)
+        axes[kHcNW + 1 + j] = std::pow(10.0, l_min_t + j * d_l_t);
+    double *d = nullptr;
+    CK(cudaMalloc(&d, (n + axes.size()) * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d + n, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        hotcross_table_kernel<<<(n + 63) / 64, 64>>>(d, d + n, d + n + kHcNW + 1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpy(table, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return fail(nullptr, GRMONTY_B200_ECUDA, "hotcross_table_kernel: %s", cudaGetErrorString(e));
+    return GRMONTY_B200_OK;
+}
+
 void grmonty_b200_trim_cache(void) {
     std::lock_guard<std::mutex> lock(g_arena_mutex);
     for (DeviceArena &a : g_arena_cache) {

@@ -428,6 +428,19 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
     }
 }
 
+/* Hot Compton cross-section table on the device (reference hotcross.cpp:60-79 with the numeric
+ * integral :108-142): one thread per (w, theta_e) cell runs the reference's 40 x 240-point midpoint sum in the
+ * reference's order, so the entries agree with the CPU table to rounding.  17 901 cells x 9 600 points. */
+__global__ void hotcross_table_kernel(double *table, const double *w_axis, const double *theta_axis) {
+    /* the axes 10^(l_min + i d_l) are evaluated on the host with std::pow, like the reference: the first theta_e
+     * is exactly the table edge 1e-4, where a last-bit difference would select the analytic Klein-Nishina branch */
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= (kHcNW + 1) * (kHcNT + 1))
+        return;
+    const int i = cell / (kHcNT + 1), j = cell % (kHcNT + 1);
+    table[cell] = log10(hotcross_num(w_axis[i], theta_axis[j]));
+}
+
 /* FP64 FMA peak probe: 8 independent dependent-FMA chains per thread */
 __global__ void fp64_peak_kernel(double *out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,

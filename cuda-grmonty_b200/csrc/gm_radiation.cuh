@@ -86,10 +86,13 @@ __device__ __forceinline__ double hc_klein_nishina(double w) {
  * which converges geometrically for this analytic integrand.  The reference calls std::cyl_bessel_k
  * (hotcross.cpp:157); only the cold out-of-table fall-back needs it on the device. */
 __device__ __noinline__ double k2_scaled(double x) {
-    const double h = 0.125;
+    /* step: the integrand is ~ exp(-x t^2 / 2) cosh(2t), of width 1/sqrt(x) for large x; the trapezoid error is
+     * ~ exp(-2 pi^2 / (h^2 x)), so h = 0.25 / sqrt(x) (error < 1e-130) once that is below the 0.125 that suffices
+     * for the broad small-x integrand */
+    const double h = x > 4.0 ? 0.25 / sqrt(x) : 0.125;
     double s = 0.5;
 #pragma unroll 1
-    for (int n = 1; n < 400; ++n) {
+    for (int n = 1; n < 4000; ++n) {
         const double t = n * h;
         const double arg = x * (cosh(t) - 1.0);
         if (arg > 745.0)
@@ -110,16 +113,24 @@ __device__ __noinline__ double hotcross_num(double w, double theta_e) {
         return hc_klein_nishina(w) * kSigmaThomson;
     const double k2f = (theta_e > 1.0e-2) ? k2_scaled(1.0 / theta_e) : sqrt(kPi * theta_e / 2.0);
     double cross = 0.0;
+    /* gamma_e - 1 ~ theta_e is the difference of two numbers of order one: the loop variable and gamma_e^2 - 1 are
+     * formed with explicitly rounded multiplies and adds (no FMA contraction), as the reference's host code does,
+     * otherwise the table entries at theta_e ~ 1e-4 drift by 5e-10 */
+    const double d_gamma = __dmul_rn(theta_e, kHcDGammaE);
+    const double gamma_0 = __dadd_rn(1.0, __dmul_rn(__dmul_rn(0.5, theta_e), kHcDGammaE));
+    const double gamma_max = __dadd_rn(1.0, __dmul_rn(kHcMaxGamma, theta_e));
 #pragma unroll 1
     for (double mu_e = -1.0 + 0.5 * kHcDMuE; mu_e < 1.0; mu_e += kHcDMuE) {
 #pragma unroll 1
-        for (double gamma_e = 1.0 + 0.5 * theta_e * kHcDGammaE; gamma_e < 1.0 + kHcMaxGamma * theta_e;
-             gamma_e += theta_e * kHcDGammaE) {
-            const double sq = sqrt(gamma_e * gamma_e - 1.);
+        for (double gamma_e = gamma_0; gamma_e < gamma_max; gamma_e = __dadd_rn(gamma_e, d_gamma)) {
+            const double sq = sqrt(__dadd_rn(__dmul_rn(gamma_e, gamma_e), -1.));
             const double dnd = (gamma_e * sq / (theta_e * k2f)) * exp(-(gamma_e - 1.) / theta_e);
             const double v = sq / gamma_e;
-            const double we = w * gamma_e * (1.0 - mu_e * v);
-            cross += theta_e * kHcDMuE * kHcDGammaE * (hc_klein_nishina(we) * (1.0 - mu_e * v)) * (0.5 * dnd);
+            const double one_m_muv = __dadd_rn(1.0, -__dmul_rn(mu_e, v));
+            const double we = w * gamma_e * one_m_muv;
+            cross = __dadd_rn(cross, __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(theta_e, kHcDMuE), kHcDGammaE),
+                                                         __dmul_rn(hc_klein_nishina(we), one_m_muv)),
+                                               __dmul_rn(0.5, dnd)));
         }
     }
     return cross * kSigmaThomson;

@@ -172,6 +172,11 @@ void grmonty_b200_trim_cache(void);
 /* Message of the last error on this context (ctx == NULL: of the last failed create on this thread). */
 const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx);
 
+/* Hot Compton cross-section table on the device: table[221][81] = log10 of the numeric integral of reference
+ * hotcross.cpp:108-142 on the grid of consts.hpp:97-112 (what hotcross::init_table fills, hotcross.cpp:60-79, 33 s on
+ * one CPU core).  Needs no context; `table` is a host buffer of GRMONTY_B200_HOTCROSS_N doubles. */
+int grmonty_b200_hotcross_table(int device, double *table);
+
 /* FP64 FMA throughput micro-benchmark on the context's device (TFLOP/s, FMA = 2 flop); the roofline
  * denominator of this path (MEASURED_PEAKS.json has no FP64 entry). */
 int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops);

@@ -136,6 +136,19 @@ def test_hotcross_out_of_table_fallback(ctx, orc_model):
     assert np.all(got > 0) and np.all(got < sig_t)
 
 
+def test_hotcross_table_built_on_device_matches_reference(gm, golden_model):
+    """SURVEY 8f N1: the [221][81] table of reference hotcross::init_table, computed by hotcross_table_kernel"""
+    import time
+    t0 = time.time()
+    got = gm.hotcross_table(0)
+    dt = time.time() - t0
+    want = np.asarray(golden_model["hotcross"]).reshape(221, 81)
+    assert np.all(np.isfinite(got))
+    # entries are log10(sigma) ~ -24: compare sigma itself to 1e-10 relative
+    assert np.max(np.abs(10.0 ** (got - want) - 1.0)) < 1e-10
+    assert dt < 5.0
+
+
 def test_bias_and_tetrads(ctx, golden):
     mt, ns, nr = golden["bias_stats"]
     got = ctx.t_bias(golden["bias_args"], mt, ns, nr)
