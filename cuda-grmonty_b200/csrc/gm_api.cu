@@ -56,6 +56,11 @@ struct grmonty_b200_ctx {
     SlotQueue carry{};
     PhotonPool stage{}; /* staging pool: suspended photons between two batches */
     unsigned long long n_carry = 0; /* records in `stage` waiting for the next batch */
+    unsigned long long h_qc[8] = {0}; /* staging of the queue counters written at each batch start */
+    unsigned long long h_counters[3] = {0, 0, 0}, h_maxtau_bits = 0; /* accumulators as of the last batch end */
+    bool h_bias_valid = false;
+    unsigned long long host_tracked = 0; /* primaries started (the device counts scattered children) */
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;
     DeviceArena arena;     /* the one device allocation all buffers below live in */
     size_t arena_used = 0;
     int budget = 256;               /* attempts a lineage may make per generation */
@@ -176,6 +181,8 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
+        CK(cudaEventCreate(&ctx->ev2));
+        CK(cudaEventCreate(&ctx->ev3));
 
         /* ---- parameter block ---- */
         GmParams &P = ctx->P;
@@ -457,6 +464,8 @@ int grmonty_b200_reset(grmonty_b200_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->d_maxtau, &bits, sizeof(bits), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->h_bias_valid = false;
+    ctx->host_tracked = 0;
     return GRMONTY_B200_OK;
 }
 
@@ -505,10 +514,11 @@ static int begin_batch(grmonty_b200_ctx *ctx, long long count) {
     if (ctx->used_carry)
         CK(cudaMemsetAsync(ctx->carry.entries, 0, ctx->used_carry * sizeof(unsigned int), ctx->stream));
     ctx->used_ready = ctx->used_scatter = ctx->used_carry = 0;
-    const unsigned long long qc[8] = {(unsigned long long)count, 0ull, 0ull, (unsigned long long)count, 0ull, 0ull,
-                                      0ull, 0ull};
-    CK(cudaMemcpyAsync(ctx->d_qctr, qc, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream)); /* qc is a stack buffer */
+    /* the source buffer lives in the context: it is rewritten only after the batch's final synchronisation */
+    unsigned long long *qc = ctx->h_qc;
+    qc[0] = qc[3] = (unsigned long long)count;
+    qc[1] = qc[2] = qc[4] = qc[5] = qc[6] = qc[7] = 0ull;
+    CK(cudaMemcpyAsync(ctx->d_qctr, qc, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
     return GRMONTY_B200_OK;
 }
 
@@ -529,7 +539,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         int rc = begin_batch(ctx, n_start);
         if (rc)
             return rc;
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(cudaEventRecord(ctx->ev2, ctx->stream));
         if (count > 0) {
             const int bb = 128;
             const long long want = (count + bb - 1) / bb;
@@ -546,10 +556,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
             ctx->stats.n_kernel_launches += 1;
             ctx->n_carry = 0;
         }
-        CK(cudaEventRecord(ctx->ev1, ctx->stream));
-        CK(cudaEventSynchronize(ctx->ev1));
-        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->stats.kernel_ms += ms;
+        CK(cudaEventRecord(ctx->ev3, ctx->stream)); /* read after the batch's one synchronisation below */
     }
     const size_t smem = (size_t)13 * ctx->threads * sizeof(double);
     /* do not launch far more threads than there are photons to start with (tiny generations / test batches) */
@@ -570,7 +577,18 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     v->fn<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    CK(cudaEventSynchronize(ctx->ev1));
+    /* one host synchronisation per batch: error word, queue counters and the accumulators the next generation's
+     * bias statistics are made of come back together */
+    unsigned int err = 0;
+    unsigned long long qc[8];
+    CK(cudaMemcpyAsync(&err, ctx->d_error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(qc, ctx->d_qctr, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->h_maxtau_bits, ctx->d_maxtau, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_bias_valid = true;
     if (prof) {
         cudaProfilerStop();
         prof_min = -1;
@@ -579,20 +597,16 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     ctx->stats.kernel_ms += ms;
     ctx->stats.transport_ms += ms;
     ctx->stats.n_kernel_launches += 1;
-    unsigned int err = 0;
-    unsigned long long qc[8];
-    CK(cudaMemcpyAsync(&err, ctx->d_error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(qc, ctx->d_qctr, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!preloaded) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+        ctx->stats.kernel_ms += ms;
+    }
     ctx->used_ready = std::min<unsigned long long>(qc[3], ctx->ready.capacity);
     ctx->used_scatter = std::min<unsigned long long>(qc[5], ctx->scatter.capacity);
     ctx->used_carry = std::min<unsigned long long>(qc[7], ctx->carry.capacity);
     ctx->stats.queue_high_water = std::max<uint64_t>(ctx->stats.queue_high_water, qc[0]);
-    /* photons tracked = records created: primaries here, scattered children counted on the device */
-    unsigned long long w0;
-    CK(cudaMemcpy(&w0, ctx->d_work, sizeof(w0), cudaMemcpyDeviceToHost));
-    w0 += (unsigned long long)count;
-    CK(cudaMemcpy(ctx->d_work, &w0, sizeof(w0), cudaMemcpyHostToDevice));
+    /* photons tracked = records created: primaries counted here, scattered children on the device */
+    ctx->host_tracked += (unsigned long long)count;
     if (err & 1u)
         return fail(ctx, GRMONTY_B200_EQUEUE,
                     "device photon pool/queue overflow: %llu records, %llu ready, %llu scatter, %llu carry entries "
@@ -607,8 +621,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
                         ctx->stage.capacity);
         carry_copy_kernel<<<(unsigned)((qc[7] + 127) / 128), 128, 0, ctx->stream>>>(
             ctx->stage, 0u, ctx->pool, 0u, ctx->carry.entries, (unsigned int)qc[7], nullptr);
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaGetLastError()); /* stream order keeps the next batch's queue clearing behind this copy */
         ctx->stats.n_kernel_launches += 1;
         ctx->n_carry = qc[7];
     }
@@ -617,9 +630,14 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
 
 static int read_bias_stats(grmonty_b200_ctx *ctx, GmBiasStats *b) {
     unsigned long long c[3], bits;
-    CK(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&bits, ctx->d_maxtau, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_bias_valid) { /* fetched with the previous batch's results */
+        memcpy(c, ctx->h_counters, sizeof(c));
+        bits = ctx->h_maxtau_bits;
+    } else {
+        CK(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&bits, ctx->d_maxtau, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     double mt;
     memcpy(&mt, &bits, sizeof(mt));
     *b = make_bias_stats(ctx->P.bias_norm, mt, (double)c[1], (double)c[2]);
@@ -696,6 +714,7 @@ int grmonty_b200_device_accumulators(grmonty_b200_ctx *ctx, void **spectrum, voi
         *counters = ctx->d_counters;
     if (max_tau)
         *max_tau = ctx->d_maxtau;
+    ctx->h_bias_valid = false; /* the caller may reduce into these buffers */
     return GRMONTY_B200_OK;
 }
 
@@ -740,6 +759,7 @@ int grmonty_b200_allreduce(grmonty_b200_ctx *ctx, void *nccl_comm, void *cuda_st
     if (r0 || r1 || r2 || r3)
         return fail(ctx, GRMONTY_B200_ENCCL, "ncclAllReduce failed (%d %d %d %d)", r0, r1, r2, r3);
     CK(cudaStreamSynchronize(s));
+    ctx->h_bias_valid = false;
     return GRMONTY_B200_OK;
 }
 
@@ -766,7 +786,7 @@ int grmonty_b200_result(grmonty_b200_ctx *ctx, double *spectrum, uint64_t counts
     if (stats) {
         unsigned long long w[8];
         CK(cudaMemcpy(w, ctx->d_work, sizeof(w), cudaMemcpyDeviceToHost));
-        ctx->stats.n_tracked = w[0];
+        ctx->stats.n_tracked = w[0] + ctx->host_tracked;
         ctx->stats.n_steps = w[1];
         ctx->stats.n_push_attempts = w[2];
         ctx->stats.n_interactions = w[3];
@@ -800,6 +820,10 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
         cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2)
+        cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3)
+        cudaEventDestroy(ctx->ev3);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
