@@ -276,6 +276,8 @@ def main():
     sync()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
+    print(f"[bench rank {rank}] wall {1e3 * wall / args.steps:.1f} ms/step, kernels {kernel_ms / args.steps:.1f} ms/step, "
+          f"generations {res['stats']['n_generations']}, attempts {res['stats']['n_push_attempts']}", file=sys.stderr)
     local = torch.tensor([wall, kernel_ms, transport_ms, flops, float(launches)], dtype=torch.float64, device=f"cuda:{dev}")
     if dist:
         mx = local.clone()

@@ -661,8 +661,11 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
     unsigned long long created = 0;
     GmBiasStats bias;
     for (long long g = 0; g_start < last; ++g) {
+        /* the schedule runs on rank-local positions (global position / world): every rank sees the generation sizes
+         * of a stand-alone run of its own share, whatever the number of GPUs */
         const long long g_end =
-            g_start + generation_size(g_start, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from, ctx->gen_fine_div, ctx->gen_ramp);
+            g_start + world * generation_size(g_start / world, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from,
+                                              ctx->gen_fine_div, ctx->gen_ramp);
         const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
         if (lo < hi) {
             long long f0 = lo + ((rank - lo % world) % world + world) % world; /* first index >= lo, = rank mod world */

@@ -99,7 +99,8 @@ typedef struct grmonty_b200_config {
      * must stay short relative to the run so far (the reference updates its statistics after every photon):
      * the generation starting at run position s holds gen0 positions if s < gen0, (gen_ramp - 1) s positions (the
      * cumulative count grows gen_ramp-fold) while s < gen_fine_from, then s / gen_fine_div positions, and never
-     * more than gen_cap. */
+     * more than gen_cap.  Positions are rank-local here (global position / world), so each GPU of a multi-GPU job
+     * runs the schedule of a stand-alone run of its own share. */
     int64_t gen0;           /* default 32 */
     int64_t gen_cap;        /* default 2^20 */
     int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over

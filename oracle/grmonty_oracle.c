@@ -1456,7 +1456,9 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
     int64_t g_start = 0;
     const int budget = m->budget > 0 ? m->budget : INT_MAX;
     for (int64_t g = 0; g_start < last; ++g) {
-        int64_t g_end = g_start + orc_generation_size(g_start, gen0, gen_cap, m->gen_fine_from, m->gen_fine_div, m->gen_ramp);
+        /* rank-local schedule, like the CUDA path (gm_api.cu grmonty_b200_run_range) */
+        int64_t g_end = g_start + world * orc_generation_size(g_start / world, gen0, gen_cap, m->gen_fine_from,
+                                                              m->gen_fine_div, m->gen_ramp);
         const int64_t lo = g_start > first ? g_start : first, hi = g_end < last ? g_end : last;
         if (lo < hi) {
             if (m->stats_mode == ORC_STATS_FROZEN) {
