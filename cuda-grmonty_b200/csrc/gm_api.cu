@@ -63,7 +63,7 @@ struct grmonty_b200_ctx {
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;
     DeviceArena arena;     /* the one device allocation all buffers below live in */
     size_t arena_used = 0;
-    int budget = 256;               /* attempts a lineage may make per generation */
+    int budget = 384;               /* attempts a lineage may make per generation */
     unsigned long long *d_qctr = nullptr; /* n_alloc, finished, ready head/tail, scatter head/tail, carry head/tail */
     unsigned long long used_ready = 0, used_scatter = 0, used_carry = 0; /* entries to clear before the next batch */
     Accumulators A{};
@@ -77,7 +77,7 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
-    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 4, gen_ramp = 8;
+    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 6, gen_ramp = 8;
     grmonty_b200_stats stats{};
     std::string err;
 };
@@ -570,7 +570,14 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         const char *e = getenv("GRMONTY_B200_PROFILE_MIN_COUNT");
         prof_min = e ? atoll(e) : -1;
     }
-    const bool prof = prof_min >= 0 && n_start >= prof_min;
+    /* GRMONTY_B200_PROFILE_DRAIN=k: bracket the k-th final-drain launch of the process instead */
+    static int prof_drain = -1;
+    if (prof_drain < 0)
+        prof_drain = getenv("GRMONTY_B200_PROFILE_DRAIN") ? atoi(getenv("GRMONTY_B200_PROFILE_DRAIN")) : 0;
+    const bool is_drain = budget == INT_MAX && !preloaded;
+    const bool prof = (prof_min >= 0 && n_start >= prof_min) || (prof_drain == 1 && is_drain);
+    if (is_drain && prof_drain > 1)
+        --prof_drain; /* not yet */
     if (prof)
         cudaProfilerStart();
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -592,11 +599,21 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     if (prof) {
         cudaProfilerStop();
         prof_min = -1;
+        prof_drain = 0;
     }
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.kernel_ms += ms;
     ctx->stats.transport_ms += ms;
     ctx->stats.n_kernel_launches += 1;
+    {
+        static int trace = -1; /* GRMONTY_B200_TRACE=1: one line per transport launch on stderr */
+        if (trace < 0)
+            trace = getenv("GRMONTY_B200_TRACE") ? 1 : 0;
+        if (trace)
+            fprintf(stderr, "[grmonty_b200] batch first=%lld count=%lld carried_in=%lld budget=%d blocks=%lld: %.3f ms, "
+                            "records=%llu ready=%llu scatter=%llu carried_out=%llu\n",
+                    first, count, n_carry, budget, blocks, ms, qc[0], qc[3], qc[5], qc[7]);
+    }
     if (!preloaded) {
         CK(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
         ctx->stats.kernel_ms += ms;

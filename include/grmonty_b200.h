@@ -104,12 +104,13 @@ typedef struct grmonty_b200_config {
     int64_t gen0;           /* default 32 */
     int64_t gen_cap;        /* default 2^20 */
     int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over
-                               to the next one (default 256); bounds the tail of every generation */
+                               to the next one (default 384); bounds the tail of every generation */
     int64_t gen_fine_from;  /* default 16384 */
     int64_t gen_ramp;       /* default 8 */
-    int64_t gen_fine_div;   /* default 4 (each generation adds 25 % to the run so far); <= 1: keep doubling.
+    int64_t gen_fine_div;   /* default 6 (each generation adds 1/6 to the run so far); <= 1: keep doubling.
                                Measured at configs[0] against 20 reference runs (profiles/r1_bias_schedule.txt):
-                               doubling gives +5.8 % scattered / +2.5 % recorded counts, div 4 +0.3 % / -0.05 %. */
+                               doubling with budget 256 gives +5.8 % scattered / +2.5 % recorded counts,
+                               div 6 with budget 384 gives +0.6 % / +0.1 %. */
 } grmonty_b200_config;
 
 /* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */

@@ -591,13 +591,26 @@ double orc_hotcross_num(double w, double theta_e, double k2f) {
 
 /* ref: hotcross.cpp:81-106.  The out-of-table numeric fall-back (:90-93) needs K2 and is out of the
  * oracle's reach in C99; it returns NaN there so that a test hitting it fails loudly. */
+/* Diagnostics (read by tools through ctypes): out-of-table cross-section calls, the longest-lived photon, and how far
+ * from the light cone scattered wave-vectors come out (a degenerate scattering tetrad shows up here). */
+double orc_diag_max_offcone = 0.0;
+uint64_t orc_diag_n_offcone = 0;
+int orc_diag_max_n_step = 0;
+double orc_diag_longest[10] = {0};
+uint64_t orc_n_out_of_table = 0;
+double orc_out_of_table_args[2] = {0.0, 0.0};
 double orc_hotcross_lkup(const orc_model *m, double w, double theta_e) {
     if (w * theta_e < 1.0e-6)
         return C_SIGMA_THOMSON;
     if (theta_e < C_HC_MIN_T)
         return hc_klein_nishina(w) * C_SIGMA_THOMSON;
-    if (w <= C_HC_MIN_W || w >= C_HC_MAX_W || theta_e <= C_HC_MIN_T || theta_e >= C_HC_MAX_T)
+    if (w <= C_HC_MIN_W || w >= C_HC_MAX_W || theta_e <= C_HC_MIN_T || theta_e >= C_HC_MAX_T) {
+        if (orc_n_out_of_table++ == 0) {
+            orc_out_of_table_args[0] = w;
+            orc_out_of_table_args[1] = theta_e;
+        }
         return NAN;
+    }
     const double l_w = log10(w);
     const double l_t = log10(theta_e);
     int i = (int)((l_w - c_hc_l_min_w()) / c_hc_d_l_w());
@@ -951,6 +964,19 @@ int orc_scatter_super_photon(const orc_model *m, orc_photon *ph, orc_photon *php
     if (isnan(php->k[1])) {
         php->w = 0.0;
         return 0;
+    }
+    { /* diagnostics: |k.k| relative to the size of its terms */
+        double kk = 0.0, sz = 0.0;
+        for (int a = 0; a < 4; ++a)
+            for (int b = 0; b < 4; ++b) {
+                kk += gcov[a][b] * php->k[a] * php->k[b];
+                sz += fabs(gcov[a][b] * php->k[a] * php->k[b]);
+            }
+        const double rel = fabs(kk) / (sz + 1e-300);
+        if (rel > orc_diag_max_offcone)
+            orc_diag_max_offcone = rel;
+        if (rel > 1e-6)
+            orc_diag_n_offcone++;
     }
     double tmp_k[4];
     ktp[0] *= -1.0;
@@ -1334,6 +1360,15 @@ static int track_loop(orc_model *m, orc_track_state *s) {
         ++s->n_step;
         if (s->n_step > C_MAX_N_STEP)
             break;
+    }
+    if (s->n_step > orc_diag_max_n_step) { /* diagnostics: the longest-lived photon seen and where it ended */
+        orc_diag_max_n_step = s->n_step;
+        for (int i = 0; i < 4; ++i) {
+            orc_diag_longest[i] = ph->x[i];
+            orc_diag_longest[4 + i] = ph->k[i];
+        }
+        orc_diag_longest[8] = ph->w;
+        orc_diag_longest[9] = (double)ph->n_scatt;
     }
     if (ph->x[1] > c_x1_max() && s->n_step <= C_MAX_N_STEP)
         orc_record_super_photon(m, ph);

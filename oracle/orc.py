@@ -251,8 +251,8 @@ class Model:
         self.L.orc_track_super_photon(self.ptr, C.byref(ph))
         return self.flat(ph)
 
-    def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22, budget=256, fine_from=16384,
-            fine_div=4, ramp=8):
+    def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22, budget=384, fine_from=16384,
+            fine_div=6, ramp=8):
         self.m.budget = budget if self.m.stats_mode == 0 else 0
         self.m.gen_fine_from, self.m.gen_fine_div, self.m.gen_ramp = fine_from, fine_div, ramp
         self.L.orc_run(self.ptr, first, last, rank, world, gen0, gen_cap)

@@ -113,9 +113,14 @@ def make_dump(n0=192, n1=192, a=0.9375, hslope=0.3, r_out=40.0, profile="torus_c
     pgas = (GAMMA - 1.0) * uu
     beta = 30.0
     bsq_target = 2.0 * pgas / beta
-    B3 = 0.9 * np.sqrt(bsq_target / gcov[3][3])
-    B1 = 0.3 * np.sqrt(bsq_target / gcov[1][1]) * np.sign(0.5 - x2)
-    B2 = np.zeros_like(r)
+    # All three components are non-zero everywhere, as in a turbulent GRMHD dump.  (A field that is purely toroidal
+    # anywhere makes the reference's scattering tetrad degenerate there -- make_tetrad orthogonalises d/dphi
+    # against u and b, tetrads.cpp:46-123 -- and the scattered wave-vectors come out off the light cone: with a
+    # radial component that changed sign across the equator, 60 % of the scatterings in the torus mid-plane did,
+    # and a few of those "photons" orbit the hole for 4e5 steps.)
+    B3 = 0.85 * np.sqrt(bsq_target / gcov[3][3])
+    B1 = 0.40 * np.sqrt(bsq_target / gcov[1][1])
+    B2 = 0.33 * np.sqrt(bsq_target / gcov[2][2]) * np.cos(np.pi * x2) ** 2 + 0.1 * np.sqrt(bsq_target / gcov[2][2])
     Bp = [np.zeros_like(r), B1, B2, B3]
     udotb = sum(ucov[m] * Bp[m] for m in range(1, 4))
     bcon = [udotb] + [(Bp[m] + ucon[m] * udotb) / ucon[0] for m in range(1, 4)]
