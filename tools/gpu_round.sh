@@ -26,7 +26,7 @@ for w in $what; do
         > $out/${tag}_launches.log 2>&1
       echo "launches rc=$?" ;;
     ncu)
-      GRMONTY_B200_PROFILE_MIN_COUNT=1000000 timeout 1200 ncu --set full --clock-control none --import-source on \
+      GRMONTY_B200_PROFILE_MIN_COUNT=700000 timeout 1200 ncu --set full --clock-control none --import-source on \
         --profile-from-start off -k regex:transport_kernel -c 1 -f -o $out/${tag}_transport \
         python tools/gpu_gen_profile.py 200 0 192 > $out/${tag}_ncu.log 2>&1
       echo "ncu rc=$?" ;;
