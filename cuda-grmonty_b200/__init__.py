@@ -99,7 +99,7 @@ class Config(C.Structure):
         ("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32),
         ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
         ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64), ("gen_budget", C.c_int64),
-        ("gen_fine_from", C.c_int64), ("gen_ramp", C.c_int64), ("gen_fine_div", C.c_int64),
+        ("gen_budget_spread", C.c_int64), ("gen_fine_from", C.c_int64), ("gen_ramp", C.c_int64), ("gen_fine_div", C.c_int64),
     ]
 
 
@@ -178,7 +178,7 @@ class Context:
     def __init__(self, model: dict, seed: int = 123, rank: int = 0, world: int = 1, device: int = 0,
                  threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
                  gen_cap: int = 0, gen_budget: int = 0, gen_fine_from: int = 0, gen_fine_div: int = 0,
-                 gen_ramp: int = 0):
+                 gen_ramp: int = 0, gen_budget_spread: int = 0):
         self.L = lib()
         cfg = Config()
         cfg.abi_version = 2
@@ -202,6 +202,7 @@ class Context:
         cfg.threads_per_block, cfg.blocks_per_sm = threads_per_block, blocks_per_sm
         cfg.queue_capacity, cfg.gen0, cfg.gen_cap, cfg.gen_budget = queue_capacity, gen0, gen_cap, gen_budget
         cfg.gen_fine_from, cfg.gen_fine_div, cfg.gen_ramp = gen_fine_from, gen_fine_div, gen_ramp
+        cfg.gen_budget_spread = gen_budget_spread
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))

@@ -77,7 +77,7 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
-    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 6, gen_ramp = 8;
+    long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 6, gen_ramp = 8, gen_budget_spread = 0;
     grmonty_b200_stats stats{};
     std::string err;
 };
@@ -432,6 +432,8 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             ctx->gen_fine_div = cfg->gen_fine_div;
         if (cfg->gen_ramp > 1)
             ctx->gen_ramp = cfg->gen_ramp;
+        if (cfg->gen_budget_spread != 0)
+            ctx->gen_budget_spread = cfg->gen_budget_spread; /* negative: off */
         return GRMONTY_B200_OK;
     }();
     if (rc != GRMONTY_B200_OK) {
@@ -533,6 +535,8 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     fill_args(ctx, bias, dbg, budget, args);
     CK(cudaMemcpy(ctx->d_args, &args, sizeof(args), cudaMemcpyHostToDevice));
     float ms = 0.f;
+    /* extra attempts for lineages that start early in the batch (see birth_kernel); none in the final drain */
+    const long long spread = (budget != INT_MAX && ctx->gen_budget_spread > 0) ? ctx->gen_budget_spread : 0;
     const long long n_carry = preloaded ? 0 : (long long)ctx->n_carry;
     const long long n_start = count + n_carry;
     if (!preloaded) {
@@ -545,13 +549,14 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
             const long long want = (count + bb - 1) / bb;
             const int nb = (int)std::min<long long>(want, (long long)ctx->sm_count * 16);
             birth_kernel<<<nb, bb, 0, ctx->stream>>>(args, ctx->d_zones, ctx->d_prefix, first, stride, count,
-                                                     ctx->perm_mult, ctx->total);
+                                                     ctx->perm_mult, ctx->total, spread);
             CK(cudaGetLastError());
             ctx->stats.n_kernel_launches += 1;
         }
         if (n_carry > 0) {
             carry_copy_kernel<<<(unsigned)((n_carry + 127) / 128), 128, 0, ctx->stream>>>(
-                ctx->pool, (unsigned int)count, ctx->stage, 0u, nullptr, (unsigned int)n_carry, ctx->ready.entries);
+                ctx->pool, (unsigned int)count, ctx->stage, 0u, nullptr, (unsigned int)n_carry, ctx->ready.entries,
+                spread > 0 ? -(int)(count / spread) : 0);
             CK(cudaGetLastError());
             ctx->stats.n_kernel_launches += 1;
             ctx->n_carry = 0;
@@ -637,7 +642,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
             return fail(ctx, GRMONTY_B200_EQUEUE, "carry-over staging pool overflow: %llu records (capacity %u)", qc[7],
                         ctx->stage.capacity);
         carry_copy_kernel<<<(unsigned)((qc[7] + 127) / 128), 128, 0, ctx->stream>>>(
-            ctx->stage, 0u, ctx->pool, 0u, ctx->carry.entries, (unsigned int)qc[7], nullptr);
+            ctx->stage, 0u, ctx->pool, 0u, ctx->carry.entries, (unsigned int)qc[7], nullptr, 0);
         CK(cudaGetLastError()); /* stream order keeps the next batch's queue clearing behind this copy */
         ctx->stats.n_kernel_launches += 1;
         ctx->n_carry = qc[7];

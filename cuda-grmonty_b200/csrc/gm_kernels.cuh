@@ -178,7 +178,7 @@ __host__ __device__ __forceinline__ long long permute_position(long long j, long
 __device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigned int slot, const double x[4],
                                                  const double k[4], double w, double e, double x1i, double x2i,
                                                  double n_e_0, double theta_e_0, double b_0, double e_0,
-                                                 int n_scatt, const Rng &rng) {
+                                                 int n_scatt, const Rng &rng, int clock0) {
     const GmParams &P = A.P;
     const GeoPoint q = geo_point(P, x[1], x[2]);
     const MetricCov g = metric_cov(P, q);
@@ -198,18 +198,22 @@ __device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigne
     pstore(A.pool, P_B0, slot, b_0);
     pstore(A.pool, P_E0, slot, e_0);
     __stcg(A.pool.n_scatt + slot, n_scatt);
-    __stcg(A.pool.gclock + slot, 0);
+    __stcg(A.pool.gclock + slot, clock0);
 }
 
 /* positions first, first + stride, ... (count of them) -> pool slots / ready-queue entries 0..count-1 */
+/* `spread` > 0: the t-th of the batch's primaries starts its lineage clock at -(count - 1 - t) / spread, i.e. may
+ * make that many attempts on top of the generation's budget -- lanes pick the primaries up in order, so a lineage that
+ * starts early has the rest of the generation to run without delaying its end */
 __global__ void birth_kernel(TransportArgs A, const ZoneData *zones, const long long *prefix, long long first,
-                             long long stride, long long count, long long mult, long long total) {
+                             long long stride, long long count, long long mult, long long total, long long spread) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
          t += (long long)gridDim.x * blockDim.x) {
         Birth B;
         make_primary(A.P, zones, prefix, permute_position(first + t * stride, mult, total), B);
+        const int clock0 = spread > 0 ? -(int)((count - 1 - t) / spread) : 0;
         store_new_photon(A, (unsigned int)t, B.x, B.k, B.w, B.e, B.x[1], B.x[2], B.n_e, B.theta_e, B.b, B.e, 0,
-                         B.rng);
+                         B.rng, clock0);
         A.ready.entries[t] = (unsigned int)t + 1u;
     }
 }
@@ -217,7 +221,7 @@ __global__ void birth_kernel(TransportArgs A, const ZoneData *zones, const long 
 /* copy carried records between pools: dst slot (dst0 + i) <- src slot (list ? list[i] - 1 : src0 + i);
  * when `ready` is given the destination slots are also published on that queue at position dst0 + i */
 __global__ void carry_copy_kernel(PhotonPool dst, unsigned int dst0, PhotonPool src, unsigned int src0,
-                                  const unsigned int *list, unsigned int n, unsigned int *ready_entries) {
+                                  const unsigned int *list, unsigned int n, unsigned int *ready_entries, int clock0) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
@@ -227,7 +231,7 @@ __global__ void carry_copy_kernel(PhotonPool dst, unsigned int dst0, PhotonPool 
     dst.rng[d] = src.rng[s];
     dst.n_scatt[d] = src.n_scatt[s];
     dst.n_step[d] = src.n_step[s];
-    dst.gclock[d] = 0;
+    dst.gclock[d] = clock0;
     if (ready_entries)
         ready_entries[d] = d + 1u;
 }

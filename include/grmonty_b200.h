@@ -105,6 +105,11 @@ typedef struct grmonty_b200_config {
     int64_t gen_cap;        /* default 2^20 */
     int64_t gen_budget;     /* push attempts a photon lineage may make per generation before it is carried over
                                to the next one (default 384); bounds the tail of every generation */
+    int64_t gen_budget_spread; /* > 0: the t-th of a generation's n primaries (rank-local) may make gen_budget +
+                               (n - 1 - t) / gen_budget_spread attempts and a carried lineage gen_budget + n /
+                               gen_budget_spread: lanes take the primaries in order, so a lineage that starts early
+                               can run for the rest of the generation without delaying its end (~100 attempts per
+                               primary on 37 888 lanes = one attempt per 384 positions); negative: off */
     int64_t gen_fine_from;  /* default 16384 */
     int64_t gen_ramp;       /* default 8 */
     int64_t gen_fine_div;   /* default 6 (each generation adds 1/6 to the run so far); <= 1: keep doubling.

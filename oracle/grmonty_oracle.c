@@ -1385,15 +1385,17 @@ void orc_track_super_photon(orc_model *m, orc_photon *ph) {
 }
 
 /* continue the photons suspended so far (they may be suspended again) */
-static void run_carried(orc_model *m) {
+static void run_carried(orc_model *m, int clock0) {
     size_t n = m->n_carry;
     if (!n)
         return;
     orc_track_state *list = (orc_track_state *)malloc(n * sizeof(orc_track_state));
     memcpy(list, m->carry, n * sizeof(orc_track_state));
     m->n_carry = 0;
-    for (size_t i = 0; i < n; ++i)
+    for (size_t i = 0; i < n; ++i) {
+        list[i].clock = clock0;
         track_loop(m, &list[i]);
+    }
     free(list);
 }
 
@@ -1440,10 +1442,12 @@ void orc_make_primary(const orc_model *m, const int64_t *prefix, const double *d
     orc_sample_zone_photon(m, i, j, dn_max[i * m->n1 + j], &r, ph);
 }
 
-void orc_run_primary(orc_model *m, const int64_t *prefix, const double *dn_max, int64_t idx) {
+void orc_run_primary(orc_model *m, const int64_t *prefix, const double *dn_max, int64_t idx, int clock0) {
     orc_photon ph;
     orc_make_primary(m, prefix, dn_max, idx, &ph);
-    orc_track_super_photon(m, &ph);
+    orc_track_state s;
+    if (track_begin(m, &ph, clock0, &s))
+        track_loop(m, &s);
     m->n_created++;
 }
 
@@ -1502,12 +1506,19 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
                 m->bias_n_recorded = (double)m->acc_n_recorded;
             }
             m->budget = budget;
-            run_carried(m); /* photons suspended in the previous generation continue with this one's statistics */
-            for (int64_t j = lo; j < hi; ++j) {
-                if ((j % world) != rank)
-                    continue;
-                orc_run_primary(m, prefix, dn_max, m->zone_order ? j : orc_permute(j, mult, (int64_t)total));
-            }
+            /* Attempt budgets (same rule as the CUDA path, gm_api.cu run_batch): the t-th of the generation's
+             * `count` primaries may make budget + (count - 1 - t) / spread attempts, carried lineages
+             * budget + count / spread -- lanes take the primaries in order, so a lineage that starts early has the
+             * rest of the generation to run without delaying its end.  A negative start value of the lineage
+             * clock implements it. */
+            int64_t f0 = lo + ((rank - lo % world) % world + world) % world;
+            const int64_t count = f0 < hi ? (hi - f0 + world - 1) / world : 0;
+            const int64_t spread = (budget != INT_MAX && m->gen_budget_spread > 0) ? m->gen_budget_spread : 0;
+            run_carried(m, spread ? -(int)(count / spread) : 0); /* suspended photons: this generation's statistics */
+            int64_t t = 0;
+            for (int64_t j = f0; j < hi; j += world, ++t)
+                orc_run_primary(m, prefix, dn_max, m->zone_order ? j : orc_permute(j, mult, (int64_t)total),
+                                spread ? -(int)((count - 1 - t) / spread) : 0);
         }
         g_start = g_end;
     }
@@ -1519,7 +1530,7 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
             m->bias_n_recorded = (double)m->acc_n_recorded;
         }
         m->budget = INT_MAX;
-        run_carried(m);
+        run_carried(m, 0);
     }
     m->budget = budget == INT_MAX ? 0 : budget;
     free(num);

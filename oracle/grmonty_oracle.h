@@ -81,7 +81,7 @@ typedef struct orc_model {
      * generation before it is suspended and continued in the next one; <= 0: unlimited (the reference) */
     int budget;
     /* generation schedule (shared with the CUDA path, see orc_generation_size) */
-    int64_t gen_fine_from, gen_fine_div, gen_ramp;
+    int64_t gen_fine_from, gen_fine_div, gen_ramp, gen_budget_spread;
     struct orc_track_state *carry; /* suspended photons (owned by the model) */
     uint64_t n_carry, cap_carry;
     /* outputs */
@@ -175,7 +175,7 @@ int64_t orc_perm_multiplier(int64_t total);
 int64_t orc_permute(int64_t j, int64_t mult, int64_t total);
 void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int64_t gen0, int64_t gen_cap);
 /* track one primary by global index; optionally returns the flat birth state */
-void orc_run_primary(orc_model *m, const int64_t *prefix, const double *dn_max, int64_t idx);
+void orc_run_primary(orc_model *m, const int64_t *prefix, const double *dn_max, int64_t idx, int clock0);
 void orc_make_primary(const orc_model *m, const int64_t *prefix, const double *dn_max, int64_t idx, orc_photon *ph);
 void orc_clear_outputs(orc_model *m);
 

@@ -36,7 +36,7 @@ class OrcModel(C.Structure):
         ("bias_max_tau_scatt", C.c_double), ("bias_n_scatt", C.c_double), ("bias_n_recorded", C.c_double),
         ("acc_max_tau_scatt", C.c_double), ("acc_n_scatt", C.c_uint64), ("acc_n_recorded", C.c_uint64),
         ("stats_mode", C.c_int), ("zone_order", C.c_int),
-        ("budget", C.c_int), ("gen_fine_from", C.c_int64), ("gen_fine_div", C.c_int64), ("gen_ramp", C.c_int64), ("carry", C.c_void_p), ("n_carry", C.c_uint64), ("cap_carry", C.c_uint64),
+        ("budget", C.c_int), ("gen_fine_from", C.c_int64), ("gen_fine_div", C.c_int64), ("gen_ramp", C.c_int64), ("gen_budget_spread", C.c_int64), ("carry", C.c_void_p), ("n_carry", C.c_uint64), ("cap_carry", C.c_uint64),
         ("spectrum", C.c_double * (N_TH * N_E * N_F)),
         ("n_created", C.c_uint64),
         ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64), ("n_interactions", C.c_uint64),
@@ -113,7 +113,7 @@ def lib():
                                              C.POINTER(OrcPhoton)]
         L.orc_make_primary.argtypes = [C.POINTER(OrcModel), C.POINTER(C.c_int64), dp, C.c_int64,
                                        C.POINTER(OrcPhoton)]
-        L.orc_run_primary.argtypes = [C.POINTER(OrcModel), C.POINTER(C.c_int64), dp, C.c_int64]
+        L.orc_run_primary.argtypes = [C.POINTER(OrcModel), C.POINTER(C.c_int64), dp, C.c_int64, C.c_int]
         L.orc_rng_primary.argtypes = [C.POINTER(OrcRng), C.c_uint64]
         L.orc_rng_zone.argtypes = [C.POINTER(OrcRng), C.c_uint64]
         _lib = L
@@ -252,7 +252,8 @@ class Model:
         return self.flat(ph)
 
     def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22, budget=384, fine_from=16384,
-            fine_div=6, ramp=8):
+            fine_div=6, ramp=8, spread=0):
         self.m.budget = budget if self.m.stats_mode == 0 else 0
         self.m.gen_fine_from, self.m.gen_fine_div, self.m.gen_ramp = fine_from, fine_div, ramp
+        self.m.gen_budget_spread = spread
         self.L.orc_run(self.ptr, first, last, rank, world, gen0, gen_cap)

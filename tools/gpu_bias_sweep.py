@@ -17,8 +17,10 @@ model = hm.model_dict()
 r_rec, r_scat, r_lum = ref["recorded"].mean(), ref["scattered"].mean(), ref["spec"][..., 1].sum(axis=(1, 2)).mean()
 print("reference: recorded %.0f (sd %.2f%%) scattered %.0f (sd %.2f%%) n=%d" % (
     r_rec, 100 * ref["recorded"].std(ddof=1) / r_rec, r_scat, 100 * ref["scattered"].std(ddof=1) / r_scat, len(ref["recorded"])))
-configs = [dict(gen_fine_div=8, gen_ramp=8, gen_budget=384), dict(gen_fine_div=6, gen_ramp=8, gen_budget=384),
-           dict(gen_fine_div=8, gen_ramp=8, gen_budget=320), dict(gen_fine_div=6, gen_ramp=8, gen_budget=512)]
+configs = [dict(gen_fine_div=6, gen_budget=384),
+           dict(gen_fine_div=6, gen_budget=128, gen_budget_spread=384), dict(gen_fine_div=6, gen_budget=192, gen_budget_spread=384),
+           dict(gen_fine_div=6, gen_budget=128, gen_budget_spread=256), dict(gen_fine_div=8, gen_budget=128, gen_budget_spread=384),
+           dict(gen_fine_div=6, gen_budget=256, gen_budget_spread=384)]
 for cfg in configs:
     rec, scat, lum, ms, gens = [], [], [], [], []
     for s in range(n_seeds):
