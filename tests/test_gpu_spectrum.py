@@ -130,3 +130,47 @@ def test_run_is_deterministic(gpu_runs, ref):
     assert (r["created"], r["recorded"], r["scattered"]) == (r0["created"], r0["recorded"], r0["scattered"])
     assert np.array_equal(r["spectrum"][:, :, 2], r0["spectrum"][:, :, 2])
     assert np.allclose(r["spectrum"][:, :, 1], r0["spectrum"][:, :, 1], rtol=1e-9, atol=0)
+
+
+def test_bench_workload_photon_n_1e6_vs_reference():
+    """configs[1] (the bench workload, photon_n = 1e6): 6 CUDA runs against 6 complete runs of the reference CLI
+    (36 minutes each on one core; tests/golden/spectrum_192_4e19_1e6.npz, `oracle/make_golden.py spectrum_1e6`)."""
+    import tempfile
+    import cuda_grmonty_b200 as gm
+    from tools import make_harm_dump
+    ref = dict(np.load(os.path.join(ROOT, "tests", "golden", "spectrum_192_4e19_1e6.npz")))
+    dump = os.path.join(tempfile.mkdtemp(), "dump192.txt")
+    make_harm_dump.write_dump(dump, *make_harm_dump.make_dump(n0=192, n1=192))
+    hm = gm.HarmModel(int(ref["photon_n"]), float(ref["mass_unit"]))
+    hm.read_file(dump)
+    hm.init()
+    model = hm.model_dict()
+    runs = []
+    for s in range(len(ref["recorded"])):
+        ctx = gm.Context(model, seed=4000 + s)
+        ctx.run()
+        runs.append(ctx.result())
+        ctx.close()
+    rep = {}
+    g_lum = np.array([r["spectrum"][:, :, 1].sum() for r in runs])
+    r_lum = ref["spec"][..., 1].sum(axis=(1, 2))
+    for name, g, r in (("luminosity", g_lum, r_lum),
+                       ("recorded", np.array([r["recorded"] for r in runs], float), ref["recorded"].astype(float)),
+                       ("scattered", np.array([r["scattered"] for r in runs], float), ref["scattered"].astype(float))):
+        d = g.mean() / r.mean() - 1
+        se = np.hypot(g.std(ddof=1) / np.sqrt(len(g)) / g.mean(), r.std(ddof=1) / np.sqrt(len(r)) / r.mean())
+        rep[name] = {"rel_diff": float(d), "std_err": float(se)}
+    gs = np.array([r["spectrum"][:, :, 1] for r in runs])
+    rs = ref["spec"][..., 1]
+    mask = ref["spec"][..., 2].mean(0) >= 1e3
+    var = gs.var(0, ddof=1) / len(gs) + rs.var(0, ddof=1) / len(rs)
+    z = (gs.mean(0) - rs.mean(0))[mask] / np.sqrt(var[mask])
+    l1 = float(np.abs(gs.mean(0) - rs.mean(0))[mask].sum() / rs.mean(0)[mask].sum())
+    rep["spectrum"] = {"bins": int(mask.sum()), "chi2_per_bin": float((z ** 2).mean()), "l1": l1,
+                       "max_abs_z": float(np.abs(z).max())}
+    print(rep)
+    report("configs1_photon_n_1e6", rep | {"n_gpu_seeds": len(runs), "n_ref_seeds": int(len(r_lum))})
+    for name in ("luminosity", "recorded", "scattered"):
+        assert abs(rep[name]["rel_diff"]) < 0.01 + 2 * rep[name]["std_err"], (name, rep[name])
+    assert rep["spectrum"]["chi2_per_bin"] < 2.0          # variances from 6 + 6 samples: E[z^2] ~ 1.6
+    assert l1 < 0.02
