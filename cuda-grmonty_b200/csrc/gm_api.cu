@@ -21,6 +21,8 @@
 #include <vector>
 
 #include "../../include/grmonty_b200.h"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "gm_kernels.cuh"
 
 using namespace gm;
@@ -57,6 +59,15 @@ struct grmonty_b200_ctx {
     PhotonPool stage{}; /* staging pool: suspended photons between two batches */
     unsigned long long n_carry = 0; /* records in `stage` waiting for the next batch */
     unsigned long long h_qc[8] = {0}; /* staging of the queue counters written at each batch start */
+    /* issue order within a generation: primaries of long-lived zones first (see run_batch) */
+    unsigned long long *d_zone_cost = nullptr; /* [2][n0] */
+    std::vector<unsigned long long> h_zone_cost;
+    unsigned char *d_bin_rank = nullptr, *d_keys_in = nullptr, *d_keys_out = nullptr;
+    long long *d_vals_in = nullptr, *d_vals_out = nullptr;
+    void *d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    long long sort_cap = 0;
+    int order_mode = 1; /* 0: positions in sequence, 1: sorted by measured zone lifetime */
     unsigned long long h_counters[3] = {0, 0, 0}, h_maxtau_bits = 0; /* accumulators as of the last batch end */
     bool h_bias_valid = false;
     unsigned long long host_tracked = 0; /* primaries started (the device counts scattered children) */
@@ -249,6 +260,13 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
                           ((size_t)ctx->ready.capacity + ctx->scatter.capacity + ctx->carry.capacity) *
                               sizeof(unsigned int) +
                           (size_t)kNThBins * kNEBins * kSpecFields * sizeof(double) + sizeof(TransportArgs) + 4096;
+            /* issue-order sort buffers for one batch (keys 1 B, values 8 B, double-buffered) + cub temporary storage */
+            ctx->sort_cap = (long long)std::max<unsigned long long>(1024, cap / 4);
+            cub::DeviceRadixSort::SortPairs(nullptr, ctx->sort_tmp_bytes, (const unsigned char *)nullptr,
+                                            (unsigned char *)nullptr, (const long long *)nullptr, (long long *)nullptr,
+                                            (int)ctx->sort_cap, 0, 8, ctx->stream);
+            need += (size_t)ctx->sort_cap * 2 * (1 + sizeof(long long)) + ctx->sort_tmp_bytes +
+                    (size_t)cfg->n0 * (2 * sizeof(unsigned long long) + 1);
             need += 64 * 256; /* alignment padding of the ~40 sub-allocations */
             {
                 std::lock_guard<std::mutex> lock(g_arena_mutex);
@@ -380,6 +398,20 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         CK(cudaMemsetAsync(ctx->ready.entries, 0, (size_t)ctx->ready.capacity * sizeof(unsigned int), ctx->stream));
         CK(cudaMemsetAsync(ctx->scatter.entries, 0, (size_t)ctx->scatter.capacity * sizeof(unsigned int), ctx->stream));
         CK(cudaMemsetAsync(ctx->carry.entries, 0, (size_t)ctx->carry.capacity * sizeof(unsigned int), ctx->stream));
+        CK(arena_alloc(ctx, &ctx->d_zone_cost, (size_t)2 * cfg->n0));
+        CK(arena_alloc(ctx, &ctx->d_bin_rank, (size_t)cfg->n0));
+        CK(arena_alloc(ctx, &ctx->d_keys_in, (size_t)ctx->sort_cap));
+        CK(arena_alloc(ctx, &ctx->d_keys_out, (size_t)ctx->sort_cap));
+        CK(arena_alloc(ctx, &ctx->d_vals_in, (size_t)ctx->sort_cap));
+        CK(arena_alloc(ctx, &ctx->d_vals_out, (size_t)ctx->sort_cap));
+        {
+            char *tmp = nullptr;
+            CK(arena_alloc(ctx, &tmp, ctx->sort_tmp_bytes + 256));
+            ctx->d_sort_tmp = tmp;
+        }
+        ctx->h_zone_cost.assign((size_t)2 * cfg->n0, 0ull);
+        if (const char *e = getenv("GRMONTY_B200_ORDER"))
+            ctx->order_mode = atoi(e);
         CK(arena_alloc(ctx, &ctx->d_qctr, 8));
         CK(cudaMemsetAsync(ctx->d_qctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
         ctx->pool.n_alloc = ctx->d_qctr;
@@ -460,6 +492,8 @@ int grmonty_b200_reset(grmonty_b200_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(unsigned int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_zone_cost, 0, (size_t)2 * ctx->P.n0 * sizeof(unsigned long long), ctx->stream));
+    std::fill(ctx->h_zone_cost.begin(), ctx->h_zone_cost.end(), 0ull);
     unsigned long long bits;
     const double mt = ctx->cfg.max_tau_scatt0;
     memcpy(&bits, &mt, sizeof(bits));
@@ -504,6 +538,7 @@ static void fill_args(grmonty_b200_ctx *ctx, const GmBiasStats &bias, const Debu
     args.budget = budget;
     args.A = ctx->A;
     args.D = dbg;
+    args.zone_cost = ctx->d_zone_cost;
     args.self = ctx->d_args;
 }
 
@@ -544,12 +579,48 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         if (rc)
             return rc;
         CK(cudaEventRecord(ctx->ev2, ctx->stream));
+        /* Issue order.  Lanes take the batch's pool slots in sequence, and a launch ends when its last lineage has
+         * finished or used up its budget, so the primaries that live longest should start first (longest-processing-
+         * time-first): lineages born at r = 3..10 M make ~400 attempts on the bench dump, those born inside the
+         * photon orbit or beyond 15 M fewer than 50.  The transport kernel counts steps of finished primaries per
+         * radial bin of their birth zone; once 4096 primaries have finished, each batch is sorted by the measured
+         * mean lifetime of its zones' bins (cub radix sort on an 8-bit rank).  Results do not depend on the order. */
+        const long long *order = nullptr;
+        if (count > 0 && ctx->order_mode == 1 && count <= ctx->sort_cap && ctx->P.n0 <= 4096) {
+            const int n0 = ctx->P.n0;
+            unsigned long long finished = 0;
+            for (int i = 0; i < n0; ++i)
+                finished += ctx->h_zone_cost[n0 + i];
+            if (finished >= 4096) {
+                std::vector<std::pair<double, int>> by_cost(n0);
+                for (int i = 0; i < n0; ++i) {
+                    const unsigned long long c = ctx->h_zone_cost[n0 + i];
+                    by_cost[i] = {c ? (double)ctx->h_zone_cost[i] / (double)c : 0.0, i};
+                }
+                std::stable_sort(by_cost.begin(), by_cost.end(),
+                                 [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; });
+                std::vector<unsigned char> rank(n0);
+                for (int r = 0; r < n0; ++r) /* at most 256 distinct ranks: bins of similar lifetime share one */
+                    rank[by_cost[r].second] = (unsigned char)((long long)r * 256 / n0);
+                CK(cudaMemcpyAsync(ctx->d_bin_rank, rank.data(), n0, cudaMemcpyHostToDevice, ctx->stream));
+                order_key_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+                    ctx->d_prefix, n0, ctx->P.n1, ctx->d_bin_rank, first, stride, count, ctx->perm_mult, ctx->total,
+                    ctx->d_keys_in, ctx->d_vals_in);
+                CK(cudaGetLastError());
+                size_t tmp_bytes = ctx->sort_tmp_bytes;
+                CK(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp, tmp_bytes, ctx->d_keys_in, ctx->d_keys_out,
+                                                   ctx->d_vals_in, ctx->d_vals_out, (int)count, 0, 8, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream)); /* `rank` is a stack buffer */
+                order = ctx->d_vals_out;
+                ctx->stats.n_kernel_launches += 2;
+            }
+        }
         if (count > 0) {
             const int bb = 128;
             const long long want = (count + bb - 1) / bb;
             const int nb = (int)std::min<long long>(want, (long long)ctx->sm_count * 16);
             birth_kernel<<<nb, bb, 0, ctx->stream>>>(args, ctx->d_zones, ctx->d_prefix, first, stride, count,
-                                                     ctx->perm_mult, ctx->total, spread);
+                                                     ctx->perm_mult, ctx->total, spread, order);
             CK(cudaGetLastError());
             ctx->stats.n_kernel_launches += 1;
         }
@@ -599,6 +670,8 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
                        ctx->stream));
     CK(cudaMemcpyAsync(&ctx->h_maxtau_bits, ctx->d_maxtau, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                        ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_zone_cost.data(), ctx->d_zone_cost, ctx->h_zone_cost.size() * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->h_bias_valid = true;
     if (prof) {

@@ -205,17 +205,41 @@ __device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigne
 /* `spread` > 0: the t-th of the batch's primaries starts its lineage clock at -(count - 1 - t) / spread, i.e. may
  * make that many attempts on top of the generation's budget -- lanes pick the primaries up in order, so a lineage that
  * starts early has the rest of the generation to run without delaying its end */
+/* `order` (optional): the batch's primary indices sorted by the expected lifetime of their birth zone, longest first.
+ * Lanes take pool slots in order, so the long-lived lineages start first and the generation's drain is short; the
+ * results do not depend on the order (statistics are frozen within a generation). */
 __global__ void birth_kernel(TransportArgs A, const ZoneData *zones, const long long *prefix, long long first,
-                             long long stride, long long count, long long mult, long long total, long long spread) {
+                             long long stride, long long count, long long mult, long long total, long long spread,
+                             const long long *order) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
          t += (long long)gridDim.x * blockDim.x) {
         Birth B;
-        make_primary(A.P, zones, prefix, permute_position(first + t * stride, mult, total), B);
+        make_primary(A.P, zones, prefix, order ? order[t] : permute_position(first + t * stride, mult, total), B);
         const int clock0 = spread > 0 ? -(int)((count - 1 - t) / spread) : 0;
         store_new_photon(A, (unsigned int)t, B.x, B.k, B.w, B.e, B.x[1], B.x[2], B.n_e, B.theta_e, B.b, B.e, 0,
                          B.rng, clock0);
         A.ready.entries[t] = (unsigned int)t + 1u;
     }
+}
+
+/* sort keys of a batch: key[t] = rank of the birth zone's radial bin (0 = longest-lived), val[t] = primary index */
+__global__ void order_key_kernel(const long long *prefix, int n0, int n1, const unsigned char *bin_rank,
+                                 long long first, long long stride, long long count, long long mult, long long total,
+                                 unsigned char *keys, long long *vals) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= count)
+        return;
+    const long long idx = permute_position(first + t * stride, mult, total);
+    long long lo = 0, hi = (long long)n0 * n1;
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= idx)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    keys[t] = bin_rank[(int)(lo / n1)];
+    vals[t] = idx;
 }
 
 /* copy carried records between pools: dst slot (dst0 + i) <- src slot (list ? list[i] - 1 : src0 + i);
@@ -242,6 +266,17 @@ extern __shared__ double gm_smem[];
 __device__ __noinline__ void record_call(const TransportArgs *Ag, unsigned int slot, double x2, double x3, double w,
                                          double tau_abs, double tau_scatt) {
     record_super_photon(*Ag, slot, x2, x3, w, tau_abs, tau_scatt);
+}
+
+/* lifetime statistics of primaries by birth radius (cold: once per photon) */
+__device__ __noinline__ void cost_call(const TransportArgs *Ag, unsigned int slot, int n_step) {
+    const TransportArgs &A = *Ag;
+    if (!A.zone_cost || __ldcg(A.pool.n_scatt + slot) != 0)
+        return;
+    int i = (int)((pload(A.pool, P_X1I, slot) - A.P.x_start1) * A.P.inv_dx1);
+    i = max(0, min(i, A.P.n0 - 1));
+    atomicAdd(A.zone_cost + i, (unsigned long long)n_step);
+    atomicAdd(A.zone_cost + A.P.n0 + i, 1ull);
 }
 
 #ifndef GM_ITERS_PER_SYNC
@@ -359,6 +394,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                 bool record;
                 const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
                 if (r == STEP_FINISHED) {
+                    cost_call(A.self, L.slot, L.n_step);
                     if (record) {
                         record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
                         L.status |= 1;

@@ -92,6 +92,9 @@ struct TransportArgs {
     int budget;      /* attempts a lineage may make per generation ("generation clock") */
     Accumulators A;
     DebugOut D;
+    /* [2][n0]: sum of steps and number of finished PRIMARIES per radial bin of their birth zone: what the host
+     * sorts the next generations' issue order by (long-lived zones first; see gm_api.cu run_batch) */
+    unsigned long long *zone_cost;
     /* device-global copy of this very struct: out-of-line (cold) stages take it by pointer so that the kernel
      * parameter itself never has its address taken and stays in the constant bank for the hot loop */
     const TransportArgs *self;

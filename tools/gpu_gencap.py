@@ -10,9 +10,7 @@ if not os.path.exists(p):
     make_harm_dump.write_dump(p, *make_harm_dump.make_dump(n0=192, n1=192))
 hm = gm.HarmModel(1000000, 4e19); hm.read_file(p); hm.init()
 model = hm.model_dict()
-for cfg in (dict(), dict(gen_budget=128, gen_budget_spread=256), dict(gen_budget=192, gen_budget_spread=256),
-            dict(gen_budget=128, gen_budget_spread=384), dict(gen_budget=256, gen_budget_spread=384),
-            dict(gen_budget=96, gen_budget_spread=192)):
+for cfg in (dict(), dict(gen_budget=256), dict(gen_budget=512)):
     c = gm.Context(model, **cfg)
     c.run(0, 20000); c.reset()
     t0 = time.time(); c.run(); dt = time.time() - t0
