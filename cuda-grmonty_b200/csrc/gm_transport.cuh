@@ -437,11 +437,7 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
     const double b_e = outside ? 1.0 : f.b;
     const double l_nu = fm::log_(nu_e), l_theta = fm::log_(te_e);
     const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta);
-#ifdef GM_DIAG_NO_ABS /* diagnostic build only: drops ~250 hot instructions to probe instruction-cache sensitivity */
-    const double a_af = 0.0 * mu;
-#else
     const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta);
-#endif
     const double bf = bias_func(P, A.bias, te_e, L.w);
     double d_tau_scatt, d_tau_abs, bias;
     if (outside) {
