@@ -20,6 +20,21 @@
  * row, in each fixed-point iteration, instead of holding the 36 connection components across the two iterations.
  * Measured on B200: t_push_kernel 194 -> 165 registers, transport kernel spills 102 -> 40 bytes, run time -2.6 %
  * in spite of the recomputation. */
+/* Measured switches (tools/gpu_ab.sh, interleaved A/B on one B200, configs[1], ms per step; base 706):
+ *   GM_ACQUIRE_POLL   ld.acquire on the ready-queue entry instead of ld.volatile + membar    694  (kept)
+ *   GM_PREFETCH_FLUID prefetch.global.L1 of the four zone records one attempt ahead          724  (off: the extra
+ *                     address arithmetic and LSU slots cost more than the L2 latency they hide at 8 warps/SM)
+ *   GM_SMEM_TABLES    hot cross-section + K2 tables in shared memory (145 KB)                721  (off: the carve-out
+ *                     shrinks L1 from ~200 KB to ~60 KB and the fluid-grid / local-memory hit rate pays for it) */
+#ifndef GM_PREFETCH_FLUID
+#define GM_PREFETCH_FLUID 0
+#endif
+#ifndef GM_SMEM_TABLES
+#define GM_SMEM_TABLES 0
+#endif
+#ifndef GM_ACQUIRE_POLL
+#define GM_ACQUIRE_POLL 1
+#endif
 #ifndef GM_FUSED_RHS
 #define GM_FUSED_RHS 1
 #endif
@@ -342,6 +357,20 @@ __device__ __forceinline__ double rel_change(double a, double b) {
 #endif
 }
 
+__device__ __forceinline__ void prefetch_fluid_cell(const GmParams &P, double x1, double x2) {
+    if (x1 < P.x_start1 || x1 > P.x_stop1 || x2 < P.x_start2 || x2 > P.x_stop2)
+        return;
+    int i = (int)((x1 - P.x_start1) * P.inv_dx1 - 0.5 + 1000) - 1000;
+    int j = (int)((x2 - P.x_start2) * P.inv_dx2 - 0.5 + 1000) - 1000;
+    i = max(0, min(i, P.n0 - 2));
+    j = max(0, min(j, P.n1 - 2));
+    const double *z = P.grid + ((size_t)i * P.n1 + j) * 8;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(z));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(z + 8));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(z + (size_t)P.n1 * 8));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(z + (size_t)P.n1 * 8 + 8));
+}
+
 /* One push_photon attempt of size dl from (x,k,dk) (reference harm_model.cpp:1230-1277): half kick, drift,
  * connection at the new point, <= 2 fixed-point iterations, energy check.  Returns true if the attempt must
  * be rejected and halved (the caller applies the depth limit).  Outputs are written to xn/kn/dkn/e1. */
@@ -357,6 +386,11 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
         kp[i] = kh[i] + d;
         xn[i] = x[i] + kh[i] * dl;
     }
+    /* the interaction step after an accepted attempt interpolates the fluid at xn: start pulling its four zone
+     * records (2 x 128 B) into L1 now, a whole attempt ahead of their use (an L2 hit costs ~600 cycles otherwise) */
+#if GM_PREFETCH_FLUID
+    prefetch_fluid_cell(P, xn[1], xn[2]);
+#endif
     q = geo_point(P, xn[1], xn[2]);
 #if !GM_FUSED_RHS
     Connection c;

@@ -108,6 +108,11 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
     return *reinterpret_cast<const volatile unsigned int *>(p);
 }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ double pload(const PhotonPool &pool, int field, unsigned int slot) {
     return __ldcg(pool.f + (size_t)field * pool.capacity + slot);
 }
@@ -416,7 +421,8 @@ enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_S
  * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER).
  * Single exit, no early returns: the lanes of a warp must leave this function together (see advance). */
 __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const GeoPoint &q,
-                                               const double *snap, int snap_stride, Work &wk) {
+                                               const double *snap, int snap_stride, Work &wk, const double *hc_tab,
+                                               const double *k2_tab) {
     const GmParams &P = A.P;
     ++wk.interactions;
     /* q = geometry at the new position, already evaluated by the accepted push attempt */
@@ -436,8 +442,8 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
     const double te_e = outside ? 1.0 : f.theta_e, ne_e = outside ? 1.0 : f.n_e;
     const double b_e = outside ? 1.0 : f.b;
     const double l_nu = fm::log_(nu_e), l_theta = fm::log_(te_e);
-    const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta);
-    const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta);
+    const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta, hc_tab);
+    const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta, k2_tab);
     const double bf = bias_func(P, A.bias, te_e, L.w);
     double d_tau_scatt, d_tau_abs, bias;
     if (outside) {
@@ -511,7 +517,8 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
  * the middle of a halved step run phase B separately: ncu showed 15.6 of ~27 live threads per instruction.)
  * `record` tells whether a finished photon escaped through r > r_max (reference :1066-1068). */
 __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, unsigned int live, double *snap,
-                                              int snap_stride, Work &wk, bool &record) {
+                                              int snap_stride, Work &wk, bool &record, const double *hc_tab,
+                                              const double *k2_tab) {
     const GmParams &P = A.P;
     record = false;
     StepResult st = STEP_CONTINUE;
@@ -584,7 +591,7 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, u
             st = STEP_FINISHED;
         } else {
             if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos)
-                st = interact(A, L, q, snap, snap_stride, wk);
+                st = interact(A, L, q, snap, snap_stride, wk, hc_tab, k2_tab);
             if (st == STEP_CONTINUE) {
                 ++L.n_step;
                 if (L.n_step > kMaxNStep)
