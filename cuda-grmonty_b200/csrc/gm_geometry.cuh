@@ -334,7 +334,7 @@ __device__ __forceinline__ void init_dkdlam(const GmParams &P, const double x[4]
 __device__ __forceinline__ double step_size(const GmParams &P, const double x[4], const double k[4]) {
     const double b1 = fabs(k[1]) + kEps, b2 = fabs(k[2]) + kEps, b3 = fabs(k[3]) + kEps;
     const double a1 = fabs(kStepEps * x[1]);
-    const double a2 = fabs(kStepEps * fmin(x[2], P.x_stop2 - x[2]));
+    const double a2 = fabs(kStepEps * fm::min_(x[2], P.x_stop2 - x[2]));
     const double a3 = kStepEps;
     const double i1 = fm::div(b1, a1 + kEps * b1);
     const double i2 = fm::div(b2, a2 + kEps * b2);

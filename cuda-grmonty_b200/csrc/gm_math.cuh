@@ -49,6 +49,10 @@ GM_HD uint64_t to_bits(double d) {
     return u;
 #endif
 }
+/* min/max by one compare and a select: fmin()/fmax() cost ~8 instructions each for their IEEE NaN rules.  A NaN in
+ * the FIRST argument yields the second (as fmin/fmax do); callers put the constant bound second. */
+GM_HD double min_(double a, double b) { return a < b ? a : b; }
+GM_HD double max_(double a, double b) { return a > b ? a : b; }
 GM_HD int hi_word(double d) { return (int)(to_bits(d) >> 32); }
 GM_HD double with_hi(double d, int hi) {
     return from_bits((to_bits(d) & 0xffffffffull) | ((uint64_t)(uint32_t)hi << 32));
@@ -214,24 +218,24 @@ GM_HD double exp_core(double r, double n) {
 }
 
 GM_HD double exp_(double x) {
-    const double xc = fmin(fmax(x, -708.0), 709.0);
-    const double t = fma(xc, C_(LOG2E), C_(MAGIC));
+    /* no clamp of x: inside [-708, 709.78] n stays in [-1021, 1024] (n = 1024 only with r < 0, p < 1, so the
+     * exponent field still fits); outside, whatever the core produced is replaced by the selects below */
+    const double t = fma(x, C_(LOG2E), C_(MAGIC));
     const double n = t - C_(MAGIC);
-    double r = fma(n, -C_(LN2_HI), xc);
+    double r = fma(n, -C_(LN2_HI), x);
     r = fma(n, -C_(LN2_LO), r);
     double v = exp_core(r, n);
     v = x < -708.0 ? 0.0 : v;
     v = x > 709.78 ? from_bits(0x7ff0000000000000ull) : v;
-    return x != x ? x : v; /* NaN in, NaN out (the clamps above would hide it) */
+    return x != x ? x : v; /* NaN in, NaN out */
 }
 
 /* 10^x */
 GM_HD double exp10_(double x) {
-    const double xc = fmin(fmax(x, -307.0), 308.0);
-    const double t = fma(xc, C_(LOG2_10), C_(MAGIC));
+    const double t = fma(x, C_(LOG2_10), C_(MAGIC)); /* unclamped, as in exp_ */
     const double n = t - C_(MAGIC);
     /* x - n log10(2) in two parts, then to the natural base */
-    double r = fma(n, -C_(LG2_HI), xc);
+    double r = fma(n, -C_(LG2_HI), x);
     r = fma(n, -C_(LG2_LO), r);
     const double rh = r * C_(LN10_HI);
     const double rl = fma(r, C_(LN10_HI), -rh);

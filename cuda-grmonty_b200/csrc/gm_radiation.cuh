@@ -41,7 +41,7 @@ __device__ __forceinline__ double k2_eval_l(const GmParams &P, double theta_e, d
     return theta_e < kThetaEMin ? 0.0 : v;
 }
 __device__ __forceinline__ double k2_eval(const GmParams &P, double theta_e) {
-    return k2_eval_l(P, theta_e, fm::log_(fmax(theta_e, 1.0e-300)));
+    return k2_eval_l(P, theta_e, fm::log_(fm::max_(theta_e, 1.0e-300)));
 }
 
 __device__ __forceinline__ double f_eval(const GmParams &P, double theta_e, double b_mag, double nu) {
@@ -75,7 +75,7 @@ __device__ __forceinline__ double synch_sin_l(const GmParams &P, double nu, doub
 }
 __device__ __forceinline__ double synch_sin(const GmParams &P, double nu, double n_e, double theta_e, double b,
                                             double sin_th) {
-    return synch_sin_l(P, nu, n_e, theta_e, b, sin_th, fm::log_(fmax(theta_e, 1.0e-300)));
+    return synch_sin_l(P, nu, n_e, theta_e, b, sin_th, fm::log_(fm::max_(theta_e, 1.0e-300)));
 }
 
 /* Klein-Nishina total cross-section / sigma_T (reference hotcross.cpp:144-152) */
@@ -158,8 +158,8 @@ __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, d
     const double kLog10E = 0.43429448190325182765;
     double qw = (l_w * kLog10E - P.hc_l_min_w) * P.inv_hc_d_l_w;
     double qt = (l_theta * kLog10E - P.hc_l_min_t) * P.inv_hc_d_l_t;
-    qw = fmin(fmax(qw, 0.0), (double)kHcNW - 1.0e-6);
-    qt = fmin(fmax(qt, 0.0), (double)kHcNT - 1.0e-6);
+    qw = fm::min_(fm::max_(qw, 0.0), (double)kHcNW - 1.0e-6);
+    qt = fm::min_(fm::max_(qt, 0.0), (double)kHcNT - 1.0e-6);
     const int i = (int)qw, j = (int)qt;
     const double d_i = qw - i, d_j = qt - j;
     const int off = i * (kHcNT + 1) + j;
@@ -185,7 +185,7 @@ __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, d
     return sigma;
 }
 __device__ __forceinline__ double hotcross_lkup(const GmParams &P, double w, double theta_e) {
-    return hotcross_lkup_l(P, w, theta_e, fm::log_(fmax(w, 1.0e-300)), fm::log_(fmax(theta_e, 1.0e-300)));
+    return hotcross_lkup_l(P, w, theta_e, fm::log_(fm::max_(w, 1.0e-300)), fm::log_(fm::max_(theta_e, 1.0e-300)));
 }
 
 /* fluid-frame photon energy (units of m_e c^2) and cosine of the angle between k and b
@@ -198,7 +198,7 @@ __device__ __forceinline__ void fluid_frame(const GmParams &P, const double k[4]
     const bool no_b = (f.b == 0.0);
     const double den = fabs(ku) * (no_b ? 1.0 : f.b) * P.inv_b_unit;
     mu = fm::div(kb, den);
-    mu = fmin(fmax(mu, -1.0), 1.0);
+    mu = fm::min_(fm::max_(mu, -1.0), 1.0);
     mu = no_b ? 0.0 : mu; /* theta = pi/2 */
 }
 
@@ -211,7 +211,7 @@ __device__ __forceinline__ double alpha_inv_scatt_l(const GmParams &P, double nu
     return nu * hotcross_lkup_l(P, e_g, theta_e, l_nu + kLnHOverMc2, l_theta, hc_tab) * n_e;
 }
 __device__ __forceinline__ double alpha_inv_scatt(const GmParams &P, double nu, double theta_e, double n_e) {
-    return alpha_inv_scatt_l(P, nu, theta_e, n_e, fm::log_(fmax(nu, 1.0e-300)), fm::log_(fmax(theta_e, 1.0e-300)));
+    return alpha_inv_scatt_l(P, nu, theta_e, n_e, fm::log_(fm::max_(nu, 1.0e-300)), fm::log_(fm::max_(theta_e, 1.0e-300)));
 }
 
 /* reference b_nu_inv, radiation.cpp:120-128 (series below x = 1e-3), as a select between the two forms */
@@ -222,7 +222,7 @@ __device__ __forceinline__ double b_nu_inv(double nu, double theta_e) {
     /* x >= 1e-3 means h nu >= 1e-3 k T_e: only up-scattered X-ray photons get here, so the exponential is a
      * rarely taken branch instead of a select that every lane pays for */
     if (!(x < 1.0e-3))
-        den = fm::exp_(fmin(x, 700.0)) - 1.0;
+        den = fm::exp_(fm::min_(x, 700.0)) - 1.0;
     return fm::div(c, den);
 }
 
@@ -236,15 +236,15 @@ __device__ __forceinline__ double alpha_inv_abs_sin_l(const GmParams &P, double 
 }
 __device__ __forceinline__ double alpha_inv_abs_sin(const GmParams &P, double nu, double theta_e, double n_e,
                                                     double b, double sin_th) {
-    return alpha_inv_abs_sin_l(P, nu, theta_e, n_e, b, sin_th, fm::log_(fmax(theta_e, 1.0e-300)));
+    return alpha_inv_abs_sin_l(P, nu, theta_e, n_e, b, sin_th, fm::log_(fm::max_(theta_e, 1.0e-300)));
 }
 
 /* reference bias_func, harm_model.cpp:1391-1404, with the generation's frozen statistics */
 __device__ __forceinline__ double bias_func(const GmParams &P, const GmBiasStats &s, double theta_e, double w) {
     const double mx = w * (0.5 / kWeightMin);
     double bias = fm::div(100.0 * theta_e * theta_e, s.bias_den);
-    bias = fmax(bias, kTpOverTe);
-    bias = fmin(bias, mx);
+    bias = fm::max_(bias, kTpOverTe);
+    bias = fm::min_(bias, mx);
     return bias * (1.0 / kTpOverTe);
 }
 
