@@ -391,6 +391,9 @@ def host_lib():
                                       C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_char_p]
         H.gmh_run_simulation.argtypes = [C.c_void_p]
         H.gmh_report_spectrum.argtypes = [C.c_void_p, C.c_char_p]
+        H.gmh_report_spectrum_binary.argtypes = [C.c_void_p, C.c_char_p]
+        H.gmh_set_dump_cache.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        H.gmh_read_from_cache.argtypes = [C.c_void_p]
         for n in ("gmh_get_header", "gmh_get_header_raw", "gmh_get_units", "gmh_get_scalars", "gmh_get_spectrum",
                   "gmh_set_spectrum", "gmh_get_stats"):
             getattr(H, n).argtypes = [C.c_void_p, dp]
@@ -398,6 +401,30 @@ def host_lib():
         H.gmh_get_table.argtypes = [C.c_void_p, C.c_int, dp]
         _hlib = H
     return _hlib
+
+
+SPECTRUM_BIN_DTYPE = np.dtype([("magic", "S8"), ("version", "<u4"), ("n_th", "<u4"), ("n_e", "<u4"),
+                               ("n_fields", "<u4"), ("created", "<u8"), ("scattered", "<u8"), ("recorded", "<u8"),
+                               ("max_tau_scatt", "<f8"), ("mass_unit", "<f8"), ("photon_n", "<f8"), ("a", "<f8"),
+                               ("h_slope", "<f8"), ("x_start2", "<f8"), ("x_stop2", "<f8")])
+
+
+def read_spectrum_binary(path: str) -> dict:
+    """Reader of HarmModel.report_spectrum_binary: header fields + `spectrum` [6][200][13] (harm::Spectrum order)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if len(raw) < SPECTRUM_BIN_DTYPE.itemsize:
+        raise GrmontyError(f"{path}: not a grmonty_b200 binary spectrum")
+    h = np.frombuffer(raw[:SPECTRUM_BIN_DTYPE.itemsize], dtype=SPECTRUM_BIN_DTYPE)[0]
+    if h["magic"] != b"GMB2SPEC" or h["version"] != 1:
+        raise GrmontyError(f"{path}: not a grmonty_b200 binary spectrum")
+    shape = (int(h["n_th"]), int(h["n_e"]), int(h["n_fields"]))
+    body = np.frombuffer(raw[SPECTRUM_BIN_DTYPE.itemsize:], dtype="<f8")
+    if body.size != shape[0] * shape[1] * shape[2]:
+        raise GrmontyError(f"{path}: truncated binary spectrum")
+    out = {k: h[k].item() for k in SPECTRUM_BIN_DTYPE.names if k != "magic"}
+    out["spectrum"] = body.reshape(shape).copy()
+    return out
 
 
 class HarmModel:
@@ -429,6 +456,17 @@ class HarmModel:
 
     def read_file(self, path: str):
         self._ck(self.H.gmh_read_file(self.h, path.encode()))
+
+    def set_dump_cache(self, on: bool = True, directory: str = ""):
+        """Binary dump cache `<dump>.b200cache`: loaded by read_file when it matches the text dump,
+        written after parsing otherwise."""
+        self.H.gmh_set_dump_cache(self.h, int(bool(on)), directory.encode())
+
+    def read_from_cache(self) -> bool:
+        return bool(self.H.gmh_read_from_cache(self.h))
+
+    def report_spectrum_binary(self, path: str):
+        self._ck(self.H.gmh_report_spectrum_binary(self.h, path.encode()))
 
     def init(self, threads: int = 0):
         self._ck(self.H.gmh_init(self.h, threads))

@@ -31,6 +31,17 @@ void *gmh_create(int photon_n, double mass_unit, int verbosity) {
 void gmh_destroy(void *h) { delete static_cast<HARMModel *>(h); }
 
 int gmh_read_file(void *h, const char *path) { GUARD(static_cast<HARMModel *>(h)->read_file(path)) }
+/* mode 0: off, 1: load/store `<dump>.b200cache` (dir: NULL or "" = next to the dump) */
+int gmh_set_dump_cache(void *h, int mode, const char *dir) {
+    auto *m = static_cast<HARMModel *>(h);
+    m->dump_cache = mode != 0;
+    m->dump_cache_dir = dir ? dir : "";
+    return 0;
+}
+int gmh_read_from_cache(void *h) { return static_cast<HARMModel *>(h)->read_from_cache() ? 1 : 0; }
+int gmh_report_spectrum_binary(void *h, const char *path) {
+    GUARD(static_cast<HARMModel *>(h)->report_spectrum_binary(path))
+}
 int gmh_init(void *h, int threads) {
     auto *m = static_cast<HARMModel *>(h);
     m->init_threads = threads;

@@ -115,25 +115,58 @@ struct Tokenizer {
 };
 } /* namespace */
 
-void HARMModel::read_file(std::string filepath) {
-    log_info("Reading file %s", filepath.c_str());
-    if (!std::filesystem::exists(filepath))
-        throw std::runtime_error("File does not exist " + filepath);
-    std::ifstream in(filepath, std::ios::binary | std::ios::ate);
-    if (!in.is_open())
-        throw std::runtime_error("Cannot open file " + filepath);
-    const std::streamsize size = in.tellg();
-    in.seekg(0);
-    std::string buf((size_t)size, '\0');
-    in.read(buf.data(), size);
-    Tokenizer tk{buf.data(), buf.data() + buf.size()};
+/* ---- binary dump cache ------------------------------------------------------------------------
+ * The 34-column text dump is 29 MB at 192^2 and ~0.9 GB at 1024^2, and the run needs 8 of the 34 columns plus one
+ * scalar.  With `dump_cache` on, read_file() leaves `<dump>.b200cache` (or the same name under `dump_cache_dir`)
+ * behind: the 26 header fields, bias_norm and the 8 primitive grids as raw doubles, stamped with the size, the
+ * modification time and a hash of the first 64 KB of the text file it was made from.  The next read_file() of the same
+ * dump maps straight into the grids; any mismatch (other file, edited file, truncated or foreign cache) falls back to
+ * the text parser and rewrites the cache.  Little-endian IEEE doubles, as everything else this library reads. */
+namespace {
+constexpr char kDumpCacheMagic[8] = {'G', 'M', 'B', '2', 'D', 'U', 'M', 'P'};
+constexpr uint32_t kDumpCacheVersion = 1;
+struct DumpCacheHeader {
+    char magic[8];
+    uint32_t version, header_fields;
+    uint64_t src_size;
+    int64_t src_mtime_ns;
+    uint64_t src_head_hash, n_zones;
+    double bias_norm;
+    double header[26];
+};
+uint64_t fnv1a(const char *p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i)
+        h = (h ^ (unsigned char)p[i]) * 1099511628211ull;
+    return h;
+}
+struct SourceStamp {
+    uint64_t size = 0;
+    int64_t mtime_ns = 0;
+    uint64_t head_hash = 0;
+};
+SourceStamp stamp_of(const std::string &path) {
+    SourceStamp st;
+    st.size = (uint64_t)std::filesystem::file_size(path);
+    st.mtime_ns = (int64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                      std::filesystem::last_write_time(path).time_since_epoch())
+                      .count();
+    std::ifstream in(path, std::ios::binary);
+    std::string head((size_t)std::min<uint64_t>(st.size, 65536), '\0');
+    in.read(head.data(), (std::streamsize)head.size());
+    st.head_hash = fnv1a(head.data(), head.size());
+    return st;
+}
+} /* namespace */
 
-    /* header: 26 fields (reference :99-137) */
-    double h[26] = {0};
-    for (int i = 0; i < 26; ++i)
-        if (!tk.next(h[i]))
-            break;
-    tk.end_line();
+std::string HARMModel::dump_cache_path(const std::string &filepath) const {
+    namespace fs = std::filesystem;
+    if (dump_cache_dir.empty())
+        return filepath + ".b200cache";
+    return (fs::path(dump_cache_dir) / (fs::path(filepath).filename().string() + ".b200cache")).string();
+}
+
+void HARMModel::apply_header(const double h[26], const std::string &filepath) {
     Header &H = header_;
     H.t = h[0];
     H.n[0] = (int)h[1];
@@ -171,10 +204,109 @@ void HARMModel::read_file(std::string filepath) {
     H.r_0 = h[25];
     if (H.n[0] < 1 || H.n[1] < 1)
         throw std::runtime_error("Bad HARM dump header in " + filepath);
-
     /* reference :139-141 */
     const double two_temp_gamma = 0.5 * ((1. + 2. / 3. * (gm::kTpOverTe + 1.) / (gm::kTpOverTe + 2.)) + H.gamma);
     units_.theta_e_unit = (two_temp_gamma - 1.) * (gm::kMP / gm::kME) / (1. + gm::kTpOverTe);
+    rh_ = 1.0 + std::sqrt(1.0 - H.a * H.a);
+    x1_min_ = std::log(rh_);
+}
+
+bool HARMModel::load_dump_cache(const std::string &filepath) {
+    const std::string cpath = dump_cache_path(filepath);
+    std::error_code ec;
+    if (!std::filesystem::exists(cpath, ec))
+        return false;
+    std::ifstream in(cpath, std::ios::binary | std::ios::ate);
+    if (!in.is_open())
+        return false;
+    const uint64_t csize = (uint64_t)in.tellg();
+    in.seekg(0);
+    DumpCacheHeader ch;
+    if (csize < sizeof(ch) || !in.read(reinterpret_cast<char *>(&ch), sizeof(ch)))
+        return false;
+    const SourceStamp st = stamp_of(filepath);
+    if (std::memcmp(ch.magic, kDumpCacheMagic, 8) != 0 || ch.version != kDumpCacheVersion || ch.header_fields != 26 ||
+        ch.src_size != st.size || ch.src_mtime_ns != st.mtime_ns || ch.src_head_hash != st.head_hash)
+        return false;
+    const int64_t n0 = (int64_t)ch.header[1], n1 = (int64_t)ch.header[2];
+    if (n0 < 1 || n1 < 1 || ch.n_zones != (uint64_t)(n0 * n1) ||
+        csize != sizeof(ch) + 8ull * ch.n_zones * sizeof(double))
+        return false;
+    std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
+                                     &data_.u_3,   &data_.b_1, &data_.b_2, &data_.b_3};
+    for (auto *g : grids) {
+        g->resize(ch.n_zones);
+        if (!in.read(reinterpret_cast<char *>(g->data()), (std::streamsize)(ch.n_zones * sizeof(double))))
+            return false;
+    }
+    apply_header(ch.header, filepath);
+    bias_norm_ = ch.bias_norm;
+    return true;
+}
+
+void HARMModel::store_dump_cache(const std::string &filepath, const double h[26]) const {
+    /* best effort: a read-only dump directory must not fail the run */
+    try {
+        const std::string cpath = dump_cache_path(filepath), tmp = cpath + ".tmp";
+        DumpCacheHeader ch{};
+        std::memcpy(ch.magic, kDumpCacheMagic, 8);
+        ch.version = kDumpCacheVersion;
+        ch.header_fields = 26;
+        const SourceStamp st = stamp_of(filepath);
+        ch.src_size = st.size;
+        ch.src_mtime_ns = st.mtime_ns;
+        ch.src_head_hash = st.head_hash;
+        ch.n_zones = data_.k_rho.size();
+        ch.bias_norm = bias_norm_;
+        std::memcpy(ch.header, h, sizeof(ch.header));
+        {
+            std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
+            if (!out.is_open())
+                return;
+            out.write(reinterpret_cast<const char *>(&ch), sizeof(ch));
+            const std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
+                                                   &data_.u_3,   &data_.b_1, &data_.b_2, &data_.b_3};
+            for (auto *g : grids)
+                out.write(reinterpret_cast<const char *>(g->data()), (std::streamsize)(g->size() * sizeof(double)));
+            if (!out.good()) {
+                out.close();
+                std::filesystem::remove(tmp);
+                return;
+            }
+        }
+        std::filesystem::rename(tmp, cpath); /* atomic: a concurrent reader sees the old or the new file */
+    } catch (const std::exception &e) {
+        log_info("Dump cache not written: %s", e.what());
+    }
+}
+
+void HARMModel::read_file(std::string filepath) {
+    log_info("Reading file %s", filepath.c_str());
+    if (!std::filesystem::exists(filepath))
+        throw std::runtime_error("File does not exist " + filepath);
+    read_from_cache_ = false;
+    if (dump_cache && load_dump_cache(filepath)) {
+        read_from_cache_ = true;
+        log_info("Reading file done (binary cache %s)", dump_cache_path(filepath).c_str());
+        return;
+    }
+    std::ifstream in(filepath, std::ios::binary | std::ios::ate);
+    if (!in.is_open())
+        throw std::runtime_error("Cannot open file " + filepath);
+    const std::streamsize size = in.tellg();
+    in.seekg(0);
+    std::string buf((size_t)size, '\0');
+    in.read(buf.data(), size);
+    Tokenizer tk{buf.data(), buf.data() + buf.size()};
+
+    /* header: 26 fields (reference :99-137) */
+    double h[26] = {0};
+    for (int i = 0; i < 26; ++i)
+        if (!tk.next(h[i]))
+            break;
+    tk.end_line();
+    apply_header(h, filepath);
+    const Header &H = header_;
 
     const size_t nz = (size_t)H.n[0] * H.n[1];
     std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
@@ -198,8 +330,8 @@ void HARMModel::read_file(std::string filepath) {
         v += d_v * g_det;
     }
     bias_norm_ /= v;
-    rh_ = 1.0 + std::sqrt(1.0 - H.a * H.a);
-    x1_min_ = std::log(rh_);
+    if (dump_cache)
+        store_dump_cache(filepath, h);
     log_info("Reading file done");
 }
 
@@ -728,6 +860,47 @@ void HARMModel::report_spectrum(std::string filepath) {
     log_info("Writing spectrum done");
     log_info("\tlumosity: %g", l);
     log_info("\tmax_tau_scatt: %g", max_tau_scatt);
+}
+
+/* ---- full-field binary spectrum --------------------------------------------------------------
+ * The text file keeps 6 derived columns per angle bin; 7 of the 13 accumulated fields (dn_dle, nph, nscatt, ne_0,
+ * theta_e_0, b_0, e_0) never reach it (reference harm_model.cpp:443-455 vs :1323-1334).  This side-file is the whole
+ * [6][200][13] accumulator in harm::Spectrum field order plus the run counters, for parity checks and for merging
+ * runs (spectra are additive).  Layout: SpectrumBinHeader, then 6*200*13 little-endian doubles. */
+namespace {
+struct SpectrumBinHeader {
+    char magic[8]; /* "GMB2SPEC" */
+    uint32_t version, n_th, n_e, n_fields;
+    uint64_t created, scattered, recorded;
+    double max_tau_scatt, mass_unit, photon_n, a, h_slope, x_start2, x_stop2;
+};
+} /* namespace */
+
+void HARMModel::report_spectrum_binary(std::string filepath) {
+    log_info("Writing binary spectrum to file %s", filepath.c_str());
+    SpectrumBinHeader h{};
+    std::memcpy(h.magic, "GMB2SPEC", 8);
+    h.version = 1;
+    h.n_th = kNThBins;
+    h.n_e = kNEBins;
+    h.n_fields = kSpecFields;
+    h.created = stats_.created;
+    h.scattered = stats_.scattered;
+    h.recorded = stats_.recorded;
+    h.max_tau_scatt = stats_.max_tau_scatt;
+    h.mass_unit = units_.mass_unit;
+    h.photon_n = photon_n_;
+    h.a = header_.a;
+    h.h_slope = header_.h_slope;
+    h.x_start2 = header_.x_start[2];
+    h.x_stop2 = header_.x_stop[2];
+    std::ofstream out(filepath, std::ios::binary | std::ios::trunc);
+    if (!out.is_open())
+        throw std::runtime_error("Cannot open file " + filepath);
+    out.write(reinterpret_cast<const char *>(&h), sizeof(h));
+    out.write(reinterpret_cast<const char *>(spectrum_.data()), (std::streamsize)(spectrum_.size() * sizeof(double)));
+    if (!out.good())
+        throw std::runtime_error("Short write to " + filepath);
 }
 
 } /* namespace harm */

@@ -79,6 +79,8 @@ public:
     void init();                          /* geometry, hot cross-section, emissivity, weight and nint tables */
     void run_simulation();                /* on the GPU, through the C ABI; throws on failure */
     void report_spectrum(std::string filepath);
+    /* the whole [6][200][13] accumulator + run counters, binary (the text file drops 7 of the 13 fields) */
+    void report_spectrum_binary(std::string filepath);
 
     const Header *get_header() const { return &header_; }
     const Data *get_data() const { return &data_; }
@@ -86,6 +88,12 @@ public:
     /* ---- beyond the reference surface (used by the CLI, the tests and bench.py) ---- */
     RunOptions options;
     int init_threads = 0; /* 0: hardware concurrency */
+    /* binary dump cache: read_file() loads `<dump>.b200cache` when it matches the text dump, and writes it after
+     * parsing otherwise.  Off by default (the reference leaves no side files). */
+    bool dump_cache = false;
+    std::string dump_cache_dir; /* empty: next to the dump */
+    std::string dump_cache_path(const std::string &filepath) const;
+    bool read_from_cache() const { return read_from_cache_; }
     const Units &units() const { return units_; }
     const RunStats &stats() const { return stats_; }
     double bias_norm() const { return bias_norm_; }
@@ -119,6 +127,11 @@ private:
     std::array<double, kNESamp + 1> f_{}, k2_{}, weight_{};
     RunStats stats_;
     double luminosity_ = 0, max_tau_reported_ = 0;
+    bool read_from_cache_ = false;
+
+    void apply_header(const double h[26], const std::string &filepath);
+    bool load_dump_cache(const std::string &filepath);
+    void store_dump_cache(const std::string &filepath, const double h[26]) const;
 
     void gcov(const double x[4], double g[4][4]) const;
     void gcon(const double x[4], double g[4][4]) const;

@@ -2,7 +2,8 @@
  * main.cpp -- command-line driver with the reference's flags (cuda_grmonty/main.cpp:20-56):
  *     --photon_n N   --mass_unit M   --harm_dump_path FILE   --spectrum_path FILE   --verbosity LEVEL
  * Both `--flag value`, `--flag=value` and the single-dash spellings abseil accepts (`-photon_n 5000000`,
- * reference README.md:30) work.  Extra flags of the B200 path: --seed, --device, --init_threads.
+ * reference README.md:30) work.  Extra flags of the B200 path: --seed, --device, --init_threads, --dump_cache 0|1
+ * (binary cache next to the dump, or under --dump_cache_dir), --spectrum_bin_path FILE (all 13 accumulated fields).
  * Call order is the reference's: HARMModel(photon_n, mass_unit) -> read_file -> init -> run_simulation ->
  * report_spectrum.  (The reference seeds its global mt19937 with 123 at this point; here the seed is the
  * Philox key and is part of the run options.)
@@ -67,10 +68,17 @@ int main(int argc, char **argv) {
             model.options.device = std::atoi(v.c_str());
         if (flag_value(argc, argv, "init_threads", v))
             model.init_threads = std::atoi(v.c_str());
+        if (flag_value(argc, argv, "dump_cache", v))
+            model.dump_cache = std::atoi(v.c_str()) != 0;
+        flag_value(argc, argv, "dump_cache_dir", model.dump_cache_dir);
+        std::string spectrum_bin_path;
+        flag_value(argc, argv, "spectrum_bin_path", spectrum_bin_path);
         model.read_file(harm_dump_path);
         model.init();
         model.run_simulation();
         model.report_spectrum(spectrum_path);
+        if (!spectrum_bin_path.empty())
+            model.report_spectrum_binary(spectrum_bin_path);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "[error] %s\n", e.what());
         return 1;

@@ -155,3 +155,92 @@ def test_cli_flags(tmp_path):
                         str(tmp_path / "s"), "-photon_n", "1000", "--mass_unit=4e19", "--verbosity", "error"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "File does not exist" in r.stderr
+
+
+# ---- binary dump cache and the full-field binary spectrum --------------------------------------------
+
+def _grids(m):
+    d = m.model_dict()
+    return {k: d[k] for k in ("k_rho", "u", "u_1", "u_2", "u_3", "b_1", "b_2", "b_3")}, d["bias_norm"], d["theta_e_unit"]
+
+
+def test_dump_cache_round_trip_is_bit_exact(tmp_path):
+    p = str(tmp_path / "dump32.txt")
+    header, table = make_harm_dump.make_dump(n0=32, n1=24)
+    make_harm_dump.write_dump(p, header, table)
+    ref = gm.HarmModel(1000, 4e19)
+    ref.read_file(p)                       # plain text parse, cache off (the default): no side file
+    assert not os.path.exists(p + ".b200cache") and not ref.read_from_cache()
+    a = gm.HarmModel(1000, 4e19)
+    a.set_dump_cache(True)
+    a.read_file(p)                         # parses, then writes the cache
+    assert not a.read_from_cache() and os.path.exists(p + ".b200cache")
+    b = gm.HarmModel(1000, 4e19)
+    b.set_dump_cache(True)
+    b.read_file(p)                         # loads the cache
+    assert b.read_from_cache()
+    assert np.array_equal(ref.header_raw(), b.header_raw())
+    (g0, bn0, te0), (g1, bn1, te1) = _grids(ref), _grids(b)
+    assert bn0 == bn1 and te0 == te1
+    for k in g0:
+        assert np.array_equal(g0[k], g1[k]), k
+    # tables built from cached data are the same bits as from the parsed text
+    ref.init_stage(0); b.init_stage(0)
+    assert np.array_equal(ref.model_dict()["geom_det"], b.model_dict()["geom_det"])
+    # size = header + 8 grids of raw doubles
+    assert os.path.getsize(p + ".b200cache") == 8 + 8 + 8 * 4 + 8 + 26 * 8 + 8 * 32 * 24 * 8
+
+
+def test_dump_cache_is_invalidated_by_a_changed_dump_or_a_bad_cache(tmp_path):
+    p = str(tmp_path / "dump16.txt")
+    cdir = tmp_path / "cache"
+    cdir.mkdir()
+    header, table = make_harm_dump.make_dump(n0=16, n1=16)
+    make_harm_dump.write_dump(p, header, table)
+    m = gm.HarmModel(1000, 4e19)
+    m.set_dump_cache(True, str(cdir))
+    m.read_file(p)
+    cpath = str(cdir / "dump16.txt.b200cache")
+    assert os.path.exists(cpath) and not os.path.exists(p + ".b200cache")
+    m.read_file(p)
+    assert m.read_from_cache()
+    # another dump under the same name: different content (and size) -> the cache is ignored and rewritten
+    table2 = table.copy()
+    table2[:, 4] *= 2.0
+    make_harm_dump.write_dump(p, header, table2)
+    m.read_file(p)
+    assert not m.read_from_cache()
+    assert np.allclose(m.model_dict()["k_rho"].ravel(), table2[:, 4], rtol=1e-14)
+    m.read_file(p)
+    assert m.read_from_cache()
+    # truncated / foreign cache files fall back to the text parser
+    raw = open(cpath, "rb").read()
+    for bad in (raw[:100], raw[:-8], b"XXXXXXXX" + raw[8:], b""):
+        with open(cpath, "wb") as f:
+            f.write(bad)
+        m.read_file(p)
+        assert not m.read_from_cache()
+        assert np.allclose(m.model_dict()["k_rho"].ravel(), table2[:, 4], rtol=1e-14)
+        assert open(cpath, "rb").read() == raw      # and the cache is rewritten
+    # an unwritable cache directory must not fail the read
+    m.set_dump_cache(True, str(tmp_path / "does" / "not" / "exist"))
+    m.read_file(p)
+    assert not m.read_from_cache()
+
+
+def test_binary_spectrum_keeps_all_thirteen_fields(host48, tmp_path):
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "spectrum_file.npz"))
+    host48.set_spectrum(fx["spectrum"])
+    p = str(tmp_path / "spectrum.bin")
+    host48.report_spectrum_binary(p)
+    got = gm.read_spectrum_binary(p)
+    assert got["spectrum"].shape == (6, 200, 13) and np.array_equal(got["spectrum"], fx["spectrum"])
+    assert got["n_th"] == 6 and got["n_e"] == 200 and got["n_fields"] == 13
+    assert got["mass_unit"] == 4e19 and got["photon_n"] == 2000
+    assert os.path.getsize(p) == gm.SPECTRUM_BIN_DTYPE.itemsize + 6 * 200 * 13 * 8
+    with open(p, "r+b") as f:
+        f.truncate(1000)
+    with pytest.raises(gm.GrmontyError, match="truncated"):
+        gm.read_spectrum_binary(p)
+    with pytest.raises(gm.GrmontyError):
+        host48.report_spectrum_binary(str(tmp_path / "no" / "such" / "dir" / "s.bin"))
