@@ -118,6 +118,7 @@ ABI_SYMBOLS = [
     "grmonty_b200_create", "grmonty_b200_total_primaries", "grmonty_b200_run_range", "grmonty_b200_run",
     "grmonty_b200_allreduce", "grmonty_b200_device_accumulators", "grmonty_b200_result", "grmonty_b200_reset",
     "grmonty_b200_destroy", "grmonty_b200_trim_cache", "grmonty_b200_last_error", "grmonty_b200_fp64_peak", "grmonty_b200_hotcross_table",
+    "grmonty_b200_init_tables",
     "grmonty_b200_test_geometry", "grmonty_b200_test_dkdlam_step", "grmonty_b200_test_push_photon",
     "grmonty_b200_test_trajectory", "grmonty_b200_test_fluid_params", "grmonty_b200_test_radiation",
     "grmonty_b200_test_hotcross", "grmonty_b200_test_angles", "grmonty_b200_test_tetrad",
@@ -153,6 +154,7 @@ def lib():
         L.grmonty_b200_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.grmonty_b200_fp64_peak.argtypes = [C.c_void_p, dp]
         L.grmonty_b200_hotcross_table.argtypes = [C.c_int, dp]
+        L.grmonty_b200_init_tables.argtypes = [C.POINTER(Config), dp, dp, dp, dp, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -370,6 +372,34 @@ def hotcross_table(device: int = 0) -> np.ndarray:
     return t
 
 
+def init_tables(model: dict, device: int = 0) -> dict:
+    """geom_det [n0][n1], weight [201], nint [20001], dndlnu_max [20001] built on the GPU (grmonty_b200_init_tables)
+    from the grids, units, photon_n and the F(K) / K2 tables of `model`; also `device_ms` of the three kernels."""
+    cfg = Config()
+    cfg.abi_version = 2
+    cfg.struct_size = C.sizeof(Config)
+    cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
+    for k in Context.SCALARS:
+        if k in model:
+            setattr(cfg, k, float(model[k]))
+    keep = []
+    for k in Context.GRIDS[:8] + ["f", "k2"]:
+        a = _arr(model[k]).reshape(-1)
+        keep.append(a)
+        setattr(cfg, k, _ptr(a))
+    cfg.device = device
+    out = dict(geom_det=np.zeros((cfg.n0, cfg.n1)), weight=np.zeros(201), nint=np.zeros(20001),
+               dndlnu_max=np.zeros(20001))
+    ms = C.c_double()
+    L = lib()
+    rc = L.grmonty_b200_init_tables(C.byref(cfg), _ptr(out["geom_det"]), _ptr(out["weight"]), _ptr(out["nint"]),
+                                    _ptr(out["dndlnu_max"]), C.byref(ms))
+    if rc != 0:
+        raise GrmontyError(f"grmonty_b200_init_tables failed ({rc}): {L.grmonty_b200_last_error(None).decode()}")
+    out["device_ms"] = ms.value
+    return out
+
+
 # ---- host library binding (libgrmonty_b200_host.so): the reference's HARMModel surface -------------------------
 _hlib = None
 
@@ -394,6 +424,7 @@ def host_lib():
         H.gmh_report_spectrum_binary.argtypes = [C.c_void_p, C.c_char_p]
         H.gmh_set_dump_cache.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         H.gmh_read_from_cache.argtypes = [C.c_void_p]
+        H.gmh_set_device_tables.argtypes = [C.c_void_p, C.c_int]
         for n in ("gmh_get_header", "gmh_get_header_raw", "gmh_get_units", "gmh_get_scalars", "gmh_get_spectrum",
                   "gmh_set_spectrum", "gmh_get_stats"):
             getattr(H, n).argtypes = [C.c_void_p, dp]
@@ -461,6 +492,10 @@ class HarmModel:
         """Binary dump cache `<dump>.b200cache`: loaded by read_file when it matches the text dump,
         written after parsing otherwise."""
         self.H.gmh_set_dump_cache(self.h, int(bool(on)), directory.encode())
+
+    def set_device_tables(self, on: bool = True):
+        """init() builds the geometry / weight / nint / hot cross-section tables on the GPU."""
+        self.H.gmh_set_device_tables(self.h, int(bool(on)))
 
     def read_from_cache(self) -> bool:
         return bool(self.H.gmh_read_from_cache(self.h))

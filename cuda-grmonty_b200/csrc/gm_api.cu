@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gm_kernels.cuh"
+#include "gm_tables.cuh"
 
 using namespace gm;
 
@@ -167,6 +168,54 @@ extern "C" {
 
 const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+/* scalar part of the device parameter block (pointers are filled in by the caller) */
+static void fill_params(GmParams &P, const grmonty_b200_config *cfg) {
+    memset(&P, 0, sizeof(P));
+    P.n0 = cfg->n0;
+    P.n1 = cfg->n1;
+    P.x_start1 = cfg->x_start1;
+    P.x_start2 = cfg->x_start2;
+    P.dx1 = cfg->dx1;
+    P.dx2 = cfg->dx2;
+    P.x_stop1 = cfg->x_stop1;
+    P.x_stop2 = cfg->x_stop2;
+    P.a = cfg->a;
+    P.h_slope = cfg->h_slope;
+    P.r_0 = cfg->r_0;
+    P.b_unit = cfg->b_unit;
+    P.theta_e_unit = cfg->theta_e_unit;
+    P.n_e_unit = cfg->n_e_unit;
+    P.photon_n = cfg->photon_n;
+    P.bias_norm = cfg->bias_norm;
+    /* reference harm_model.cpp:73, :228-229 */
+    P.d_tau_k = 2.0 * kPi * cfg->l_unit / (kME * kCL * kCL / kHBAR);
+    P.x1_min = std::log(1.0 + std::sqrt(1.0 - cfg->a * cfg->a));
+    P.x1_max = std::log(kRMax);
+    P.seed_lo = (uint32_t)cfg->seed;
+    P.seed_hi = (uint32_t)(cfg->seed >> 32);
+    P.l_nu_min = std::log(kNuMin);
+    P.n_l_n = std::log(kNuMax) - std::log(kNuMin);
+    P.d_l_nu = (std::log(kNuMax) - std::log(kNuMin)) / kNESamp;
+    P.l_b_min = std::log(kBthsqMin);
+    P.d_l_b = std::log(kBthsqMax / kBthsqMin) / kNint;
+    P.hc_l_min_w = std::log10(kHcMinW);
+    P.hc_l_min_t = std::log10(kHcMinT);
+    P.hc_d_l_w = std::log10(kHcMaxW / kHcMinW) / kHcNW;
+    P.hc_d_l_t = std::log10(kHcMaxT / kHcMinT) / kHcNT;
+    P.jnu_l_min_k = std::log(kJnuMinK);
+    P.jnu_d_l_k = std::log(kJnuMaxK / kJnuMinK) / kNESamp;
+    P.jnu_l_min_t = std::log(kThetaEMin);
+    P.jnu_d_l_t = std::log(kJnuMaxT / kThetaEMin) / kNESamp;
+    P.spec_l_e_0 = std::log(1.0e-12);
+    P.nz_max = cfg->photon_n * std::log(kNuMax / kNuMin);
+    P.inv_dx1 = 1.0 / P.dx1;
+    P.inv_dx2 = 1.0 / P.dx2;
+    P.inv_b_unit = 1.0 / P.b_unit;
+    P.inv_hc_d_l_w = 1.0 / P.hc_d_l_w;
+    P.inv_hc_d_l_t = 1.0 / P.hc_d_l_t;
+    P.inv_jnu_d_l_t = 1.0 / P.jnu_d_l_t;
+}
+
 int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) {
     grmonty_b200_ctx *ctx = nullptr;
     if (!out || !cfg)
@@ -207,50 +256,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
 
         /* ---- parameter block ---- */
         GmParams &P = ctx->P;
-        memset(&P, 0, sizeof(P));
-        P.n0 = cfg->n0;
-        P.n1 = cfg->n1;
-        P.x_start1 = cfg->x_start1;
-        P.x_start2 = cfg->x_start2;
-        P.dx1 = cfg->dx1;
-        P.dx2 = cfg->dx2;
-        P.x_stop1 = cfg->x_stop1;
-        P.x_stop2 = cfg->x_stop2;
-        P.a = cfg->a;
-        P.h_slope = cfg->h_slope;
-        P.r_0 = cfg->r_0;
-        P.b_unit = cfg->b_unit;
-        P.theta_e_unit = cfg->theta_e_unit;
-        P.n_e_unit = cfg->n_e_unit;
-        P.photon_n = cfg->photon_n;
-        P.bias_norm = cfg->bias_norm;
-        /* reference harm_model.cpp:73, :228-229 */
-        P.d_tau_k = 2.0 * kPi * cfg->l_unit / (kME * kCL * kCL / kHBAR);
-        P.x1_min = std::log(1.0 + std::sqrt(1.0 - cfg->a * cfg->a));
-        P.x1_max = std::log(kRMax);
-        P.seed_lo = (uint32_t)cfg->seed;
-        P.seed_hi = (uint32_t)(cfg->seed >> 32);
-        P.l_nu_min = std::log(kNuMin);
-        P.n_l_n = std::log(kNuMax) - std::log(kNuMin);
-        P.d_l_nu = (std::log(kNuMax) - std::log(kNuMin)) / kNESamp;
-        P.l_b_min = std::log(kBthsqMin);
-        P.d_l_b = std::log(kBthsqMax / kBthsqMin) / kNint;
-        P.hc_l_min_w = std::log10(kHcMinW);
-        P.hc_l_min_t = std::log10(kHcMinT);
-        P.hc_d_l_w = std::log10(kHcMaxW / kHcMinW) / kHcNW;
-        P.hc_d_l_t = std::log10(kHcMaxT / kHcMinT) / kHcNT;
-        P.jnu_l_min_k = std::log(kJnuMinK);
-        P.jnu_d_l_k = std::log(kJnuMaxK / kJnuMinK) / kNESamp;
-        P.jnu_l_min_t = std::log(kThetaEMin);
-        P.jnu_d_l_t = std::log(kJnuMaxT / kThetaEMin) / kNESamp;
-        P.spec_l_e_0 = std::log(1.0e-12);
-        P.nz_max = cfg->photon_n * std::log(kNuMax / kNuMin);
-        P.inv_dx1 = 1.0 / P.dx1;
-        P.inv_dx2 = 1.0 / P.dx2;
-        P.inv_b_unit = 1.0 / P.b_unit;
-        P.inv_hc_d_l_w = 1.0 / P.hc_d_l_w;
-        P.inv_hc_d_l_t = 1.0 / P.hc_d_l_t;
-        P.inv_jnu_d_l_t = 1.0 / P.jnu_d_l_t;
+        fill_params(P, cfg);
 
         /* ---- one device arena for everything (reused from the cache when possible) ---- */
         const size_t nz = (size_t)cfg->n0 * cfg->n1;
@@ -965,6 +971,92 @@ int grmonty_b200_hotcross_table(int device, double *table) {
     cudaFree(d);
     if (e != cudaSuccess)
         return fail(nullptr, GRMONTY_B200_ECUDA, "hotcross_table_kernel: %s", cudaGetErrorString(e));
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_init_tables(const grmonty_b200_config *cfg, double *geom_det, double *weight, double *nint,
+                             double *dndlnu_max, double *device_ms) {
+    grmonty_b200_ctx *ctx = nullptr; /* for the CK macro: errors go to the thread's create-error slot */
+    if (!cfg)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "null config");
+    if (cfg->abi_version != GRMONTY_B200_ABI_VERSION || cfg->struct_size != sizeof(grmonty_b200_config))
+        return fail(nullptr, GRMONTY_B200_EINVAL, "ABI mismatch: version %u size %u (library: %u, %zu)",
+                    cfg->abi_version, cfg->struct_size, GRMONTY_B200_ABI_VERSION, sizeof(grmonty_b200_config));
+    if (cfg->n0 < 2 || cfg->n1 < 2 || !(cfg->photon_n > 0))
+        return fail(nullptr, GRMONTY_B200_EINVAL, "bad grid %d x %d or photon_n", cfg->n0, cfg->n1);
+    const double *src[8] = {cfg->k_rho, cfg->u, cfg->u_1, cfg->u_2, cfg->u_3, cfg->b_1, cfg->b_2, cfg->b_3};
+    for (const double *g : src)
+        if (!g)
+            return fail(nullptr, GRMONTY_B200_EINVAL, "null input array");
+    if (!cfg->f || !cfg->k2)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "init_tables needs the F(K) and K2 tables");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, GRMONTY_B200_ECUDA, "no such CUDA device %d (there is no CPU fallback)", cfg->device);
+    CK(cudaSetDevice(cfg->device));
+
+    GmParams P;
+    fill_params(P, cfg);
+    const size_t nz = (size_t)cfg->n0 * cfg->n1;
+    const size_t n_tab = GRMONTY_B200_TABLE_N, n_nint = GRMONTY_B200_NINT_N;
+    /* one allocation: grid[nz][8] det fac te bb [nz] | f k2 weight [201] | nint dnmax [20001] */
+    const size_t total = nz * 12 + 3 * n_tab + 2 * n_nint;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, total * sizeof(double)));
+    double *d_grid = d, *d_det = d + nz * 8, *d_fac = d_det + nz, *d_te = d_fac + nz, *d_bb = d_te + nz;
+    double *d_f = d_bb + nz, *d_k2 = d_f + n_tab, *d_w = d_k2 + n_tab, *d_nint = d_w + n_tab, *d_dn = d_nint + n_nint;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) {
+        if (e == cudaSuccess)
+            e = r;
+    };
+    {
+        std::vector<double> inter(nz * 8);
+        for (size_t z = 0; z < nz; ++z)
+            for (int v = 0; v < 8; ++v)
+                inter[z * 8 + v] = src[v][z];
+        step(cudaMemcpy(d_grid, inter.data(), nz * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    step(cudaMemcpy(d_f, cfg->f, n_tab * sizeof(double), cudaMemcpyHostToDevice));
+    step(cudaMemcpy(d_k2, cfg->k2, n_tab * sizeof(double), cudaMemcpyHostToDevice));
+    P.grid = d_grid;
+    P.f = d_f;
+    P.k2 = d_k2;
+    step(cudaEventCreate(&e0));
+    step(cudaEventCreate(&e1));
+    if (e == cudaSuccess) {
+        /* reference :283-285 (zone volume in cm^3) and :329-333 */
+        const double s_fac = cfg->dx1 * cfg->dx2 * cfg->dx3 * cfg->l_unit * cfg->l_unit * cfg->l_unit;
+        const double n_fac = s_fac * 1.41421356237309504880 * kEE * kEE * kEE / (27.0 * kME * kCL * kCL) * (1.0 / kHPL);
+        cudaEventRecord(e0);
+        zone_table_kernel<<<(unsigned)((nz + 127) / 128), 128>>>(P, s_fac, d_det, d_fac, d_te, d_bb);
+        weight_table_kernel<512><<<(unsigned)n_tab, 512>>>(P, d_fac, d_te, d_bb, d_w);
+        nint_table_kernel<<<(unsigned)((n_nint + 127) / 128), 128>>>(P, d_w, n_fac, d_nint, d_dn);
+        cudaEventRecord(e1);
+        step(cudaGetLastError());
+        step(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        if (e == cudaSuccess)
+            cudaEventElapsedTime(&ms, e0, e1);
+        if (device_ms)
+            *device_ms = ms;
+    }
+    if (geom_det)
+        step(cudaMemcpy(geom_det, d_det, nz * sizeof(double), cudaMemcpyDeviceToHost));
+    if (weight)
+        step(cudaMemcpy(weight, d_w, n_tab * sizeof(double), cudaMemcpyDeviceToHost));
+    if (nint)
+        step(cudaMemcpy(nint, d_nint, n_nint * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dndlnu_max)
+        step(cudaMemcpy(dndlnu_max, d_dn, n_nint * sizeof(double), cudaMemcpyDeviceToHost));
+    if (e0)
+        cudaEventDestroy(e0);
+    if (e1)
+        cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return fail(nullptr, GRMONTY_B200_ECUDA, "init_tables: %s", cudaGetErrorString(e));
     return GRMONTY_B200_OK;
 }
 

@@ -38,6 +38,10 @@ int gmh_set_dump_cache(void *h, int mode, const char *dir) {
     m->dump_cache_dir = dir ? dir : "";
     return 0;
 }
+int gmh_set_device_tables(void *h, int on) {
+    static_cast<HARMModel *>(h)->options.device_tables = on != 0;
+    return 0;
+}
 int gmh_read_from_cache(void *h) { return static_cast<HARMModel *>(h)->read_from_cache() ? 1 : 0; }
 int gmh_report_spectrum_binary(void *h, const char *path) {
     GUARD(static_cast<HARMModel *>(h)->report_spectrum_binary(path))
@@ -47,7 +51,7 @@ int gmh_init(void *h, int threads) {
     m->init_threads = threads;
     GUARD(m->init())
 }
-/* which: 0 geometry 1 hotcross 2 emiss 3 weight 4 nint */
+/* which: 0 geometry 1 hotcross 2 emiss 3 weight 4 nint (host); 5, 6: device builders */
 int gmh_init_stage(void *h, int which, int threads) {
     auto *m = static_cast<HARMModel *>(h);
     m->init_threads = threads;
@@ -57,6 +61,8 @@ int gmh_init_stage(void *h, int which, int threads) {
         case 2: m->init_emiss_tables(); break;
         case 3: m->init_weight_table(); break;
         case 4: m->init_nint_table(); break;
+        case 5: m->init_tables_on_device(false); break; /* geometry + weight + nint on the GPU */
+        case 6: m->init_tables_on_device(true); break;  /* ... and the hot cross-section table */
         default: throw std::runtime_error("bad init stage");
     })
 }

@@ -657,15 +657,7 @@ void HARMModel::init_nint_table() {
     log_info("Initializing nint table done");
 }
 
-void HARMModel::init() {
-    init_geometry();
-    init_hotcross_table();
-    init_emiss_tables();
-    init_weight_table();
-    init_nint_table();
-}
-
-/* ---- run_simulation: the C ABI call sequence (replaces reference harm_model.cpp:345-405) ----------------- */
+/* ---- the CUDA library, loaded on demand (run_simulation and the device table builders) ------------------- */
 namespace {
 struct CudaLib {
     void *h = nullptr;
@@ -675,6 +667,8 @@ struct CudaLib {
     decltype(&grmonty_b200_result) result = nullptr;
     decltype(&grmonty_b200_destroy) destroy = nullptr;
     decltype(&grmonty_b200_last_error) last_error = nullptr;
+    decltype(&grmonty_b200_hotcross_table) hotcross_table = nullptr;
+    decltype(&grmonty_b200_init_tables) init_tables = nullptr;
 };
 
 std::string self_dir() {
@@ -706,18 +700,13 @@ CudaLib load_cuda_lib(const std::string &hint) {
     L.name = reinterpret_cast<decltype(L.name)>(dlsym(L.h, "grmonty_b200_" #name)); \
     if (!L.name)                                                                  \
         throw std::runtime_error("libgrmonty_b200.so lacks grmonty_b200_" #name);
-    SYM(create) SYM(run) SYM(allreduce) SYM(result) SYM(destroy) SYM(last_error)
+    SYM(create) SYM(run) SYM(allreduce) SYM(result) SYM(destroy) SYM(last_error) SYM(hotcross_table) SYM(init_tables)
 #undef SYM
     return L;
 }
 } /* namespace */
 
-void HARMModel::run_simulation() {
-    const auto start = std::chrono::steady_clock::now();
-    log_info("Starting main loop");
-    CudaLib L = load_cuda_lib(options.cuda_library);
-
-    grmonty_b200_config cfg;
+void HARMModel::fill_config(grmonty_b200_config &cfg) const {
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.abi_version = GRMONTY_B200_ABI_VERSION;
     cfg.struct_size = sizeof(cfg);
@@ -771,6 +760,51 @@ void HARMModel::run_simulation() {
     cfg.gen_budget = options.gen_budget;
     cfg.gen_fine_from = options.gen_fine_from;
     cfg.gen_fine_div = options.gen_fine_div;
+}
+
+/* The grid-dependent tables (geometry, weight, nint) and the hot cross-section table on options.device, through
+ * grmonty_b200_init_tables / grmonty_b200_hotcross_table.  The F(K) and K2 tables (201 entries each)
+ * stay on the host and must exist. */
+void HARMModel::init_tables_on_device(bool with_hotcross) {
+    log_info("Initializing geometry, weight and nint tables on device %d", options.device);
+    CudaLib L = load_cuda_lib(options.cuda_library);
+    const size_t nz = (size_t)header_.n[0] * header_.n[1];
+    det_.assign(nz, 0.0);
+    nint_.assign(kNint + 1, 0.0);
+    dndlnu_max_.assign(kNint + 1, 0.0);
+    if (with_hotcross) {
+        hotcross_.assign((size_t)(kHcNW + 1) * (kHcNT + 1), 0.0);
+        if (L.hotcross_table(options.device, hotcross_.data()) != GRMONTY_B200_OK)
+            throw std::runtime_error(std::string("grmonty_b200_hotcross_table: ") + L.last_error(nullptr));
+    }
+    grmonty_b200_config cfg;
+    fill_config(cfg);
+    double ms = 0.0;
+    if (L.init_tables(&cfg, det_.data(), weight_.data(), nint_.data(), dndlnu_max_.data(), &ms) != GRMONTY_B200_OK)
+        throw std::runtime_error(std::string("grmonty_b200_init_tables: ") + L.last_error(nullptr));
+    log_info("Initializing tables on device done (%.3f ms of kernels)", ms);
+}
+
+void HARMModel::init() {
+    if (options.device_tables) {
+        init_emiss_tables();
+        init_tables_on_device(true);
+        return;
+    }
+    init_geometry();
+    init_hotcross_table();
+    init_emiss_tables();
+    init_weight_table();
+    init_nint_table();
+}
+
+void HARMModel::run_simulation() {
+    const auto start = std::chrono::steady_clock::now();
+    log_info("Starting main loop");
+    CudaLib L = load_cuda_lib(options.cuda_library);
+
+    grmonty_b200_config cfg;
+    fill_config(cfg);
 
     grmonty_b200_ctx *ctx = nullptr;
     if (L.create(&ctx, &cfg) != 0)

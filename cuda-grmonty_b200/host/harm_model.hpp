@@ -20,6 +20,8 @@
 #include <string>
 #include <vector>
 
+struct grmonty_b200_config;
+
 namespace harm {
 
 /* reference harm_data.hpp:19-44 */
@@ -58,6 +60,7 @@ struct RunOptions {
     int rank = 0, world = 1, device = 0;
     int threads_per_block = 0, blocks_per_sm = 0;
     int64_t queue_capacity = 0, gen0 = 0, gen_cap = 0, gen_budget = 0, gen_fine_from = 0, gen_fine_div = 0;
+    bool device_tables = false; /* init(): geometry / weight / nint / hot cross-section tables on the GPU */
     void *nccl_comm = nullptr; /* ncclComm_t for world > 1 (optional: the caller may reduce by other means) */
     std::string cuda_library;  /* path of libgrmonty_b200.so; empty: $GRMONTY_B200_LIB or next to this library */
 };
@@ -116,6 +119,8 @@ public:
     void init_emiss_tables();
     void init_weight_table();
     void init_nint_table();
+    /* the same tables through the C ABI on options.device (needs init_emiss_tables() first) */
+    void init_tables_on_device(bool with_hotcross);
 
 private:
     Header header_;
@@ -129,6 +134,7 @@ private:
     double luminosity_ = 0, max_tau_reported_ = 0;
     bool read_from_cache_ = false;
 
+    void fill_config(struct grmonty_b200_config &cfg) const;
     void apply_header(const double h[26], const std::string &filepath);
     bool load_dump_cache(const std::string &filepath);
     void store_dump_cache(const std::string &filepath, const double h[26]) const;

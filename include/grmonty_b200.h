@@ -184,6 +184,16 @@ const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx);
  * one CPU core).  Needs no context; `table` is a host buffer of GRMONTY_B200_HOTCROSS_N doubles. */
 int grmonty_b200_hotcross_table(int device, double *table);
 
+/* Grid-dependent initialisation tables on the device (what HARMModel::init_geometry, init_weight_table and
+ * init_nint_table compute: reference harm_model.cpp:242-266, :268-306, :308-338).  Reads from `cfg` the grid geometry,
+ * the units, dx3, photon_n, the eight primitive grids and the F(K) / K2 tables (cfg->f, cfg->k2; everything else,
+ * including cfg->geom_det / weight / nint / dndlnu_max, is ignored) and writes
+ *   geom_det[n0*n1]  sqrt|det g_cov| at zone centres,        weight[201]  ln of the super-photon weight per frequency,
+ *   nint[20001], dndlnu_max[20001]  ln of the zone photon-number integral and of max dN/dln(nu) per B theta_e^2.
+ * Any output may be NULL.  `device_ms` (optional) receives the device time of the three kernels.  Needs no context. */
+int grmonty_b200_init_tables(const grmonty_b200_config *cfg, double *geom_det, double *weight, double *nint,
+                             double *dndlnu_max, double *device_ms);
+
 /* FP64 FMA throughput micro-benchmark on the context's device (TFLOP/s, FMA = 2 flop); the roofline
  * denominator of this path (MEASURED_PEAKS.json has no FP64 entry). */
 int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops);
