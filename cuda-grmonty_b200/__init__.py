@@ -425,6 +425,8 @@ def host_lib():
         H.gmh_set_dump_cache.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         H.gmh_read_from_cache.argtypes = [C.c_void_p]
         H.gmh_set_device_tables.argtypes = [C.c_void_p, C.c_int]
+        H.gmh_set_hotcross_cache.argtypes = [C.c_void_p, C.c_char_p]
+        H.gmh_hotcross_from_cache.argtypes = [C.c_void_p]
         for n in ("gmh_get_header", "gmh_get_header_raw", "gmh_get_units", "gmh_get_scalars", "gmh_get_spectrum",
                   "gmh_set_spectrum", "gmh_get_stats"):
             getattr(H, n).argtypes = [C.c_void_p, dp]
@@ -496,6 +498,13 @@ class HarmModel:
     def set_device_tables(self, on: bool = True):
         """init() builds the geometry / weight / nint / hot cross-section tables on the GPU."""
         self.H.gmh_set_device_tables(self.h, int(bool(on)))
+
+    def set_hotcross_cache(self, path: str = ""):
+        """on-disk copy of the grid-independent hot cross-section table (loaded if valid, else built and written)"""
+        self.H.gmh_set_hotcross_cache(self.h, path.encode())
+
+    def hotcross_from_cache(self) -> bool:
+        return bool(self.H.gmh_hotcross_from_cache(self.h))
 
     def read_from_cache(self) -> bool:
         return bool(self.H.gmh_read_from_cache(self.h))

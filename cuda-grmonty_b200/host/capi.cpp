@@ -42,6 +42,11 @@ int gmh_set_device_tables(void *h, int on) {
     static_cast<HARMModel *>(h)->options.device_tables = on != 0;
     return 0;
 }
+int gmh_set_hotcross_cache(void *h, const char *path) {
+    static_cast<HARMModel *>(h)->hotcross_cache = path ? path : "";
+    return 0;
+}
+int gmh_hotcross_from_cache(void *h) { return static_cast<HARMModel *>(h)->hotcross_from_cache() ? 1 : 0; }
 int gmh_read_from_cache(void *h) { return static_cast<HARMModel *>(h)->read_from_cache() ? 1 : 0; }
 int gmh_report_spectrum_binary(void *h, const char *path) {
     GUARD(static_cast<HARMModel *>(h)->report_spectrum_binary(path))

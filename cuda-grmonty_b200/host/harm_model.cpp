@@ -448,8 +448,75 @@ static double total_compton_cross_num(double w, double theta_e) {
     return cross * gm::kSigmaThomson;
 }
 
+/* On-disk copy of the table: it depends on nothing but the grid constants of consts.hpp:97-112, which
+ * the header repeats so that a file written for another grid is not used. */
+namespace {
+struct HotcrossCacheHeader {
+    char magic[8]; /* "GMB2HOTX" */
+    uint32_t version, n_w, n_t, reserved;
+    double min_w, max_w, min_t, max_t;
+};
+HotcrossCacheHeader hotcross_cache_header() {
+    HotcrossCacheHeader h{};
+    std::memcpy(h.magic, "GMB2HOTX", 8);
+    h.version = 1;
+    h.n_w = kHcNW;
+    h.n_t = kHcNT;
+    h.min_w = gm::kHcMinW;
+    h.max_w = gm::kHcMaxW;
+    h.min_t = gm::kHcMinT;
+    h.max_t = gm::kHcMaxT;
+    return h;
+}
+} /* namespace */
+
+bool HARMModel::load_hotcross_cache() {
+    if (hotcross_cache.empty())
+        return false;
+    std::ifstream in(hotcross_cache, std::ios::binary | std::ios::ate);
+    if (!in.is_open())
+        return false;
+    const size_t n = (size_t)(kHcNW + 1) * (kHcNT + 1);
+    const HotcrossCacheHeader want = hotcross_cache_header();
+    HotcrossCacheHeader got;
+    if ((size_t)in.tellg() != sizeof(got) + n * sizeof(double))
+        return false;
+    in.seekg(0);
+    if (!in.read(reinterpret_cast<char *>(&got), sizeof(got)) || std::memcmp(&got, &want, sizeof(got)) != 0)
+        return false;
+    hotcross_.resize(n);
+    return (bool)in.read(reinterpret_cast<char *>(hotcross_.data()), (std::streamsize)(n * sizeof(double)));
+}
+
+void HARMModel::store_hotcross_cache() const {
+    if (hotcross_cache.empty())
+        return;
+    try {
+        const std::string tmp = hotcross_cache + ".tmp";
+        const HotcrossCacheHeader h = hotcross_cache_header();
+        {
+            std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
+            if (!out.is_open())
+                return;
+            out.write(reinterpret_cast<const char *>(&h), sizeof(h));
+            out.write(reinterpret_cast<const char *>(hotcross_.data()),
+                      (std::streamsize)(hotcross_.size() * sizeof(double)));
+            if (!out.good())
+                return;
+        }
+        std::filesystem::rename(tmp, hotcross_cache);
+    } catch (const std::exception &e) {
+        log_info("Hotcross cache not written: %s", e.what());
+    }
+}
+
 void HARMModel::init_hotcross_table() {
     log_info("Initializing HARM model hotcross");
+    hotcross_from_cache_ = load_hotcross_cache();
+    if (hotcross_from_cache_) {
+        log_info("Initializing HARM model hotcross done (cache %s)", hotcross_cache.c_str());
+        return;
+    }
     hotcross_.assign((size_t)(kHcNW + 1) * (kHcNT + 1), 0.0);
     const double l_min_w = std::log10(gm::kHcMinW), l_min_t = std::log10(gm::kHcMinT);
     const double d_l_w = std::log10(gm::kHcMaxW / gm::kHcMinW) / kHcNW;
@@ -461,6 +528,7 @@ void HARMModel::init_hotcross_table() {
                 std::log10(total_compton_cross_num(std::pow(10.0, l_w), std::pow(10.0, l_t)));
         }
     });
+    store_hotcross_cache();
     log_info("Initializing HARM model hotcross done");
 }
 
@@ -773,9 +841,13 @@ void HARMModel::init_tables_on_device(bool with_hotcross) {
     nint_.assign(kNint + 1, 0.0);
     dndlnu_max_.assign(kNint + 1, 0.0);
     if (with_hotcross) {
-        hotcross_.assign((size_t)(kHcNW + 1) * (kHcNT + 1), 0.0);
-        if (L.hotcross_table(options.device, hotcross_.data()) != GRMONTY_B200_OK)
-            throw std::runtime_error(std::string("grmonty_b200_hotcross_table: ") + L.last_error(nullptr));
+        hotcross_from_cache_ = load_hotcross_cache();
+        if (!hotcross_from_cache_) {
+            hotcross_.assign((size_t)(kHcNW + 1) * (kHcNT + 1), 0.0);
+            if (L.hotcross_table(options.device, hotcross_.data()) != GRMONTY_B200_OK)
+                throw std::runtime_error(std::string("grmonty_b200_hotcross_table: ") + L.last_error(nullptr));
+            store_hotcross_cache();
+        }
     }
     grmonty_b200_config cfg;
     fill_config(cfg);

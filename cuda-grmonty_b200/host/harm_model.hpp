@@ -97,6 +97,9 @@ public:
     std::string dump_cache_dir; /* empty: next to the dump */
     std::string dump_cache_path(const std::string &filepath) const;
     bool read_from_cache() const { return read_from_cache_; }
+    /* on-disk copy of the (grid-independent) hot cross-section table; empty: always rebuild it */
+    std::string hotcross_cache;
+    bool hotcross_from_cache() const { return hotcross_from_cache_; }
     const Units &units() const { return units_; }
     const RunStats &stats() const { return stats_; }
     double bias_norm() const { return bias_norm_; }
@@ -132,7 +135,9 @@ private:
     std::array<double, kNESamp + 1> f_{}, k2_{}, weight_{};
     RunStats stats_;
     double luminosity_ = 0, max_tau_reported_ = 0;
-    bool read_from_cache_ = false;
+    bool read_from_cache_ = false, hotcross_from_cache_ = false;
+    bool load_hotcross_cache();
+    void store_hotcross_cache() const;
 
     void fill_config(struct grmonty_b200_config &cfg) const;
     void apply_header(const double h[26], const std::string &filepath);

@@ -3,7 +3,7 @@
  *     --photon_n N   --mass_unit M   --harm_dump_path FILE   --spectrum_path FILE   --verbosity LEVEL
  * Both `--flag value`, `--flag=value` and the single-dash spellings abseil accepts (`-photon_n 5000000`,
  * reference README.md:30) work.  Extra flags of the B200 path: --seed, --device, --init_threads, --dump_cache 0|1
- * --device_tables 0|1 (build the init tables on the GPU),
+ * --device_tables 0|1 (build the init tables on the GPU), --hotcross_cache FILE (on-disk hot cross-section table),
  * (binary cache next to the dump, or under --dump_cache_dir), --spectrum_bin_path FILE (all 13 accumulated fields).
  * Call order is the reference's: HARMModel(photon_n, mass_unit) -> read_file -> init -> run_simulation ->
  * report_spectrum.  (The reference seeds its global mt19937 with 123 at this point; here the seed is the
@@ -71,6 +71,7 @@ int main(int argc, char **argv) {
             model.init_threads = std::atoi(v.c_str());
         if (flag_value(argc, argv, "device_tables", v))
             model.options.device_tables = std::atoi(v.c_str()) != 0;
+        flag_value(argc, argv, "hotcross_cache", model.hotcross_cache);
         if (flag_value(argc, argv, "dump_cache", v))
             model.dump_cache = std::atoi(v.c_str()) != 0;
         flag_value(argc, argv, "dump_cache_dir", model.dump_cache_dir);

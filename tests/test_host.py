@@ -244,3 +244,29 @@ def test_binary_spectrum_keeps_all_thirteen_fields(host48, tmp_path):
         gm.read_spectrum_binary(p)
     with pytest.raises(gm.GrmontyError):
         host48.report_spectrum_binary(str(tmp_path / "no" / "such" / "dir" / "s.bin"))
+
+
+def test_hotcross_table_disk_cache(host48, tmp_path):
+    """the hot cross-section table depends only on the consts grid; a second model loads it from disk"""
+    import time
+    path = str(tmp_path / "hotcross.bin")
+    a = gm.HarmModel(1000, 4e19)
+    a.set_hotcross_cache(path)
+    a.init_stage(1)
+    assert not a.hotcross_from_cache() and os.path.getsize(path) == 8 + 16 + 32 + 221 * 81 * 8
+    want = host48.model_dict()["hotcross"]
+    b = gm.HarmModel(1000, 4e19)
+    b.set_hotcross_cache(path)
+    t0 = time.perf_counter()
+    b.init_stage(1)
+    assert b.hotcross_from_cache() and time.perf_counter() - t0 < 0.05
+    assert np.array_equal(b.model_dict()["hotcross"], want) and np.array_equal(a.model_dict()["hotcross"], want)
+    raw = open(path, "rb").read()
+    for bad in (raw[:-8], raw[:8] + b"\x07" + raw[9:], b"junk"):     # truncated, other version, foreign file
+        with open(path, "wb") as f:
+            f.write(bad)
+        c = gm.HarmModel(1000, 4e19)
+        c.set_hotcross_cache(path)
+        c.init_stage(1, 0)
+        assert not c.hotcross_from_cache() and np.array_equal(c.model_dict()["hotcross"], want)
+        assert open(path, "rb").read() == raw
