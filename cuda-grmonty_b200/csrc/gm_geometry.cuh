@@ -53,7 +53,7 @@ struct GeoPoint {
 __device__ __forceinline__ GeoPoint geo_point(const GmParams &P, double x1, double x2) {
     GeoPoint g;
     /* branch-free evaluations (gm_math.cuh): exp and sincospi interleave, sincos follows */
-    g.r = fm::exp_(x1);
+    g.r = fm::exp_bounded(x1); /* x1 = ln r of a point on or near the grid; NaN stays NaN */
     g.rm = g.r + P.r_0;
     fm::sincospi_(2.0 * x2, &g.sx, &g.cx);
     const double omh = 1.0 - P.h_slope;
@@ -342,18 +342,38 @@ __device__ __forceinline__ double step_size(const GmParams &P, const double x[4]
     return fm::rcp(i1 + i2 + i3);
 }
 
-/* |a - b| / |b + eps| for the fixed-point convergence test.  The quotient only feeds the thresholds e_tol = 1e-3
- * and the halving decision, so the hardware's approximate reciprocal (rcp.approx.ftz.f64, ~2^-23 relative) is
- * used instead of a full IEEE division: eight FP64 divisions per attempt become eight MUFU ops. */
-__device__ __forceinline__ double rel_change(double a, double b) {
-#ifdef GM_FAST_ERRNORM
-    /* measured on B200: -4% kernel time, but about one halving decision in 1e8 attempts flips relative to the
-     * oracle, so it is off by default (parity first) */
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b + kEps));
-    return fabs((a - b) * r);
+/* |a - b| / |b + eps| for the fixed-point convergence test */
+__device__ __forceinline__ double rel_change(double a, double b) { return fabs(fm::div(a - b, b + kEps)); }
+
+/* The error norm sum_i |kp_i - kn_i| / |kn_i + eps| only feeds the threshold e_tol.  Two cheaper forms were measured
+ * on B200 (tools/gpu_ab.sh, ms per step at configs[1], exact IEEE divisions = 652):
+ *   - approximate reciprocals only (rcp.approx.ftz.f64, 20 mantissa bits): -4 %, but about one accept / halve decision
+ *     in 1e8 flips against the oracle -- rejected, parity first;
+ *   - GM_HYBRID_ERRNORM: approximate first, exact divisions redone in a cold call when the norm lies within 2^-16 of
+ *     the threshold (every decision exact): 677, i.e. slower -- the call keeps eight more values live across the
+ *     hottest part of the attempt (spills) and adds a reconvergence point.  Off. */
+#ifndef GM_HYBRID_ERRNORM
+#define GM_HYBRID_ERRNORM 0
+#endif
+__device__ __noinline__ double err_norm_exact(double p0, double p1, double p2, double p3, double n0, double n1,
+                                              double n2, double n3) {
+    return ((rel_change(p0, n0) + rel_change(p1, n1)) + rel_change(p2, n2)) + rel_change(p3, n3);
+}
+__device__ __forceinline__ double err_norm(const double kp[4], const double kn[4]) {
+#if GM_HYBRID_ERRNORM
+    double err = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(kn[i] + kEps));
+        err += fabs((kp[i] - kn[i]) * r);
+    }
+    if (fabs(err - kETol) < kETol * (1.0 / 65536.0))
+        err = err_norm_exact(kp[0], kp[1], kp[2], kp[3], kn[0], kn[1], kn[2], kn[3]);
+    return err;
 #else
-    return fabs(fm::div(a - b, b + kEps));
+    return ((rel_change(kp[0], kn[0]) + rel_change(kp[1], kn[1])) + rel_change(kp[2], kn[2])) +
+           rel_change(kp[3], kn[3]);
 #endif
 }
 
@@ -409,12 +429,10 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
 #else
         geodesic_rhs(c, kp, dkn);
 #endif
-        err = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i)
             kn[i] = kh[i] + dl_2 * dkn[i];
-            err += rel_change(kp[i], kn[i]);
-        }
+        err = err_norm(kp, kn);
         if (!(err > kETol))
             break;
 #pragma unroll

@@ -191,8 +191,9 @@ GM_HD double sqrt_(double x) {
     h = fma(h, r, h);
     const double d = fma(-g, g, x);
     g = fma(d, h, g);
-    const double special = x < 0.0 ? from_bits(0x7ff8000000000000ull) : x; /* 0 -> 0, NaN -> NaN */
-    return x > 0.0 ? g : special;                                           /* x == 0: the seed is inf, g is NaN */
+    /* negative or NaN x: the seed and therefore g are already NaN; only x == 0 (seed inf, g = 0 * inf) needs the
+     * select */
+    return x == 0.0 ? x : g;
 }
 
 /* exp(x), any finite x: 0 below -708 (denormal results are flushed), +inf above 709.78 */
@@ -217,22 +218,32 @@ GM_HD double exp_core(double r, double n) {
     return with_hi(p, hi_word(p) + (ni << 20));
 }
 
-GM_HD double exp_(double x) {
-    /* no clamp of x: inside [-708, 709.78] n stays in [-1021, 1024] (n = 1024 only with r < 0, p < 1, so the
-     * exponent field still fits); outside, whatever the core produced is replaced by the selects below */
+/* exp(x) for x known to lie in [-708, 709]: no range selects (table interpolants, ln r of the grid) */
+GM_HD double exp_bounded(double x) {
     const double t = fma(x, C_(LOG2E), C_(MAGIC));
     const double n = t - C_(MAGIC);
     double r = fma(n, -C_(LN2_HI), x);
     r = fma(n, -C_(LN2_LO), r);
-    double v = exp_core(r, n);
-    v = x < -708.0 ? 0.0 : v;
-    v = x > 709.78 ? from_bits(0x7ff0000000000000ull) : v;
-    return x != x ? x : v; /* NaN in, NaN out */
+    return exp_core(r, n);
 }
 
-/* 10^x */
-GM_HD double exp10_(double x) {
-    const double t = fma(x, C_(LOG2_10), C_(MAGIC)); /* unclamped, as in exp_ */
+GM_HD double exp_(double x) {
+    /* no clamp of x: inside [-708, 709.78] n stays in [-1021, 1024] (n = 1024 only with r < 0, p < 1, so the
+     * exponent field still fits); outside, whatever the core produced is replaced by the selects below.  A NaN x
+     * needs no select on the device: n, r and p are NaN, (int)NaN is 0, the scaling leaves the NaN alone. */
+    double v = exp_bounded(x);
+    v = x < -708.0 ? 0.0 : v;
+    v = x > 709.78 ? from_bits(0x7ff0000000000000ull) : v;
+#ifdef __CUDA_ARCH__
+    return v;
+#else
+    return x != x ? x : v; /* the host model's (int)NaN is not 0 */
+#endif
+}
+
+/* 10^x for x known to lie in [-307, 308] */
+GM_HD double exp10_bounded(double x) {
+    const double t = fma(x, C_(LOG2_10), C_(MAGIC));
     const double n = t - C_(MAGIC);
     /* x - n log10(2) in two parts, then to the natural base */
     double r = fma(n, -C_(LG2_HI), x);
@@ -240,10 +251,19 @@ GM_HD double exp10_(double x) {
     const double rh = r * C_(LN10_HI);
     const double rl = fma(r, C_(LN10_HI), -rh);
     const double rr = rh + fma(r, -C_(LN10_LO_NEG), rl);
-    double v = exp_core(rr, n);
+    return exp_core(rr, n);
+}
+
+/* 10^x */
+GM_HD double exp10_(double x) {
+    double v = exp10_bounded(x);
     v = x < -307.0 ? 0.0 : v;
     v = x > 308.25 ? from_bits(0x7ff0000000000000ull) : v;
+#ifdef __CUDA_ARCH__
+    return v;
+#else
     return x != x ? x : v;
+#endif
 }
 
 /* ln(x) for normal x > 0 */

@@ -36,7 +36,7 @@ __device__ __forceinline__ double k2_eval_l(const GmParams &P, double theta_e, d
     i = max(0, min(i, kNESamp - 1));
     d_i -= i;
     const double t0 = k2_tab ? k2_tab[i] : __ldg(P.k2 + i), t1 = k2_tab ? k2_tab[i + 1] : __ldg(P.k2 + i + 1);
-    const double tab = fm::exp_((1.0 - d_i) * t0 + d_i * t1);
+    const double tab = fm::exp_bounded((1.0 - d_i) * t0 + d_i * t1); /* ln K2 table: finite entries */
     const double v = theta_e > kJnuMaxT ? 2.0 * theta_e * theta_e : tab;
     return theta_e < kThetaEMin ? 0.0 : v;
 }
@@ -178,7 +178,7 @@ __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, d
     }
     const double l_cross = (1.0 - d_i) * (1.0 - d_j) * t00 + d_i * (1.0 - d_j) * t10 + (1.0 - d_i) * d_j * t01 +
                            d_i * d_j * t11;
-    double sigma = fm::exp10_(l_cross);
+    double sigma = fm::exp10_bounded(l_cross); /* log10 sigma table: finite entries */
     sigma = thomson ? kSigmaThomson : sigma;
     if (!thomson && !in_table)
         sigma = hotcross_cold(w, theta_e);
