@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -245,9 +246,18 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
     ctx->device = cfg->device;
     int rc = [&]() -> int {
         CK(cudaSetDevice(ctx->device));
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, ctx->device));
-        ctx->sm_count = prop.multiProcessorCount;
+        /* one attribute, not cudaGetDeviceProperties: the full query costs up to 0.2 s per call on this driver */
+        CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, ctx->device));
+        const bool trace_create = getenv("GRMONTY_B200_TRACE") != nullptr;
+        auto t_last = std::chrono::steady_clock::now();
+        auto mark = [&](const char *what) {
+            if (!trace_create)
+                return;
+            const auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[grmonty_b200] create: %-22s %8.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(now - t_last).count());
+            t_last = now;
+        };
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
@@ -258,6 +268,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         GmParams &P = ctx->P;
         fill_params(P, cfg);
 
+        mark("streams and events");
         /* ---- one device arena for everything (reused from the cache when possible) ---- */
         const size_t nz = (size_t)cfg->n0 * cfg->n1;
         unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 22);
@@ -304,6 +315,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             ctx->arena_used = 0;
         }
 
+        mark("arena");
         /* ---- model upload: primitives interleaved [n0][n1][8] ---- */
         {
             std::vector<double> inter(nz * 8);
@@ -329,6 +341,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         P.nint = ctx->d_nint;
         P.dndlnu_max = ctx->d_dnmax;
 
+        mark("uploads");
         /* keep the fluid grid L2-resident (access-policy window; best effort) */
         {
             size_t bytes = nz * 8 * sizeof(double);
@@ -361,6 +374,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             }
         }
 
+        mark("L2 policy");
         /* ---- per-zone emission data and the zone -> primary index prefix ---- */
         CK(arena_alloc(ctx, &ctx->d_zones, nz));
         CK(arena_alloc(ctx, &ctx->d_num, nz));
@@ -395,6 +409,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         }
         CK(cudaMemcpy(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice));
 
+        mark("zone kernel + prefix");
         /* ---- photon pool and stage queues ---- */
         auto alloc_pool = [&](PhotonPool &pl, unsigned long long c) -> cudaError_t {
             pl.capacity = (unsigned int)c;
@@ -455,6 +470,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         ctx->A.work = ctx->d_work;
         ctx->A.error = ctx->d_error;
 
+        mark("pool and queues");
         /* ---- launch geometry ---- */
         ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;
         int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 1;
@@ -482,6 +498,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             ctx->gen_ramp = cfg->gen_ramp;
         if (cfg->gen_budget_spread != 0)
             ctx->gen_budget_spread = cfg->gen_budget_spread; /* negative: off */
+        mark("launch geometry");
         return GRMONTY_B200_OK;
     }();
     if (rc != GRMONTY_B200_OK) {

@@ -11,7 +11,7 @@ if not os.path.exists(p):
     make_harm_dump.write_dump(p, *make_harm_dump.make_dump(n0=192, n1=192))
 hm = gm.HarmModel(photon_n, 4e19); hm.read_file(p); hm.init()
 model = hm.model_dict()
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', 3))):
     t0 = time.perf_counter(); c = gm.Context(model, seed=123)
     t1 = time.perf_counter(); c.run()
     t2 = time.perf_counter(); r = c.result()
@@ -22,6 +22,6 @@ for rep in range(3):
           f"{st['transport_ms']:.1f}, gens {st['n_generations']}, launches {st['n_kernel_launches']})  result {1e3*(t3-t2):6.1f} ms  "
           f"destroy {1e3*(t4-t3):8.1f} ms")
 hm.set_options(seed=123)
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', 3))):
     t0 = time.perf_counter(); hm.run_simulation(); t1 = time.perf_counter()
     print(f"HARMModel.run_simulation {1e3*(t1-t0):8.1f} ms  stats {hm.stats()['seconds']*1e3:.1f}")
