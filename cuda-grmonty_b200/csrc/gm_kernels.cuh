@@ -279,8 +279,10 @@ __device__ __noinline__ void cost_call(const TransportArgs *Ag, unsigned int slo
     atomicAdd(A.zone_cost + A.P.n0 + i, 1ull);
 }
 
+/* iterations between two block-wide synchronisations (measured, ms per step at configs[1]: 8 -> 673, 16 -> 660,
+ * 24 -> 658, 32 -> 657; with the later kernel 16 -> 640, 32 -> 636; profiles/r1_ab_microopts.txt) */
 #ifndef GM_ITERS_PER_SYNC
-#define GM_ITERS_PER_SYNC 16
+#define GM_ITERS_PER_SYNC 32
 #endif
 constexpr int kItersPerSync = GM_ITERS_PER_SYNC;
 

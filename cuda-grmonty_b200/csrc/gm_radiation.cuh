@@ -156,11 +156,11 @@ __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, d
     const bool thomson = w * theta_e < 1.0e-6;
     const bool in_table = !(w <= kHcMinW || w >= kHcMaxW || theta_e <= kHcMinT || theta_e >= kHcMaxT);
     const double kLog10E = 0.43429448190325182765;
-    double qw = (l_w * kLog10E - P.hc_l_min_w) * P.inv_hc_d_l_w;
-    double qt = (l_theta * kLog10E - P.hc_l_min_t) * P.inv_hc_d_l_t;
-    qw = fm::min_(fm::max_(qw, 0.0), (double)kHcNW - 1.0e-6);
-    qt = fm::min_(fm::max_(qt, 0.0), (double)kHcNT - 1.0e-6);
-    const int i = (int)qw, j = (int)qt;
+    const double qw = (l_w * kLog10E - P.hc_l_min_w) * P.inv_hc_d_l_w;
+    const double qt = (l_theta * kLog10E - P.hc_l_min_t) * P.inv_hc_d_l_t;
+    /* the interpolant is used only for in_table points, where 0 < qw < n_w and 0 < qt < n_t: clamping the cell index
+     * (two integer min/max) keeps the loads in bounds for all other lanes, whose result is replaced below */
+    const int i = max(0, min((int)qw, kHcNW - 1)), j = max(0, min((int)qt, kHcNT - 1));
     const double d_i = qw - i, d_j = qt - j;
     const int off = i * (kHcNT + 1) + j;
     double t00, t10, t01, t11;

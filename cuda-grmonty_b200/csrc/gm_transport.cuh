@@ -462,14 +462,25 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         L.bi = bf;
     }
     L.ne_pos = f.n_e > 0.0;
-    const double x1r = -fm::log_(rng_uniform(P, L.rng));
-    /* w / bias; bias == 0 gives +inf in the reference (Appendix A.3), which the scatter test below rejects */
-    const double w_child = bias > 0.0 ? fm::div(L.w, bias) : fm::from_bits(0x7ff0000000000000ull);
+    /* Scatter test of the reference (:980-985): x1 = -ln U, scatter iff bias * d_tau_scatt > x1 and w / bias > w_min.
+     * -ln U >= 1 - U, so when 1 - U exceeds bias * d_tau_scatt (by a margin far above the rounding of the logarithm)
+     * the test fails whatever x1 is: the logarithm and the division run only for the ~0.5 % of steps that can
+     * scatter, and every decision is the one the reference's form gives. */
+    const double u_scatt = rng_uniform(P, L.rng);
+    const double bd = bias * d_tau_scatt;
+    double x1r = 0.0, w_child = 0.0;
+    bool scatters = false;
+    if ((1.0 - u_scatt) <= bd * 1.0000001) {
+        x1r = -fm::log_(u_scatt);
+        /* w / bias; bias == 0 gives +inf in the reference (Appendix A.3), which the test rejects through bd = 0 */
+        w_child = bias > 0.0 ? fm::div(L.w, bias) : fm::from_bits(0x7ff0000000000000ull);
+        scatters = bd > x1r && w_child > kWeightMin;
+    }
     StepResult res = STEP_CONTINUE;
-    if (bias * d_tau_scatt > x1r && w_child > kWeightMin) {
+    if (scatters) {
         /* ---- the photon scatters in this step (reference :985-1005): park it ---- */
         const Rng crng = rng_child(P, L.rng);
-        const double frac = fm::div(x1r, bias * d_tau_scatt);
+        const double frac = fm::div(x1r, bd);
         d_tau_abs *= frac;
         if (d_tau_abs > 100) {
             L.status |= 4;
