@@ -335,9 +335,9 @@ def main():
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE transport launch (a 0.75 M-primary
-                     # generation) in the ncu --set full capture profiles/r1_transport_ncu_final.txt: 38 GB/s, i.e.
-                     # 0.6 % of HBM -- the path is FP64-latency bound, not traffic bound
-                     "traffic": 9.33e8,
+                     # generation) in the ncu --set full capture profiles/r1_transport_ncu_final.txt: 36 GB/s, i.e.
+                     # 0.5 % of HBM -- the path is FP64-latency bound, not traffic bound
+                     "traffic": 7.57e8,
                      "peak_source": "DFMA micro-benchmark in this process (grmonty_b200_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "kernel": "transport_kernel", "kernel_ms_per_step": transport_ms / args.steps},
