@@ -137,15 +137,8 @@ template <typename T> static cudaError_t upload(grmonty_b200_ctx *ctx, T **dst, 
     return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
 }
 
-/* dynamic shared memory of the transport kernel: 13 snapshot rows per thread, plus -- in the one-CTA-per-SM variants --
- * the hot cross-section and K2 tables */
-static size_t transport_smem_bytes(int threads, int blocks_per_sm) {
-    size_t b = (size_t)13 * threads * sizeof(double);
-    if (GM_SMEM_TABLES && blocks_per_sm == 1)
-        b += ((size_t)GRMONTY_B200_HOTCROSS_N + GRMONTY_B200_TABLE_N) * sizeof(double);
-    return b;
-}
-static int want_bps_of(const grmonty_b200_ctx *ctx) { return ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1; }
+/* dynamic shared memory of the transport kernel: 13 snapshot rows per thread */
+static size_t transport_smem_bytes(int threads) { return (size_t)13 * threads * sizeof(double); }
 
 /* ---- kernel dispatch over the compiled (block, min-blocks) variants ------------------------------------- */
 typedef void (*TransportFn)(const TransportArgs);
@@ -478,7 +471,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         if (!v)
             return fail(ctx, GRMONTY_B200_EINVAL, "no compiled kernel variant for %d threads x %d blocks/SM",
                         ctx->threads, want_bps);
-        const size_t smem = transport_smem_bytes(ctx->threads, want_bps_of(ctx));
+        const size_t smem = transport_smem_bytes(ctx->threads);
         CK(cudaFuncSetAttribute((const void *)v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)v->fn, ctx->threads, smem));
@@ -667,7 +660,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         }
         CK(cudaEventRecord(ctx->ev3, ctx->stream)); /* read after the batch's one synchronisation below */
     }
-    const size_t smem = transport_smem_bytes(ctx->threads, want_bps_of(ctx));
+    const size_t smem = transport_smem_bytes(ctx->threads);
     /* do not launch far more threads than there are photons to start with (tiny generations / test batches) */
     long long blocks = std::min<long long>(ctx->grid_blocks,
                                            std::max<long long>(1, (n_start * 2 + ctx->threads - 1) / ctx->threads));

@@ -20,24 +20,6 @@
  * row, in each fixed-point iteration, instead of holding the 36 connection components across the two iterations.
  * Measured on B200: t_push_kernel 194 -> 165 registers, transport kernel spills 102 -> 40 bytes, run time -2.6 %
  * in spite of the recomputation. */
-/* Measured switches (tools/gpu_ab.sh, interleaved A/B on one B200, configs[1], ms per step; base 706):
- *   GM_ACQUIRE_POLL   ld.acquire on the ready-queue entry instead of ld.volatile + membar    694  (kept)
- *   GM_PREFETCH_FLUID prefetch.global.L1 of the four zone records one attempt ahead          724  (off: the extra
- *                     address arithmetic and LSU slots cost more than the L2 latency they hide at 8 warps/SM)
- *   GM_SMEM_TABLES    hot cross-section + K2 tables in shared memory (145 KB)                721  (off: the carve-out
- *                     shrinks L1 from ~200 KB to ~60 KB and the fluid-grid / local-memory hit rate pays for it) */
-#ifndef GM_PREFETCH_FLUID
-#define GM_PREFETCH_FLUID 0
-#endif
-#ifndef GM_SMEM_TABLES
-#define GM_SMEM_TABLES 0
-#endif
-#ifndef GM_ACQUIRE_POLL
-#define GM_ACQUIRE_POLL 1
-#endif
-#ifndef GM_UNROLL_FIXED_POINT
-#define GM_UNROLL_FIXED_POINT 0
-#endif
 /* GM_ERRNORM_ONEDIV / GM_STEP_ONEDIV: sums of quotients over one common denominator -- one FP64 division instead of
  * four.  The results differ from the quotient-by-quotient forms by rounding only (a few ulp; every product stays far
  * inside the double range, see the comments at the two sites); measured 633 -> 618 ms per step for the error norm
@@ -367,33 +349,12 @@ __device__ __forceinline__ double step_size(const GmParams &P, const double x[4]
 /* |a - b| / |b + eps| for the fixed-point convergence test */
 __device__ __forceinline__ double rel_change(double a, double b) { return fabs(fm::div(a - b, b + kEps)); }
 
-/* The error norm sum_i |kp_i - kn_i| / |kn_i + eps| only feeds the threshold e_tol.  Two cheaper forms were measured
- * on B200 (tools/gpu_ab.sh, ms per step at configs[1], exact IEEE divisions = 652):
- *   - approximate reciprocals only (rcp.approx.ftz.f64, 20 mantissa bits): -4 %, but about one accept / halve decision
- *     in 1e8 flips against the oracle -- rejected, parity first;
- *   - GM_HYBRID_ERRNORM: approximate first, exact divisions redone in a cold call when the norm lies within 2^-16 of
- *     the threshold (every decision exact): 677, i.e. slower -- the call keeps eight more values live across the
- *     hottest part of the attempt (spills) and adds a reconvergence point.  Off. */
-#ifndef GM_HYBRID_ERRNORM
-#define GM_HYBRID_ERRNORM 0
-#endif
-__device__ __noinline__ double err_norm_exact(double p0, double p1, double p2, double p3, double n0, double n1,
-                                              double n2, double n3) {
-    return ((rel_change(p0, n0) + rel_change(p1, n1)) + rel_change(p2, n2)) + rel_change(p3, n3);
-}
+/* The error norm sum_i |kp_i - kn_i| / |kn_i + eps| of the fixed-point iteration only feeds the threshold e_tol.
+ * Measured alternatives that were rejected (profiles/r1_ab_microopts.txt): approximate reciprocals
+ * (rcp.approx.ftz.f64) are 4 % faster but flip about one accept / halve decision in 1e8 against the oracle; the same
+ * with an exact redo near the threshold is slower than the exact form (spills). */
 __device__ __forceinline__ double err_norm(const double kp[4], const double kn[4]) {
-#if GM_HYBRID_ERRNORM
-    double err = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(kn[i] + kEps));
-        err += fabs((kp[i] - kn[i]) * r);
-    }
-    if (fabs(err - kETol) < kETol * (1.0 / 65536.0))
-        err = err_norm_exact(kp[0], kp[1], kp[2], kp[3], kn[0], kn[1], kn[2], kn[3]);
-    return err;
-#elif GM_ERRNORM_ONEDIV
+#if GM_ERRNORM_ONEDIV
     /* sum_i |n_i| / |d_i| over one common denominator: one division instead of four (differs from the four-quotient
      * form by rounding only) */
     const double d0 = fabs(kn[0] + kEps), d1 = fabs(kn[1] + kEps), d2 = fabs(kn[2] + kEps), d3 = fabs(kn[3] + kEps);
@@ -405,20 +366,6 @@ __device__ __forceinline__ double err_norm(const double kp[4], const double kn[4
     return ((rel_change(kp[0], kn[0]) + rel_change(kp[1], kn[1])) + rel_change(kp[2], kn[2])) +
            rel_change(kp[3], kn[3]);
 #endif
-}
-
-__device__ __forceinline__ void prefetch_fluid_cell(const GmParams &P, double x1, double x2) {
-    if (x1 < P.x_start1 || x1 > P.x_stop1 || x2 < P.x_start2 || x2 > P.x_stop2)
-        return;
-    int i = (int)((x1 - P.x_start1) * P.inv_dx1 - 0.5 + 1000) - 1000;
-    int j = (int)((x2 - P.x_start2) * P.inv_dx2 - 0.5 + 1000) - 1000;
-    i = max(0, min(i, P.n0 - 2));
-    j = max(0, min(j, P.n1 - 2));
-    const double *z = P.grid + ((size_t)i * P.n1 + j) * 8;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(z));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(z + 8));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(z + (size_t)P.n1 * 8));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(z + (size_t)P.n1 * 8 + 8));
 }
 
 /* One push_photon attempt of size dl from (x,k,dk) (reference harm_model.cpp:1230-1277): half kick, drift,
@@ -436,11 +383,6 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
         kp[i] = kh[i] + d;
         xn[i] = x[i] + kh[i] * dl;
     }
-    /* the interaction step after an accepted attempt interpolates the fluid at xn: start pulling its four zone
-     * records (2 x 128 B) into L1 now, a whole attempt ahead of their use (an L2 hit costs ~600 cycles otherwise) */
-#if GM_PREFETCH_FLUID
-    prefetch_fluid_cell(P, xn[1], xn[2]);
-#endif
     q = geo_point(P, xn[1], xn[2]);
 #if !GM_FUSED_RHS
     Connection c;
@@ -450,11 +392,7 @@ __device__ __forceinline__ bool push_attempt(const GmParams &P, const double x[4
      * of the error norm in the instruction stream (the loop body is the largest piece of the hot code, which
      * competes for the 32 KB instruction cache) */
     double err = 0.0;
-#if GM_UNROLL_FIXED_POINT
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
     for (int it = 0; it < kMaxIter; ++it) {
 #if GM_FUSED_RHS
         GeoPoint qq = q;

@@ -297,18 +297,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
     __shared__ int s_quit;
     const int lane = threadIdx.x & 31;
     double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
-    /* one CTA per SM: the hot cross-section and K2 tables live in shared memory behind the snapshot rows */
-    const double *hc_tab = nullptr, *k2_tab = nullptr;
-    if (GM_SMEM_TABLES && MIN_BLOCKS == 1) {
-        double *s_hc = gm_smem + 13 * BLOCK, *s_k2 = s_hc + (kHcNW + 1) * (kHcNT + 1);
-        for (int i = threadIdx.x; i < (kHcNW + 1) * (kHcNT + 1); i += BLOCK)
-            s_hc[i] = __ldg(A.P.hotcross + i);
-        for (int i = threadIdx.x; i <= kNESamp; i += BLOCK)
-            s_k2[i] = __ldg(A.P.k2 + i);
-        __syncthreads();
-        hc_tab = s_hc;
-        k2_tab = s_k2;
-    }
     Live L;
     bool has = false;
     long long ticket = -1; /* position in the ready queue this lane is entitled to (monotone queue, no wrap) */
@@ -379,15 +367,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                 }
                 if (!has && ticket >= 0 && ticket < (long long)A.ready.capacity) {
                     /* acquire: pairs with the producer's fence + store in queue_push (no separate membar here) */
-#if GM_ACQUIRE_POLL
                     const unsigned int v = ld_acquire_u32(A.ready.entries + ticket);
-#else
-                    const unsigned int v = ld_volatile_u32(A.ready.entries + ticket);
-#endif
                     if (v) {
-#if !GM_ACQUIRE_POLL
-                        __threadfence();
-#endif
                         const unsigned int slot = v - 1u;
                         ticket = -1;
                         live_load(A, slot, L);
@@ -413,7 +394,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
             if (has) {
                 ++wk.live_iters;
                 bool record;
-                const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record, hc_tab, k2_tab);
+                const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
                 if (r == STEP_FINISHED) {
                     cost_call(A.self, L.slot, L.n_step);
                     if (record) {

@@ -26,17 +26,13 @@ __device__ __forceinline__ double interp_exp_table(const double *tab, double lx,
 }
 
 /* K2(1/theta_e) given l_theta = ln(theta_e) (reference jnu_mixed::k2_eval, jnu_mixed.cpp:102-111); selects only */
-/* `k2_tab` / `hc_tab` (optional, below): copies of the K2 and hot cross-section tables in shared memory -- the
- * transport kernel keeps them there (145 KB) because every interaction reads six entries whose addresses are known
- * only after two logarithms: an L2 hit (~600 cycles) at the end of a dependent chain, a shared-memory read is ~30. */
-__device__ __forceinline__ double k2_eval_l(const GmParams &P, double theta_e, double l_theta,
-                                            const double *k2_tab = nullptr) {
+__device__ __forceinline__ double k2_eval_l(const GmParams &P, double theta_e, double l_theta) {
     double d_i = (l_theta - P.jnu_l_min_t) * P.inv_jnu_d_l_t;
     int i = (int)d_i;
     i = max(0, min(i, kNESamp - 1));
     d_i -= i;
-    const double t0 = k2_tab ? k2_tab[i] : __ldg(P.k2 + i), t1 = k2_tab ? k2_tab[i + 1] : __ldg(P.k2 + i + 1);
-    const double tab = fm::exp_bounded((1.0 - d_i) * t0 + d_i * t1); /* ln K2 table: finite entries */
+    /* ln K2 table: finite entries */
+    const double tab = fm::exp_bounded((1.0 - d_i) * __ldg(P.k2 + i) + d_i * __ldg(P.k2 + i + 1));
     const double v = theta_e > kJnuMaxT ? 2.0 * theta_e * theta_e : tab;
     return theta_e < kThetaEMin ? 0.0 : v;
 }
@@ -59,8 +55,8 @@ __device__ __forceinline__ double f_eval(const GmParams &P, double theta_e, doub
  * Branch-free: the two "return 0" conditions of the reference are applied as selects at the end, the arithmetic
  * in between runs on guarded arguments. */
 __device__ __forceinline__ double synch_sin_l(const GmParams &P, double nu, double n_e, double theta_e, double b,
-                                              double sin_th, double l_theta, const double *k2_tab = nullptr) {
-    const double k2 = k2_eval_l(P, theta_e, l_theta, k2_tab);
+                                              double sin_th, double l_theta) {
+    const double k2 = k2_eval_l(P, theta_e, l_theta);
     const double nu_c = b * (kEE / (2.0 * kPi * kME * kCL));
     const double nu_s = (2.0 / 9.0) * nu_c * theta_e * theta_e * sin_th;
     const bool zero = (theta_e < kThetaEMin) || (nu > 1.0e12 * nu_s) || !(nu_s > 0.0);
@@ -152,7 +148,7 @@ __device__ __noinline__ double hotcross_cold(double w, double theta_e) {
  * The table look-up runs for every lane on clamped coordinates (its loads and exp10 cost the same for one lane
  * as for 32); the Thomson regime is a select, the out-of-table regimes a rarely taken call. */
 __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, double theta_e, double l_w,
-                                                  double l_theta, const double *hc_tab = nullptr) {
+                                                  double l_theta) {
     const bool thomson = w * theta_e < 1.0e-6;
     const bool in_table = !(w <= kHcMinW || w >= kHcMaxW || theta_e <= kHcMinT || theta_e >= kHcMaxT);
     const double kLog10E = 0.43429448190325182765;
@@ -162,20 +158,8 @@ __device__ __forceinline__ double hotcross_lkup_l(const GmParams &P, double w, d
      * (two integer min/max) keeps the loads in bounds for all other lanes, whose result is replaced below */
     const int i = max(0, min((int)qw, kHcNW - 1)), j = max(0, min((int)qt, kHcNT - 1));
     const double d_i = qw - i, d_j = qt - j;
-    const int off = i * (kHcNT + 1) + j;
-    double t00, t10, t01, t11;
-    if (hc_tab) {
-        t00 = hc_tab[off];
-        t10 = hc_tab[off + kHcNT + 1];
-        t01 = hc_tab[off + 1];
-        t11 = hc_tab[off + kHcNT + 2];
-    } else {
-        const double *t = P.hotcross + off;
-        t00 = __ldg(t);
-        t10 = __ldg(t + kHcNT + 1);
-        t01 = __ldg(t + 1);
-        t11 = __ldg(t + kHcNT + 2);
-    }
+    const double *t = P.hotcross + i * (kHcNT + 1) + j;
+    const double t00 = __ldg(t), t10 = __ldg(t + kHcNT + 1), t01 = __ldg(t + 1), t11 = __ldg(t + kHcNT + 2);
     const double l_cross = (1.0 - d_i) * (1.0 - d_j) * t00 + d_i * (1.0 - d_j) * t10 + (1.0 - d_i) * d_j * t01 +
                            d_i * d_j * t11;
     double sigma = fm::exp10_bounded(l_cross); /* log10 sigma table: finite entries */
@@ -205,10 +189,10 @@ __device__ __forceinline__ void fluid_frame(const GmParams &P, const double k[4]
 /* invariant scattering opacity nu * sigma_hot * n_e (reference alpha_inv_scatt / kappa_es,
  * radiation.cpp:103-107,142-146; the m_p factors cancel) */
 __device__ __forceinline__ double alpha_inv_scatt_l(const GmParams &P, double nu, double theta_e, double n_e,
-                                                    double l_nu, double l_theta, const double *hc_tab = nullptr) {
+                                                    double l_nu, double l_theta) {
     const double e_g = nu * (kHPL / (kME * kCL * kCL));
     const double kLnHOverMc2 = -46.263250426746548; /* ln(h / (m_e c^2)) in cgs: ln(e_g) = ln(nu) + this */
-    return nu * hotcross_lkup_l(P, e_g, theta_e, l_nu + kLnHOverMc2, l_theta, hc_tab) * n_e;
+    return nu * hotcross_lkup_l(P, e_g, theta_e, l_nu + kLnHOverMc2, l_theta) * n_e;
 }
 __device__ __forceinline__ double alpha_inv_scatt(const GmParams &P, double nu, double theta_e, double n_e) {
     return alpha_inv_scatt_l(P, nu, theta_e, n_e, fm::log_(fm::max_(nu, 1.0e-300)), fm::log_(fm::max_(theta_e, 1.0e-300)));
@@ -229,9 +213,8 @@ __device__ __forceinline__ double b_nu_inv(double nu, double theta_e) {
 /* invariant absorption opacity by Kirchhoff's law (reference alpha_inv_abs, radiation.cpp:109-118):
  * (j / nu^2) / (B + 1e-100) evaluated as j / (nu^2 (B + 1e-100)): one division, no denormal intermediate */
 __device__ __forceinline__ double alpha_inv_abs_sin_l(const GmParams &P, double nu, double theta_e, double n_e,
-                                                      double b, double sin_th, double l_theta,
-                                                      const double *k2_tab = nullptr) {
-    const double j = synch_sin_l(P, nu, n_e, theta_e, b, sin_th, l_theta, k2_tab);
+                                                      double b, double sin_th, double l_theta) {
+    const double j = synch_sin_l(P, nu, n_e, theta_e, b, sin_th, l_theta);
     return fm::div(j, nu * nu * (b_nu_inv(nu, theta_e) + 1.0e-100));
 }
 __device__ __forceinline__ double alpha_inv_abs_sin(const GmParams &P, double nu, double theta_e, double n_e,

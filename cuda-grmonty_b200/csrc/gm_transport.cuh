@@ -421,8 +421,7 @@ enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_S
  * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER).
  * Single exit, no early returns: the lanes of a warp must leave this function together (see advance). */
 __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const GeoPoint &q,
-                                               const double *snap, int snap_stride, Work &wk, const double *hc_tab,
-                                               const double *k2_tab) {
+                                               const double *snap, int snap_stride, Work &wk) {
     const GmParams &P = A.P;
     ++wk.interactions;
     /* q = geometry at the new position, already evaluated by the accepted push attempt */
@@ -442,8 +441,8 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
     const double te_e = outside ? 1.0 : f.theta_e, ne_e = outside ? 1.0 : f.n_e;
     const double b_e = outside ? 1.0 : f.b;
     const double l_nu = fm::log_(nu_e), l_theta = fm::log_(te_e);
-    const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta, hc_tab);
-    const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta, k2_tab);
+    const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta);
+    const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta);
     const double bf = bias_func(P, A.bias, te_e, L.w);
     double d_tau_scatt, d_tau_abs, bias;
     if (outside) {
@@ -528,8 +527,7 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
  * the middle of a halved step run phase B separately: ncu showed 15.6 of ~27 live threads per instruction.)
  * `record` tells whether a finished photon escaped through r > r_max (reference :1066-1068). */
 __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, unsigned int live, double *snap,
-                                              int snap_stride, Work &wk, bool &record, const double *hc_tab,
-                                              const double *k2_tab) {
+                                              int snap_stride, Work &wk, bool &record) {
     const GmParams &P = A.P;
     record = false;
     StepResult st = STEP_CONTINUE;
@@ -602,7 +600,7 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, u
             st = STEP_FINISHED;
         } else {
             if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos)
-                st = interact(A, L, q, snap, snap_stride, wk, hc_tab, k2_tab);
+                st = interact(A, L, q, snap, snap_stride, wk);
             if (st == STEP_CONTINUE) {
                 ++L.n_step;
                 if (L.n_step > kMaxNStep)
