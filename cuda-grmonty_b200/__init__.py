@@ -182,29 +182,11 @@ class Context:
                  gen_cap: int = 0, gen_budget: int = 0, gen_fine_from: int = 0, gen_fine_div: int = 0,
                  gen_ramp: int = 0, gen_budget_spread: int = 0):
         self.L = lib()
-        cfg = Config()
-        cfg.abi_version = 2
-        cfg.struct_size = C.sizeof(Config)
-        cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
-        for k in self.SCALARS:
-            setattr(cfg, k, float(model[k]))
-        self._keep = {}
-        nz = cfg.n0 * cfg.n1
-        for k in self.GRIDS:
-            a = _arr(model[k]).reshape(-1)
-            assert a.size == nz, k
-            self._keep[k] = a
-            setattr(cfg, k, _ptr(a))
-        for k, n in self.TABLES.items():
-            a = _arr(model[k]).reshape(-1)
-            assert a.size == n, k
-            self._keep[k] = a
-            setattr(cfg, k, _ptr(a))
-        cfg.seed, cfg.rank, cfg.world, cfg.device = seed, rank, world, device
-        cfg.threads_per_block, cfg.blocks_per_sm = threads_per_block, blocks_per_sm
-        cfg.queue_capacity, cfg.gen0, cfg.gen_cap, cfg.gen_budget = queue_capacity, gen0, gen_cap, gen_budget
-        cfg.gen_fine_from, cfg.gen_fine_div, cfg.gen_ramp = gen_fine_from, gen_fine_div, gen_ramp
-        cfg.gen_budget_spread = gen_budget_spread
+        cfg, self._keep = make_config(model, seed=seed, rank=rank, world=world, device=device,
+                                      threads_per_block=threads_per_block, blocks_per_sm=blocks_per_sm,
+                                      queue_capacity=queue_capacity, gen0=gen0, gen_cap=gen_cap, gen_budget=gen_budget,
+                                      gen_fine_from=gen_fine_from, gen_fine_div=gen_fine_div, gen_ramp=gen_ramp,
+                                      gen_budget_spread=gen_budget_spread)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))
@@ -361,6 +343,33 @@ class Context:
         self._ck(self.L.grmonty_b200_test_philox(self.h, C.c_int64(len(c)), _ptr(c, C.c_uint32),
                                                  _ptr(k, C.c_uint32), _ptr(out, C.c_uint32)))
         return out
+
+
+def make_config(model: dict, **options):
+    """grmonty_b200_config for `model` (see Context) + the arrays it points into (keep them alive as long as the
+    config is in use).  `options`: the integer fields of the config tail (seed, rank, world, device, gen0, ...)."""
+    cfg = Config()
+    cfg.abi_version = 2
+    cfg.struct_size = C.sizeof(Config)
+    cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
+    for k in Context.SCALARS:
+        setattr(cfg, k, float(model[k]))
+    keep = {}
+    nz = cfg.n0 * cfg.n1
+    for k in Context.GRIDS:
+        a = _arr(model[k]).reshape(-1)
+        assert a.size == nz, k
+        keep[k] = a
+        setattr(cfg, k, _ptr(a))
+    for k, n in Context.TABLES.items():
+        a = _arr(model[k]).reshape(-1)
+        assert a.size == n, k
+        keep[k] = a
+        setattr(cfg, k, _ptr(a))
+    cfg.world = 1
+    for k, v in options.items():
+        setattr(cfg, k, v)
+    return cfg, keep
 
 
 def hotcross_table(device: int = 0) -> np.ndarray:
