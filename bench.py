@@ -278,7 +278,11 @@ def main():
     clocks = sampler.stop() if sampler else None
     print(f"[bench rank {rank}] wall {1e3 * wall / args.steps:.1f} ms/step, kernels {kernel_ms / args.steps:.1f} ms/step, "
           f"generations {res['stats']['n_generations']}, attempts {res['stats']['n_push_attempts']}", file=sys.stderr)
-    local = torch.tensor([wall, kernel_ms, transport_ms, flops, float(launches)], dtype=torch.float64, device=f"cuda:{dev}")
+    # work units of the last step on this rank (every step repeats the same run): tracked photons, accepted geodesic
+    # steps, push attempts -- the honest work units next to the headline primaries/s
+    work_local = [float(res["stats"][k]) for k in ("n_tracked", "n_steps", "n_push_attempts")]
+    local = torch.tensor([wall, kernel_ms, transport_ms, flops, float(launches)] + work_local, dtype=torch.float64,
+                         device=f"cuda:{dev}")
     if dist:
         mx = local.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -286,8 +290,10 @@ def main():
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         wall, kernel_ms, transport_ms = mx[0].item(), mx[1].item(), mx[2].item()
         flops_all, launches_all = sm[3].item(), int(sm[4].item())
+        work_all = [sm[5].item(), sm[6].item(), sm[7].item()]
     else:
         flops_all, launches_all = flops, launches
+        work_all = work_local
     total = ctx.total_primaries()  # primaries of the whole job (all ranks) per step
     value = total * args.steps / wall
 
@@ -342,6 +348,9 @@ def main():
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "kernel": "transport_kernel", "kernel_ms_per_step": transport_ms / args.steps},
         "device_ms_per_step": kernel_ms / args.steps, "init_s": init_s,
+        "work_rates": {"tracked_photons_per_s": work_all[0] * args.steps / wall,
+                       "geodesic_steps_per_s": work_all[1] * args.steps / wall,
+                       "push_attempts_per_s": work_all[2] * args.steps / wall},
         "run": {"primaries_per_step": total, "recorded": res["recorded"], "scattered": res["scattered"],
                 "max_tau_scatt": res["max_tau_scatt"], **{k: res["stats"][k] for k in
                 ("n_tracked", "n_steps", "n_push_attempts", "n_interactions", "n_scatter_events", "n_generations",
