@@ -10,8 +10,10 @@
 #include "harm_model.hpp"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <chrono>
 #include <cmath>
@@ -124,16 +126,43 @@ struct Tokenizer {
  * the text parser and rewrites the cache.  Little-endian IEEE doubles, as everything else this library reads. */
 namespace {
 constexpr char kDumpCacheMagic[8] = {'G', 'M', 'B', '2', 'D', 'U', 'M', 'P'};
-constexpr uint32_t kDumpCacheVersion = 1;
+constexpr uint32_t kDumpCacheVersion = 2;
 struct DumpCacheHeader {
     char magic[8];
     uint32_t version, header_fields;
     uint64_t src_size;
     int64_t src_mtime_ns;
     uint64_t src_head_hash, n_zones;
+    uint64_t payload_hash; /* of the 8 grids, as written: a torn or bit-rotten cache is not loaded */
     double bias_norm;
     double header[26];
 };
+/* 64-bit words, multiply-xor in four independent lanes (the multiply latency would otherwise bound it to ~4 GB/s):
+ * an integrity check that runs near memory speed, not a cryptographic hash */
+uint64_t hash_words(uint64_t h, const double *p, size_t n) {
+    uint64_t a[4] = {h, h ^ 0x9E3779B97F4A7C15ull, h ^ 0xC2B2AE3D27D4EB4Full, h ^ 0x165667B19E3779F9ull};
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        uint64_t w[4];
+        std::memcpy(w, p + i, sizeof(w));
+        for (int l = 0; l < 4; ++l) {
+            a[l] = (a[l] ^ w[l]) * 0x9E3779B97F4A7C15ull;
+            a[l] ^= a[l] >> 29;
+        }
+    }
+    for (; i < n; ++i) {
+        uint64_t w;
+        std::memcpy(&w, p + i, sizeof(w));
+        a[0] = (a[0] ^ w) * 0x9E3779B97F4A7C15ull;
+        a[0] ^= a[0] >> 29;
+    }
+    uint64_t r = a[0];
+    for (int l = 1; l < 4; ++l) {
+        r = (r ^ a[l]) * 0x9E3779B97F4A7C15ull;
+        r ^= r >> 32;
+    }
+    return r;
+}
 uint64_t fnv1a(const char *p, size_t n) {
     uint64_t h = 1469598103934665603ull;
     for (size_t i = 0; i < n; ++i)
@@ -234,11 +263,19 @@ bool HARMModel::load_dump_cache(const std::string &filepath) {
         return false;
     std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
                                      &data_.u_3,   &data_.b_1, &data_.b_2, &data_.b_3};
-    for (auto *g : grids) {
-        g->resize(ch.n_zones);
-        if (!in.read(reinterpret_cast<char *>(g->data()), (std::streamsize)(ch.n_zones * sizeof(double))))
+    /* read into scratch first: a cache that fails its check must leave the model untouched */
+    std::vector<double> scratch[8];
+    uint64_t h = 0x243F6A8885A308D3ull;
+    for (auto &g : scratch) {
+        g.resize(ch.n_zones);
+        if (!in.read(reinterpret_cast<char *>(g.data()), (std::streamsize)(ch.n_zones * sizeof(double))))
             return false;
+        h = hash_words(h, g.data(), g.size());
     }
+    if (h != ch.payload_hash)
+        return false;
+    for (int k = 0; k < 8; ++k)
+        grids[k]->swap(scratch[k]);
     apply_header(ch.header, filepath);
     bias_norm_ = ch.bias_norm;
     return true;
@@ -247,7 +284,10 @@ bool HARMModel::load_dump_cache(const std::string &filepath) {
 void HARMModel::store_dump_cache(const std::string &filepath, const double h[26]) const {
     /* best effort: a read-only dump directory must not fail the run */
     try {
-        const std::string cpath = dump_cache_path(filepath), tmp = cpath + ".tmp";
+        /* the temporary name is unique per process and call: the ranks of a multi-GPU job all read the same dump */
+        static std::atomic<unsigned> serial{0};
+        const std::string cpath = dump_cache_path(filepath),
+                          tmp = cpath + ".tmp." + std::to_string((long long)getpid()) + "." + std::to_string(serial++);
         DumpCacheHeader ch{};
         std::memcpy(ch.magic, kDumpCacheMagic, 8);
         ch.version = kDumpCacheVersion;
@@ -259,13 +299,16 @@ void HARMModel::store_dump_cache(const std::string &filepath, const double h[26]
         ch.n_zones = data_.k_rho.size();
         ch.bias_norm = bias_norm_;
         std::memcpy(ch.header, h, sizeof(ch.header));
+        const std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
+                                               &data_.u_3,   &data_.b_1, &data_.b_2, &data_.b_3};
+        ch.payload_hash = 0x243F6A8885A308D3ull;
+        for (auto *g : grids)
+            ch.payload_hash = hash_words(ch.payload_hash, g->data(), g->size());
         {
             std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
             if (!out.is_open())
                 return;
             out.write(reinterpret_cast<const char *>(&ch), sizeof(ch));
-            const std::vector<double> *grids[8] = {&data_.k_rho, &data_.u,   &data_.u_1, &data_.u_2,
-                                                   &data_.u_3,   &data_.b_1, &data_.b_2, &data_.b_3};
             for (auto *g : grids)
                 out.write(reinterpret_cast<const char *>(g->data()), (std::streamsize)(g->size() * sizeof(double)));
             if (!out.good()) {
@@ -492,7 +535,9 @@ void HARMModel::store_hotcross_cache() const {
     if (hotcross_cache.empty())
         return;
     try {
-        const std::string tmp = hotcross_cache + ".tmp";
+        static std::atomic<unsigned> serial{0};
+        const std::string tmp =
+            hotcross_cache + ".tmp." + std::to_string((long long)getpid()) + "." + std::to_string(serial++);
         const HotcrossCacheHeader h = hotcross_cache_header();
         {
             std::ofstream out(tmp, std::ios::binary | std::ios::trunc);

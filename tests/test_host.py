@@ -188,7 +188,7 @@ def test_dump_cache_round_trip_is_bit_exact(tmp_path):
     ref.init_stage(0); b.init_stage(0)
     assert np.array_equal(ref.model_dict()["geom_det"], b.model_dict()["geom_det"])
     # size = header + 8 grids of raw doubles
-    assert os.path.getsize(p + ".b200cache") == 8 + 8 + 8 * 4 + 8 + 26 * 8 + 8 * 32 * 24 * 8
+    assert os.path.getsize(p + ".b200cache") == 8 + 8 + 8 * 5 + 8 + 26 * 8 + 8 * 32 * 24 * 8
 
 
 def test_dump_cache_is_invalidated_by_a_changed_dump_or_a_bad_cache(tmp_path):
@@ -215,7 +215,9 @@ def test_dump_cache_is_invalidated_by_a_changed_dump_or_a_bad_cache(tmp_path):
     assert m.read_from_cache()
     # truncated / foreign cache files fall back to the text parser
     raw = open(cpath, "rb").read()
-    for bad in (raw[:100], raw[:-8], b"XXXXXXXX" + raw[8:], b""):
+    flipped = bytearray(raw)
+    flipped[-5] ^= 0x10                           # one bit of the payload: right size, wrong content
+    for bad in (raw[:100], raw[:-8], b"XXXXXXXX" + raw[8:], b"", bytes(flipped)):
         with open(cpath, "wb") as f:
             f.write(bad)
         m.read_file(p)
@@ -270,3 +272,31 @@ def test_hotcross_table_disk_cache(host48, tmp_path):
         c.init_stage(1, 0)
         assert not c.hotcross_from_cache() and np.array_equal(c.model_dict()["hotcross"], want)
         assert open(path, "rb").read() == raw
+
+
+def _read_with_cache(path):
+    m = gm.HarmModel(1000, 4e19)
+    m.set_dump_cache(True)
+    m.read_file(path)
+    d = m.model_dict()
+    return float(d["bias_norm"]), float(np.asarray(d["b_3"]).sum()), float(np.asarray(d["k_rho"]).sum())
+
+
+def test_dump_cache_with_concurrent_readers(tmp_path):
+    """the ranks of a multi-GPU job read the same dump at the same time: each gets the right grids, the cache that
+    is left behind is valid and no temporary file survives"""
+    import multiprocessing as mp
+    p = str(tmp_path / "dump64.txt")
+    make_harm_dump.write_dump(p, *make_harm_dump.make_dump(n0=64, n1=64))
+    ref = gm.HarmModel(1000, 4e19)
+    ref.read_file(p)
+    d = ref.model_dict()
+    want = (float(d["bias_norm"]), float(np.asarray(d["b_3"]).sum()), float(np.asarray(d["k_rho"]).sum()))
+    with mp.get_context("spawn").Pool(6) as pool:
+        got = pool.map(_read_with_cache, [p] * 12)
+    assert all(g == want for g in got)
+    assert sorted(os.listdir(tmp_path)) == ["dump64.txt", "dump64.txt.b200cache"]
+    m = gm.HarmModel(1000, 4e19)
+    m.set_dump_cache(True)
+    m.read_file(p)
+    assert m.read_from_cache()
