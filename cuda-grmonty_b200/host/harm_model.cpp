@@ -498,11 +498,12 @@ struct HotcrossCacheHeader {
     char magic[8]; /* "GMB2HOTX" */
     uint32_t version, n_w, n_t, reserved;
     double min_w, max_w, min_t, max_t;
+    uint64_t payload_hash; /* of the table, filled in by store / checked by load */
 };
 HotcrossCacheHeader hotcross_cache_header() {
     HotcrossCacheHeader h{};
     std::memcpy(h.magic, "GMB2HOTX", 8);
-    h.version = 1;
+    h.version = 2;
     h.n_w = kHcNW;
     h.n_t = kHcNT;
     h.min_w = gm::kHcMinW;
@@ -525,10 +526,18 @@ bool HARMModel::load_hotcross_cache() {
     if ((size_t)in.tellg() != sizeof(got) + n * sizeof(double))
         return false;
     in.seekg(0);
-    if (!in.read(reinterpret_cast<char *>(&got), sizeof(got)) || std::memcmp(&got, &want, sizeof(got)) != 0)
+    if (!in.read(reinterpret_cast<char *>(&got), sizeof(got)))
         return false;
-    hotcross_.resize(n);
-    return (bool)in.read(reinterpret_cast<char *>(hotcross_.data()), (std::streamsize)(n * sizeof(double)));
+    const uint64_t stored_hash = got.payload_hash;
+    got.payload_hash = 0;
+    if (std::memcmp(&got, &want, sizeof(got)) != 0)
+        return false;
+    std::vector<double> table(n);
+    if (!in.read(reinterpret_cast<char *>(table.data()), (std::streamsize)(n * sizeof(double))) ||
+        hash_words(0x13198A2E03707344ull, table.data(), n) != stored_hash)
+        return false;
+    hotcross_.swap(table);
+    return true;
 }
 
 void HARMModel::store_hotcross_cache() const {
@@ -538,7 +547,8 @@ void HARMModel::store_hotcross_cache() const {
         static std::atomic<unsigned> serial{0};
         const std::string tmp =
             hotcross_cache + ".tmp." + std::to_string((long long)getpid()) + "." + std::to_string(serial++);
-        const HotcrossCacheHeader h = hotcross_cache_header();
+        HotcrossCacheHeader h = hotcross_cache_header();
+        h.payload_hash = hash_words(0x13198A2E03707344ull, hotcross_.data(), hotcross_.size());
         {
             std::ofstream out(tmp, std::ios::binary | std::ios::trunc);
             if (!out.is_open())

@@ -255,7 +255,7 @@ def test_hotcross_table_disk_cache(host48, tmp_path):
     a = gm.HarmModel(1000, 4e19)
     a.set_hotcross_cache(path)
     a.init_stage(1)
-    assert not a.hotcross_from_cache() and os.path.getsize(path) == 8 + 16 + 32 + 221 * 81 * 8
+    assert not a.hotcross_from_cache() and os.path.getsize(path) == 8 + 16 + 32 + 8 + 221 * 81 * 8
     want = host48.model_dict()["hotcross"]
     b = gm.HarmModel(1000, 4e19)
     b.set_hotcross_cache(path)
@@ -264,7 +264,10 @@ def test_hotcross_table_disk_cache(host48, tmp_path):
     assert b.hotcross_from_cache() and time.perf_counter() - t0 < 0.05
     assert np.array_equal(b.model_dict()["hotcross"], want) and np.array_equal(a.model_dict()["hotcross"], want)
     raw = open(path, "rb").read()
-    for bad in (raw[:-8], raw[:8] + b"\x07" + raw[9:], b"junk"):     # truncated, other version, foreign file
+    flipped = bytearray(raw)
+    flipped[-3] ^= 0x01
+    # truncated, other version, foreign file, one flipped payload bit
+    for bad in (raw[:-8], raw[:8] + b"\x07" + raw[9:], b"junk", bytes(flipped)):
         with open(path, "wb") as f:
             f.write(bad)
         c = gm.HarmModel(1000, 4e19)
