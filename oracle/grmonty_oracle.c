@@ -1494,6 +1494,7 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
     /* generations partition the global index range [0,total); statistics freeze at generation starts */
     int64_t g_start = 0;
     const int budget = m->budget > 0 ? m->budget : INT_MAX;
+    double lag_tau = m->acc_max_tau_scatt, lag_scatt = (double)m->acc_n_scatt, lag_rec = (double)m->acc_n_recorded;
     for (int64_t g = 0; g_start < last; ++g) {
         /* rank-local schedule, like the CUDA path (gm_api.cu grmonty_b200_run_range) */
         int64_t g_end = g_start + world * orc_generation_size(g_start / world, gen0, gen_cap, m->gen_fine_from,
@@ -1501,9 +1502,18 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
         const int64_t lo = g_start > first ? g_start : first, hi = g_end < last ? g_end : last;
         if (lo < hi) {
             if (m->stats_mode == ORC_STATS_FROZEN) {
-                m->bias_max_tau_scatt = m->acc_max_tau_scatt;
-                m->bias_n_scatt = (double)m->acc_n_scatt;
-                m->bias_n_recorded = (double)m->acc_n_recorded;
+                if (m->stats_lag > 0) { /* use the snapshot taken one generation ago, then take this one's */
+                    m->bias_max_tau_scatt = lag_tau;
+                    m->bias_n_scatt = lag_scatt;
+                    m->bias_n_recorded = lag_rec;
+                    lag_tau = m->acc_max_tau_scatt;
+                    lag_scatt = (double)m->acc_n_scatt;
+                    lag_rec = (double)m->acc_n_recorded;
+                } else {
+                    m->bias_max_tau_scatt = m->acc_max_tau_scatt;
+                    m->bias_n_scatt = (double)m->acc_n_scatt;
+                    m->bias_n_recorded = (double)m->acc_n_recorded;
+                }
             }
             m->budget = budget;
             /* Attempt budgets (same rule as the CUDA path, gm_api.cu run_batch): the t-th of the generation's

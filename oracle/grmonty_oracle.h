@@ -89,6 +89,10 @@ typedef struct orc_model {
     uint64_t n_created;
     /* diagnostics */
     uint64_t n_steps, n_push_attempts, n_interactions, n_scatter_events, n_tracked;
+    /* Study knob for the generation-overlap design: with stats_lag = 1 a generation uses
+     * the statistics that were frozen at the start of the PREVIOUS generation -- what a pipeline that starts
+     * generation g+1 while the tail of generation g still runs would see.  0 (default) is the CUDA path's schedule. */
+    int stats_lag;
 } orc_model;
 
 enum { ORC_STATS_FROZEN = 0, ORC_STATS_LIVE = 1 };

@@ -41,6 +41,7 @@ class OrcModel(C.Structure):
         ("n_created", C.c_uint64),
         ("n_steps", C.c_uint64), ("n_push_attempts", C.c_uint64), ("n_interactions", C.c_uint64),
         ("n_scatter_events", C.c_uint64), ("n_tracked", C.c_uint64),
+        ("stats_lag", C.c_int),
     ]
 
 
@@ -252,7 +253,8 @@ class Model:
         return self.flat(ph)
 
     def run(self, first=0, last=-1, rank=0, world=1, gen0=32, gen_cap=1 << 22, budget=384, fine_from=16384,
-            fine_div=6, ramp=8, spread=0):
+            fine_div=6, ramp=8, spread=0, stats_lag=0):
+        self.m.stats_lag = stats_lag
         self.m.budget = budget if self.m.stats_mode == 0 else 0
         self.m.gen_fine_from, self.m.gen_fine_div, self.m.gen_ramp = fine_from, fine_div, ramp
         self.m.gen_budget_spread = spread
