@@ -24,7 +24,9 @@ def one(args):
     model = {k: (v.item() if v.ndim == 0 else v) for k, v in d.items()}
     M = orc.Model(model, seed=seed)
     t0 = time.time()
-    M.run(0, -1, 0, 1, 32, 1 << 20, fine_div=fine_div, stats_lag=lag)
+    # BUDGET: attempts per lineage and generation before suspension (0 = never suspend, what an overlapping pipeline
+    # could afford); default = the CUDA path's 384
+    M.run(0, -1, 0, 1, 32, 1 << 20, fine_div=fine_div, stats_lag=lag, budget=int(os.environ.get("BUDGET", 384)))
     return dict(seed=seed, lag=lag, fine_div=fine_div, created=int(M.m.n_created), recorded=int(M.m.acc_n_recorded),
                 scattered=int(M.m.acc_n_scatt), lum=float(M.spectrum()[:, :, 1].sum()), s=time.time() - t0)
 
@@ -42,14 +44,15 @@ def main():
         hm.init()
         np.savez(MODEL, **{k: np.asarray(v) for k, v in hm.model_dict().items()})
     ref = np.load(os.path.join(ROOT, "tests", "golden", "spectrum_192_4e19.npz"))
-    jobs = [(1000 + s, lag, dv) for dv in divs for s in range(n_seeds) for lag in (0, 1)]
+    lags = [int(a) for a in os.environ.get("LAGS", "0,1").split(",")]
+    jobs = [(1000 + s, lag, dv) for dv in divs for s in range(n_seeds) for lag in lags]
     with mp.get_context("spawn").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
         rows = pool.map(one, jobs, chunksize=1)
     print(f"reference ensemble ({int(ref['seeds'])} runs): recorded {ref['recorded'].mean():.0f} +- "
           f"{ref['recorded'].std(ddof=1) / np.sqrt(len(ref['recorded'])):.0f}, scattered {ref['scattered'].mean():.0f} +- "
           f"{ref['scattered'].std(ddof=1) / np.sqrt(len(ref['scattered'])):.0f}")
     for dv in divs:
-        for lag in (0, 1):
+        for lag in lags:
             r = [x for x in rows if x["lag"] == lag and x["fine_div"] == dv]
             rec = np.array([x["recorded"] for x in r], float)
             sc = np.array([x["scattered"] for x in r], float)
@@ -58,6 +61,10 @@ def main():
                   f"({100 * (rec.mean() / ref['recorded'].mean() - 1):+.2f} % vs reference), scattered {sc.mean():.0f} +- "
                   f"{sc.std(ddof=1) / np.sqrt(n):.0f} ({100 * (sc.mean() / ref['scattered'].mean() - 1):+.2f} %), "
                   f"{np.mean([x['s'] for x in r]):.0f} s per run")
+        for x in rows:
+            print("   ", x)
+        if len(lags) < 2:
+            continue
         a = {x["seed"]: x for x in rows if x["lag"] == 0 and x["fine_div"] == dv}
         b = {x["seed"]: x for x in rows if x["lag"] == 1 and x["fine_div"] == dv}
         for key in ("recorded", "scattered", "lum"):
