@@ -192,3 +192,25 @@ def test_record(golden, orc_model):
         M.L.orc_record_super_photon(M.ptr, C.byref(ph))
     assert M.m.acc_n_recorded == golden["record_counters"][2]
     assert relerr(M.spectrum(), golden["record_spectrum"]) < 1e-13
+
+
+def test_stats_lag_knob(golden_model):
+    """orc.Model.run(stats_lag=1): every generation uses the bias statistics frozen one generation earlier (the study
+    knob for the generation-overlap design).  The first TWO generations then run on the initial statistics, so a run
+    a run of one generation cannot depend on it; a run of several generations does."""
+    from oracle import orc
+
+    def run(last, lag, gen0):
+        M = orc.Model(golden_model, seed=7)
+        M.m.acc_max_tau_scatt = float(golden_model["max_tau_scatt0"])
+        M.run(0, last, 0, 1, gen0, 1 << 20, stats_lag=lag)
+        return int(M.m.n_created), int(M.m.acc_n_recorded), int(M.m.acc_n_scatt), M.spectrum()[:, :, 1].sum()
+
+    # one generation: the lag cannot matter
+    assert run(300, 0, 512) == run(300, 1, 512)
+    # several generations: same primaries, different bias history
+    a, b = run(3000, 0, 64), run(3000, 1, 64)
+    assert a[0] == b[0] == 3000
+    assert a[1:] != b[1:]
+    # (with generations this small the lag keeps the initial statistics -- a far too small max tau -- in use for twice
+    # as many photons, so the counts differ by a large factor; tools/oracle_lag_study.py measures the real schedule)
