@@ -300,7 +300,7 @@ if __name__ == "__main__":
         gen_samplers()
     elif what == "spectrum":
         gen_spectrum()
-    elif what == "spectrum_1e6":
+    elif what in ("spectrum_1e6", "spectrum_1e6_more"):
         pass  # handled at the end of the file
     elif what == "spectrum_4e20":  # configs[3]: Compton-dominated regime, 8 seeds at photon_n = 2e4
         gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e20,))
@@ -313,14 +313,15 @@ if __name__ == "__main__":
         raise SystemExit(__doc__)
 
 
-def gen_spectrum_big(photon_n=1000000, seeds=6, mu=4e19):
+def gen_spectrum_big(photon_n=1000000, seeds=6, mu=4e19, first_seed=0, name="spectrum_192_4e19_1e6.npz"):
     """configs[1]: complete reference runs at the bench's photon_n (about 40 minutes per run on one core);
-    only counters and theta-summed spectra are kept (small fixture)."""
+    only counters and theta-summed spectra are kept (small fixture).  `first_seed` / `name`: further seeds of the same
+    ensemble into a second file (`spectrum_1e6_more`: seeds 506..513)."""
     tmp = tempfile.mkdtemp()
     dump = os.path.join(tmp, "dump192.txt")
     make_harm_dump.write_dump(dump, *make_harm_dump.make_dump())
     procs = []
-    for s in range(seeds):
+    for s in range(first_seed, first_seed + seeds):
         sb = os.path.join(tmp, f"spec_{s}.bin")
         cmd = [rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit", repr(mu),
                "--seed", str(500 + s), "--hotcross_cache", rh.HOTCROSS_CACHE, "--spectrum_bin", sb]
@@ -330,13 +331,13 @@ def gen_spectrum_big(photon_n=1000000, seeds=6, mu=4e19):
         o, _ = p.communicate()
         metas.append(json.loads(o.strip().splitlines()[-1]))
         specs.append(np.fromfile(sb).reshape(6, 200, 13)[:, :, [0, 1, 2, 3]])
-    np.savez_compressed(os.path.join(GOLD, "spectrum_192_4e19_1e6.npz"), photon_n=np.array(photon_n),
+    np.savez_compressed(os.path.join(GOLD, name), photon_n=np.array(photon_n), first_seed=np.array(500 + first_seed),
                         mass_unit=np.array(mu), created=np.array([m["created"] for m in metas]),
                         scattered=np.array([m["scattered"] for m in metas]),
                         recorded=np.array([m["recorded"] for m in metas]),
                         max_tau_scatt=np.array([m["max_tau_scatt"] for m in metas]),
                         run_s=np.array([m["run_s"] for m in metas]), spec=np.array(specs))
-    print("wrote spectrum_192_4e19_1e6.npz", [m["run_s"] for m in metas], file=sys.stderr)
+    print("wrote", name, [m["run_s"] for m in metas], file=sys.stderr)
 
 
 def gen_spectrum_file():
@@ -367,3 +368,7 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_fil
     gen_spectrum_file()
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6":
     gen_spectrum_big()  # configs[1] (the bench workload): 6 complete reference runs at photon_n = 1e6
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6_more":
+    # eight further seeds (506..513) of the configs[1] ensemble, kept in their own file until a GPU run has confirmed
+    # the parity test against the enlarged ensemble
+    gen_spectrum_big(seeds=8, first_seed=6, name="spectrum_192_4e19_1e6_more.npz")
