@@ -85,31 +85,83 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def run_reference_cpu(dump: str, photon_n: int, mass_unit: float, cores: int, seed0: int = 123) -> dict:
-    """`cores` concurrent single-threaded processes of the reference CPU build; rate = sum primaries / max wall of
-    run_simulation (table init excluded; the hot cross-section table is cached on disk by the harness)."""
+# End state of the scattering-bias statistics of complete runs on the bench dump (192x192, mass_unit 4e19):
+# photon_n -> (max_tau_scatt, scattered / created, recorded / created).  The bounded reference sample starts from
+# this state, so that it does the per-primary work of the full run it samples (the reference's bias divides by running
+# statistics, harm_model.cpp:1391-1404: a sample that starts from empty statistics scatters ~20 % more per primary
+# than the complete run).  photon_n = 1e6: medians of the reference's own 14 complete runs
+# (tests/golden/spectrum_192_4e19_1e6*.npz); the larger photon_n: complete runs of the CUDA path
+# (profiles/r2_end_states.txt; its statistics track the reference's, tests/test_gpu_spectrum.py), because a complete
+# reference run takes 1 - 5 hours per core there.
+REF_END_STATE = {1.0e6: (0.00256, 0.626, 0.752), 2.0e6: (0.00269, 0.604, 0.740), 4.0e6: (0.00260, 0.587, 0.732),
+                 8.0e6: (0.00281, 0.541, 0.707)}
+PRIMARIES_PER_PHOTON_N = 16.118  # created / photon_n on the bench dump: ln(nu_max / nu_min), harm_model.cpp:302
+
+
+def ref_end_state(photon_n: float):
+    """REF_END_STATE interpolated in ln(photon_n) (clamped)"""
+    ks = sorted(REF_END_STATE)
+    x = min(max(np.log(photon_n), np.log(ks[0])), np.log(ks[-1]))
+    return tuple(float(np.interp(x, np.log(ks), [REF_END_STATE[k][i] for k in ks])) for i in range(3))
+
+
+def run_reference_cpu(dump: str, photon_n: float, mass_unit: float, cores: int, target_s: float, seed0: int = 123,
+                      seeded: bool = True) -> dict:
+    """A bounded sample of the configs[1] workload on the reference CPU build: `cores` concurrent single-threaded
+    processes (the reference's CPU loop has no threading, harm_model.cpp:366-404), each running 1/thin of the primaries
+    of a run AT THE JOB'S OWN photon_n, spread over all zones like the run itself (oracle/ref_harness.cpp
+    ref_run_thinned: every call is a reference function), with the bias statistics started from the end state of a
+    complete run.  rate = sum of primaries / max wall of the transport loop (table init excluded like the reference's
+    own timer, harm_model.cpp:409; the hot cross-section table is cached on disk by the harness).
+    A process that dies or prints no result line is dropped and reported, not fatal."""
     from oracle import refharness as rh
+    total = PRIMARIES_PER_PHOTON_N * photon_n
+    thin = max(1.0, total / (6500.0 * max(1.0, target_s)))     # ~6.5 k primaries/s/core
     if os.path.exists(rh.CLI_PATH):
-        procs = [subprocess.Popen([rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit",
-                                   repr(mass_unit), "--seed", str(seed0 + i), "--hotcross_cache", rh.HOTCROSS_CACHE],
-                                  stdout=subprocess.PIPE, text=True) for i in range(cores)]
-        outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+        cmd0 = [rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(int(round(photon_n))), "--mass_unit",
+                repr(mass_unit), "--hotcross_cache", rh.HOTCROSS_CACHE, "--thin", repr(thin)]
+        if seeded:
+            mt, sc, rc = ref_end_state(photon_n)
+            cmd0 += ["--bias_stats", f"{mt!r},{int(sc * total)},{int(rc * total)}"]
+        procs = [subprocess.Popen(cmd0 + ["--seed", str(seed0 + i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                  text=True) for i in range(cores)]
+        outs, errors = [], []
+        for i, p in enumerate(procs):
+            so, se = p.communicate()
+            line = next((ln for ln in reversed(so.splitlines()) if ln.startswith('{"impl": "reference-cpu"')), None)
+            try:
+                if p.returncode != 0 or line is None:
+                    raise ValueError(f"rc={p.returncode}")
+                outs.append(json.loads(line))
+            except ValueError as e:
+                errors.append(f"process {i} (seed {seed0 + i}): {e}; stderr tail: {se.strip()[-160:]!r}")
+        if not outs:
+            raise RuntimeError("no reference process finished: " + "; ".join(errors)[:600])
         created = sum(o["created"] for o in outs)
         wall = max(o["run_s"] for o in outs)
-        return {"value": created / wall, "unit": "superphotons/s", "cores": cores, "kind": "reference",
-                "sample": f"{cores} processes x photon_n={photon_n} (reference CPU build, unmodified sources), "
-                          f"{created} primaries in {wall:.1f} s of run_simulation",
-                "recorded": sum(o["recorded"] for o in outs), "scattered": sum(o["scattered"] for o in outs),
-                "created": created, "seconds": wall}
+        res = {"value": created / wall, "unit": "superphotons/s", "cores": len(outs), "kind": "reference",
+               "sample": f"{len(outs)} processes x 1/{thin:.4g} of the primaries of a photon_n={photon_n:g} run "
+                         f"(reference CPU build, unmodified sources, all zones, weights of the full run, bias "
+                         f"statistics started from a complete run's end state), {created} primaries in "
+                         f"{wall:.1f} s of the transport loop",
+               "photon_n": photon_n, "thin": thin, "seeded_bias_stats": seeded,
+               "recorded": sum(o["recorded"] for o in outs), "scattered": sum(o["scattered"] for o in outs),
+               "created": created, "seconds": wall,
+               "scattered_per_created": sum(o["scattered"] for o in outs) / max(1, created)}
+        if errors:
+            res["dropped_processes"] = errors
+        return res
     # the reference build is not on this box: time the plain-C port instead (oracle/grmonty_oracle.c)
     import multiprocessing as mp
+    port_n = max(200, int(photon_n / thin))
     with mp.Pool(cores) as pool:
-        res = pool.map(_oracle_port_run, [(dump, photon_n, mass_unit, seed0 + i) for i in range(cores)])
+        res = pool.map(_oracle_port_run, [(dump, port_n, mass_unit, seed0 + i) for i in range(cores)])
     created = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     return {"value": created / wall, "unit": "superphotons/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} processes x photon_n={photon_n} (plain-C port of the reference algorithm)",
-            "created": created, "seconds": wall}
+            "sample": f"{cores} processes x complete runs at photon_n={port_n} (plain-C port of the reference "
+                      f"algorithm; NOT the job's photon_n: the reference build is absent on this box)",
+            "photon_n": port_n, "created": created, "seconds": wall}
 
 
 def run_reference_gpu(dump: str, photon_n: int, mass_unit: float) -> dict | None:
@@ -124,7 +176,7 @@ def run_reference_gpu(dump: str, photon_n: int, mass_unit: float) -> dict | None
         out = subprocess.run([exe, "--harm_dump_path", dump, "--photon_n", str(int(photon_n)), "--mass_unit",
                               repr(mass_unit), "--hotcross_cache", rh.HOTCROSS_CACHE], capture_output=True, text=True,
                              timeout=600)
-        o = json.loads(out.stdout.strip().splitlines()[-1])
+        o = json.loads(next(ln for ln in reversed(out.stdout.splitlines()) if ln.startswith('{"impl"')))
     except Exception as e:  # noqa: BLE001 -- a comparator that fails to run is reported, not fatal
         return {"error": str(e)[:200]}
     return {"value": o["created"] / o["run_s"], "unit": "superphotons/s", "kind": "reference GPU build (unmodified "
@@ -146,6 +198,26 @@ def _oracle_port_run(args):
     return int(M.m.n_created), time.time() - t0
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed ncu
+    summary of the transport kernel under profiles/ (written by tools/ncu_summary.py); (None, reason) if absent"""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_transport_ncu*.txt")),
+                   key=lambda f: (int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)), os.path.getmtime(f)))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for f in reversed(files):
+        tot, n = 0.0, 0
+        for ln in open(f):
+            m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.eE+-]+)\s+(\w+)", ln)
+            if m and m.group(3) in scale:
+                tot += float(m.group(2)) * scale[m.group(3)]
+                n += 1
+        if n == 2:
+            return tot, os.path.relpath(f, ROOT)
+    return None, "no ncu summary under profiles/"
+
+
 def flops_of(stats: dict) -> float:
     n_fluid = stats["n_interactions"]
     n_vac = max(0, stats["n_steps"] - n_fluid)
@@ -163,7 +235,8 @@ def main():
     ap.add_argument("--mass_unit", type=float, default=4.0e19)
     ap.add_argument("--n0", type=int, default=192)
     ap.add_argument("--n1", type=int, default=192)
-    ap.add_argument("--ref_photon_n", type=int, default=12000, help="photon_n of each reference CPU process")
+    ap.add_argument("--ref_seconds", type=float, default=0.0,
+                    help="CPU seconds per reference process and step (0: 150 / steps, clamped to 6 .. 25)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
 
@@ -171,7 +244,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     workload = (f"synthetic dump019-shaped HARM dump {args.n0}x{args.n1} (a=0.9375), mass_unit={args.mass_unit:g}, "
-                f"photon_n={args.photon_n:g} per GPU")
+                f"photon_n={args.photon_n:g} per GPU (job photon_n={args.photon_n * max(world, args.gpus):g})")
+    ref_seconds = args.ref_seconds if args.ref_seconds > 0 else min(25.0, max(6.0, 150.0 / max(1, args.steps)))
     config = {"workload": workload, "photon_n_per_gpu": args.photon_n, "mass_unit": args.mass_unit,
               "grid": [args.n0, args.n1], "sharding": f"photons x{world}, end-of-run allreduce",
               "l2": "per-step working set (photon pool, ~250 B x millions of photons) exceeds L2; no flush needed"}
@@ -182,15 +256,19 @@ def main():
             return
         dump = dump_path(args.n0, args.n1)
         cores = os.cpu_count() or 1
-        for _ in range(min(args.warmup, 1)):
-            run_reference_cpu(dump, max(200, args.ref_photon_n // 10), args.mass_unit, cores)
+        job_photon_n = args.photon_n * max(world, args.gpus)   # the job's photon_n: weak scaling, N x photon_n per GPU
+        for _ in range(min(args.warmup, 1)):                   # page cache / table file: one short pass is all a CPU needs
+            run_reference_cpu(dump, job_photon_n, args.mass_unit, cores, 1.0)
         t0 = time.time()
-        res = [run_reference_cpu(dump, args.ref_photon_n, args.mass_unit, cores, 123 + 1000 * s)
+        res = [run_reference_cpu(dump, job_photon_n, args.mass_unit, cores, ref_seconds, 123 + 1000 * s)
                for s in range(args.steps)]
         wall = time.time() - t0
         value = sum(r["created"] for r in res) / sum(r["seconds"] for r in res)
         cb = dict(res[-1])
         cb["value"] = value
+        dropped = [e for r in res for e in r.get("dropped_processes", [])]
+        if dropped:
+            cb["dropped_processes"] = dropped
         print(json.dumps({
             "impl": "reference", "metric": "superphotons/sec", "value": value, "unit": "superphotons/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -230,24 +308,21 @@ def main():
     model = hm.model_dict()
     ctx = gm.Context(model, seed=123, rank=rank, world=world, device=dev)
     fp64_peak = ctx.fp64_peak()
-    sp_ptr, cnt_ptr, mt_ptr = ctx.device_accumulators()
-
-    class DevArr:
-        def __init__(self, ptr, n, typestr):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
+    # the path's only collective is the product's own: grmonty_b200_allreduce on the device accumulators, over a
+    # communicator made through the same ABI (torch.distributed only ships the 128-byte NCCL id and does the timing
+    # barrier / max over ranks)
+    comm = None
     if dist:
-        t_spec = torch.as_tensor(DevArr(sp_ptr, 6 * 200 * 13, "<f8"), device=f"cuda:{dev}")
-        t_cnt = torch.as_tensor(DevArr(cnt_ptr, 3, "<i8"), device=f"cuda:{dev}")
-        t_mt = torch.as_tensor(DevArr(mt_ptr, 1, "<i8"), device=f"cuda:{dev}")  # bit pattern of a double >= 0
+        uid = torch.frombuffer(bytearray(gm.nccl_unique_id() if rank == 0 else bytes(gm.NCCL_ID_BYTES)),
+                               dtype=torch.uint8).to(f"cuda:{dev}")
+        dist.broadcast(uid, 0)
+        comm = gm.nccl_comm_init_rank(uid.cpu().numpy().tobytes(), rank, world, dev)
 
     def step():
         ctx.reset()
         ctx.run()
-        if dist:  # the path's only collective: end-of-run reduction of spectrum, counters and max tau
-            dist.all_reduce(t_spec, op=dist.ReduceOp.SUM)
-            dist.all_reduce(t_cnt, op=dist.ReduceOp.SUM)
-            dist.all_reduce(t_mt, op=dist.ReduceOp.MAX)
+        if comm:  # end-of-run reduction of spectrum, counters and max tau, in place on the device
+            ctx.allreduce(comm)
         return ctx.result()
 
     def sync():
@@ -298,24 +373,20 @@ def main():
     value = total * args.steps / wall
 
     # ---- e2e: through the HARMModel host API with host buffers (create + H2D + run + D2H + destroy per step)
-    hm.set_options(seed=123, rank=rank, world=world, device=dev)
+    # run_simulation = create (H2D) + run + grmonty_b200_allreduce (device, NCCL) + result (D2H) + destroy
+    hm.set_options(seed=123, rank=rank, world=world, device=dev, nccl_comm=comm)
     ctx.close()
     hm.run_simulation()  # warm-up
     sync()
     t0 = time.perf_counter()
-    t_run = t_red = 0.0
+    t_run = 0.0
     for _ in range(args.steps):
         ta = time.perf_counter()
         hm.run_simulation()
-        tb = time.perf_counter()
-        if dist:
-            spec = torch.from_numpy(hm.spectrum()).to(f"cuda:{dev}")
-            dist.all_reduce(spec, op=dist.ReduceOp.SUM)
-            hm.set_spectrum(spec.cpu().numpy())
-        t_run += tb - ta
-        t_red += time.perf_counter() - tb
+        t_run += time.perf_counter() - ta
     sync()
     e2e_wall = time.perf_counter() - t0
+    e2e_stats = hm.stats()
     if dist:
         tw = torch.tensor([e2e_wall], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
@@ -325,14 +396,18 @@ def main():
     d2h = 8 * (6 * 200 * 13 + 3 + 1 + 10)
     e2e = {"value": total * args.steps / e2e_wall, "unit": "superphotons/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
-           "rank0_run_ms": 1e3 * t_run / args.steps, "rank0_reduce_ms": 1e3 * t_red / args.steps,
-           "api": "HARMModel.run_simulation (create + run + result + destroy through the C ABI)"}
+           "rank0_run_ms": 1e3 * t_run / args.steps,
+           "recorded": int(e2e_stats["recorded"]), "created": int(e2e_stats["created"]),
+           "api": "HARMModel.run_simulation (create + run + allreduce + result + destroy through the C ABI)"}
 
+    if comm:
+        gm.nccl_comm_destroy(comm)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
     achieved = flops_all / world / (transport_ms * 1e-3) / 1e12  # per GPU
+    traffic, traffic_src = ncu_traffic()
     out = {
         "metric": "superphotons/sec", "value": value, "unit": "superphotons/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
@@ -340,10 +415,9 @@ def main():
         "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE transport launch (a 0.75 M-primary
-                     # generation) in the ncu --set full capture profiles/r1_transport_ncu_final.txt: 36 GB/s, i.e.
-                     # 0.5 % of HBM -- the path is FP64-latency bound, not traffic bound
-                     "traffic": 7.57e8,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE transport launch in the committed ncu
+                     # --set full capture (a full-size generation), read from the summary file itself
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": "DFMA micro-benchmark in this process (grmonty_b200_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 entry",
                      "kernel": "transport_kernel", "kernel_ms_per_step": transport_ms / args.steps},
@@ -358,7 +432,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        out["cpu_baseline"] = run_reference_cpu(dump, args.ref_photon_n, args.mass_unit, cores)
+        out["cpu_baseline"] = run_reference_cpu(dump, args.photon_n, args.mass_unit, cores, ref_seconds)
         ctx_gpu = run_reference_gpu(dump, args.photon_n, args.mass_unit)
         if ctx_gpu:
             out["ref_gpu_baseline"] = ctx_gpu

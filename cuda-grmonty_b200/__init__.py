@@ -25,11 +25,15 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 HOST = os.path.join(PKG_DIR, "host")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_CUDA = os.environ.get("GRMONTY_B200_LIB", os.path.join(PKG_DIR, "libgrmonty_b200.so"))
+# the same sources + the test-only batch exports of include/grmonty_b200_test.h (never loaded by the product path)
+LIB_CUDA_TEST = os.environ.get("GRMONTY_B200_TEST_LIB", os.path.join(PKG_DIR, "libgrmonty_b200_test.so"))
 LIB_HOST = os.path.join(PKG_DIR, "libgrmonty_b200_host.so")
 CLI = os.path.join(PKG_DIR, "grmonty_b200")
 
+# --cudart=shared: the CUDA runtime is taken from the process (torch's copy, or /usr/local/cuda/lib64 for the CLI)
+# instead of being linked statically into every artefact
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "--cudart=shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
 
 N_TH, N_E, N_F = 6, 200, 13
 SPEC_FIELDS = ["dn_dle", "de_dle", "nph", "nscatt", "x1i_av", "x2i_sq", "x3f_sq", "tau_abs", "tau_scatt",
@@ -49,14 +53,21 @@ def _sources(d: str, exts) -> list[str]:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a: cross-compiles without a GPU."""
-    srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".inc")) + [os.path.join(INCLUDE, "grmonty_b200.h")]
-    if force or _stale(LIB_CUDA, srcs):
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB_CUDA, os.path.join(CSRC, "gm_api.cu"), "-ldl"]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.check_call(cmd)
+    """nvcc -gencode arch=compute_100a,code=sm_100a: cross-compiles without a GPU.  Two libraries from the same
+    sources: the product library and the test superset (-DGRMONTY_B200_TEST_EXPORTS), compiled side by side."""
+    srcs = _sources(CSRC, (".cu", ".cuh", ".h", ".inc")) + [os.path.join(INCLUDE, "grmonty_b200.h"),
+                                                             os.path.join(INCLUDE, "grmonty_b200_test.h")]
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    procs = []
+    for target, extra in ((LIB_CUDA, []), (LIB_CUDA_TEST, ["-DGRMONTY_B200_TEST_EXPORTS"])):
+        if force or _stale(target, srcs):
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-shared", "-o", target, os.path.join(CSRC, "gm_api.cu"), "-ldl"]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
     return LIB_CUDA
 
 
@@ -116,9 +127,14 @@ class Stats(C.Structure):
 
 ABI_SYMBOLS = [
     "grmonty_b200_create", "grmonty_b200_total_primaries", "grmonty_b200_run_range", "grmonty_b200_run",
+    "grmonty_b200_set_progress",
     "grmonty_b200_allreduce", "grmonty_b200_device_accumulators", "grmonty_b200_result", "grmonty_b200_reset",
     "grmonty_b200_destroy", "grmonty_b200_trim_cache", "grmonty_b200_last_error", "grmonty_b200_fp64_peak", "grmonty_b200_hotcross_table",
-    "grmonty_b200_init_tables",
+    "grmonty_b200_init_tables", "grmonty_b200_nccl_unique_id", "grmonty_b200_nccl_comm_init_rank",
+    "grmonty_b200_nccl_comm_init_all", "grmonty_b200_nccl_comm_destroy",
+]
+# include/grmonty_b200_test.h: only in libgrmonty_b200_test.so
+TEST_ABI_SYMBOLS = [
     "grmonty_b200_test_geometry", "grmonty_b200_test_dkdlam_step", "grmonty_b200_test_push_photon",
     "grmonty_b200_test_trajectory", "grmonty_b200_test_fluid_params", "grmonty_b200_test_radiation",
     "grmonty_b200_test_hotcross", "grmonty_b200_test_angles", "grmonty_b200_test_tetrad",
@@ -126,20 +142,24 @@ ABI_SYMBOLS = [
     "grmonty_b200_test_track", "grmonty_b200_test_samplers", "grmonty_b200_test_philox",
 ]
 
-_lib = None
+# launch geometries (threads per block, blocks per SM) compiled into the library: csrc/gm_api.cu kVariants
+KERNEL_VARIANTS = [(256, 1), (64, 4), (128, 2), (128, 3), (384, 1), (512, 1)]
+
+_libs = {}
 
 
 class GrmontyError(RuntimeError):
     pass
 
 
-def lib():
-    """Load the CUDA library.  Raises if it is missing: there is no fallback implementation."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_CUDA):
-            raise GrmontyError(f"{LIB_CUDA} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
-        L = C.CDLL(LIB_CUDA)
+def lib(test_exports: bool = False):
+    """Load the CUDA library (test_exports: the superset library with the grmonty_b200_test_* entry points).
+    Raises if it is missing: there is no fallback implementation."""
+    if test_exports not in _libs:
+        path = LIB_CUDA_TEST if test_exports else LIB_CUDA
+        if not os.path.exists(path):
+            raise GrmontyError(f"{path} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
         L.grmonty_b200_last_error.restype = C.c_char_p
         L.grmonty_b200_last_error.argtypes = [C.c_void_p]
         L.grmonty_b200_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
@@ -155,8 +175,39 @@ def lib():
         L.grmonty_b200_fp64_peak.argtypes = [C.c_void_p, dp]
         L.grmonty_b200_hotcross_table.argtypes = [C.c_int, dp]
         L.grmonty_b200_init_tables.argtypes = [C.POINTER(Config), dp, dp, dp, dp, C.POINTER(C.c_double)]
-        _lib = L
-    return _lib
+        L.grmonty_b200_nccl_unique_id.argtypes = [C.c_void_p]
+        L.grmonty_b200_nccl_comm_init_rank.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.grmonty_b200_nccl_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]
+        L.grmonty_b200_nccl_comm_destroy.argtypes = [C.c_void_p]
+        _libs[test_exports] = L
+    return _libs[test_exports]
+
+
+NCCL_ID_BYTES = 128
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the product library (rank 0; ship the bytes to the other ranks)"""
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    rc = lib().grmonty_b200_nccl_unique_id(buf)
+    if rc != 0:
+        raise GrmontyError(f"grmonty_b200_nccl_unique_id failed ({rc}): {lib().grmonty_b200_last_error(None).decode()}")
+    return buf.raw
+
+
+def nccl_comm_init_rank(uid: bytes, rank: int, world: int, device: int) -> int:
+    """ncclCommInitRank through the product library; returns the ncclComm_t as an integer handle"""
+    comm = C.c_void_p()
+    buf = C.create_string_buffer(uid, NCCL_ID_BYTES)
+    rc = lib().grmonty_b200_nccl_comm_init_rank(C.byref(comm), buf, rank, world, device)
+    if rc != 0:
+        raise GrmontyError(f"grmonty_b200_nccl_comm_init_rank failed ({rc}): "
+                           f"{lib().grmonty_b200_last_error(None).decode()}")
+    return comm.value
+
+
+def nccl_comm_destroy(comm: int):
+    lib().grmonty_b200_nccl_comm_destroy(C.c_void_p(comm))
 
 
 def _arr(a, dtype=np.float64):
@@ -180,8 +231,9 @@ class Context:
     def __init__(self, model: dict, seed: int = 123, rank: int = 0, world: int = 1, device: int = 0,
                  threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
                  gen_cap: int = 0, gen_budget: int = 0, gen_fine_from: int = 0, gen_fine_div: int = 0,
-                 gen_ramp: int = 0, gen_budget_spread: int = 0):
-        self.L = lib()
+                 gen_ramp: int = 0, gen_budget_spread: int = 0, test_exports: bool = False):
+        # test_exports: create the context in libgrmonty_b200_test.so so that the t_* batch exports can be called on it
+        self.L = lib(test_exports)
         cfg, self._keep = make_config(model, seed=seed, rank=rank, world=world, device=device,
                                       threads_per_block=threads_per_block, blocks_per_sm=blocks_per_sm,
                                       queue_capacity=queue_capacity, gen0=gen0, gen_cap=gen_cap, gen_budget=gen_budget,
@@ -230,6 +282,10 @@ class Context:
         self._ck(self.L.grmonty_b200_result(self.h, _ptr(spec), counts, C.byref(mt), C.byref(st)))
         return dict(spectrum=spec, created=counts[0], scattered=counts[1], recorded=counts[2],
                     max_tau_scatt=mt.value, stats=st.as_dict())
+
+    def allreduce(self, nccl_comm: int, stream: int = 0):
+        """the path's only collective: sum / max of the device accumulators over the ranks of `nccl_comm`"""
+        self._ck(self.L.grmonty_b200_allreduce(self.h, C.c_void_p(nccl_comm), C.c_void_p(stream)))
 
     def device_accumulators(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -372,6 +428,11 @@ def make_config(model: dict, **options):
     return cfg, keep
 
 
+def _check_test_exports(L):
+    if not hasattr(L, "grmonty_b200_test_geometry"):
+        raise GrmontyError("this context lives in the product library; create it with test_exports=True")
+
+
 def hotcross_table(device: int = 0) -> np.ndarray:
     """[221][81] log10 hot cross-section table built on the GPU (grmonty_b200_hotcross_table)"""
     t = np.zeros((221, 81))
@@ -429,6 +490,8 @@ def host_lib():
         H.gmh_set_options.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                       C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_char_p]
         H.gmh_run_simulation.argtypes = [C.c_void_p]
+        H.gmh_set_gpus.argtypes = [C.c_void_p, C.c_int]
+        H.gmh_set_external_reduce.argtypes = [C.c_void_p, C.c_int]
         H.gmh_report_spectrum.argtypes = [C.c_void_p, C.c_char_p]
         H.gmh_report_spectrum_binary.argtypes = [C.c_void_p, C.c_char_p]
         H.gmh_set_dump_cache.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
@@ -533,6 +596,14 @@ class HarmModel:
         lib_path = (cuda_library or LIB_CUDA).encode()
         self.H.gmh_set_options(self.h, seed, rank, world, device, threads_per_block, blocks_per_sm, queue_capacity,
                                gen0, gen_cap, gen_budget, gen_fine_from, gen_fine_div, nccl_comm, lib_path)
+
+    def set_gpus(self, gpus: int):
+        """run_simulation() shards the run over GPUs 0..gpus-1 of this box (one host thread each) and all-reduces"""
+        self.H.gmh_set_gpus(self.h, int(gpus))
+
+    def set_external_reduce(self, on: bool = True):
+        """world > 1 without an NCCL communicator: the caller sums the per-rank spectra itself"""
+        self.H.gmh_set_external_reduce(self.h, int(bool(on)))
 
     def run_simulation(self):
         self._ck(self.H.gmh_run_simulation(self.h))

@@ -9,6 +9,7 @@
 #include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nccl.h> /* types and enum values only: the functions are resolved with dlopen, see nccl_api() */
 
 #include <algorithm>
 #include <chrono>
@@ -61,6 +62,7 @@ struct grmonty_b200_ctx {
     PhotonPool stage{}; /* staging pool: suspended photons between two batches */
     unsigned long long n_carry = 0; /* records in `stage` waiting for the next batch */
     unsigned long long h_qc[8] = {0}; /* staging of the queue counters written at each batch start */
+    TransportArgs h_args{};           /* staging of the device-global argument block (see run_batch) */
     /* issue order within a generation: primaries of long-lived zones first (see run_batch) */
     unsigned long long *d_zone_cost = nullptr; /* [2][n0] */
     std::vector<unsigned long long> h_zone_cost;
@@ -92,6 +94,8 @@ struct grmonty_b200_ctx {
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
     long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 6, gen_ramp = 8, gen_budget_spread = 0;
     grmonty_b200_stats stats{};
+    grmonty_b200_progress_fn progress = nullptr;
+    void *progress_user = nullptr;
     std::string err;
 };
 
@@ -147,9 +151,8 @@ struct Variant {
     TransportFn fn;
 };
 static const Variant kVariants[] = {
-    {128, 2, transport_kernel<128, 2>}, {128, 3, transport_kernel<128, 3>}, {128, 4, transport_kernel<128, 4>},
-    {256, 1, transport_kernel<256, 1>}, {64, 4, transport_kernel<64, 4>},   {384, 1, transport_kernel<384, 1>},
-    {512, 1, transport_kernel<512, 1>}, {192, 2, transport_kernel<192, 2>},
+    {128, 2, transport_kernel<128, 2>}, {128, 3, transport_kernel<128, 3>}, {256, 1, transport_kernel<256, 1>},
+    {64, 4, transport_kernel<64, 4>},   {384, 1, transport_kernel<384, 1>}, {512, 1, transport_kernel<512, 1>},
 };
 static const Variant *find_variant(int block, int min_blocks) {
     for (const Variant &v : kVariants)
@@ -300,7 +303,21 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             }
             if (!ctx->arena.base) {
                 void *b = nullptr;
-                CK(cudaMalloc(&b, need));
+                cudaError_t me = cudaMalloc(&b, need);
+                if (me == cudaErrorMemoryAllocation) {
+                    /* a parked block of another size may be what is in the way: free it and try once more */
+                    cudaGetLastError();
+                    std::lock_guard<std::mutex> lock(g_arena_mutex);
+                    for (size_t i = 0; i < g_arena_cache.size();)
+                        if (g_arena_cache[i].device == ctx->device) {
+                            cudaFree(g_arena_cache[i].base);
+                            g_arena_cache.erase(g_arena_cache.begin() + i);
+                        } else {
+                            ++i;
+                        }
+                    me = cudaMalloc(&b, need);
+                }
+                CK(me);
                 ctx->arena.device = ctx->device;
                 ctx->arena.base = static_cast<char *>(b);
                 ctx->arena.bytes = need;
@@ -341,7 +358,9 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-            if (max_persist > 0 && max_window > 0) {
+            /* GRMONTY_B200_L2_WINDOW=0 switches the window off (A/B evidence for the 1024^2 grid, profiles/) */
+            const char *l2_env = getenv("GRMONTY_B200_L2_WINDOW");
+            if (max_persist > 0 && max_window > 0 && !(l2_env && atoi(l2_env) == 0)) {
                 /* the persisting-L2 carve-out is a device-wide limit (and setting it synchronises the device):
                  * once per process and device, and only ever grown */
                 static std::mutex limit_mutex;
@@ -400,7 +419,11 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             }
             ctx->perm_mult = mult;
         }
-        CK(cudaMemcpy(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+        /* on the context's own (non-blocking) stream: a NULL-stream copy would not be ordered before the kernels
+         * that read the table */
+        CK(cudaMemcpyAsync(ctx->d_prefix, ctx->prefix.data(), (nz + 1) * sizeof(long long), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
 
         mark("zone kernel + prefix");
         /* ---- photon pool and stage queues ---- */
@@ -528,6 +551,9 @@ int grmonty_b200_reset(grmonty_b200_ctx *ctx) {
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     ctx->h_bias_valid = false;
     ctx->host_tracked = 0;
+    /* suspended photons of an aborted run must not enter the next one; used_ready / used_scatter / used_carry keep
+     * their values so that begin_batch still clears the stale queue entries */
+    ctx->n_carry = 0;
     return GRMONTY_B200_OK;
 }
 
@@ -592,9 +618,11 @@ static int begin_batch(grmonty_b200_ctx *ctx, long long count) {
 static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, long long count,
                      const GmBiasStats &bias, const DebugOut &dbg, bool preloaded, int budget) {
     const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
-    TransportArgs args;
+    /* the device-global copy of the arguments is written on the batch's own stream, ahead of the kernels that read it
+     * through A.self; the source lives in the context and is rewritten only after the batch's final synchronisation */
+    TransportArgs &args = ctx->h_args;
     fill_args(ctx, bias, dbg, budget, args);
-    CK(cudaMemcpy(ctx->d_args, &args, sizeof(args), cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ctx->d_args, &args, sizeof(args), cudaMemcpyHostToDevice, ctx->stream));
     float ms = 0.f;
     /* extra attempts for lineages that start early in the batch (see birth_kernel); none in the final drain */
     const long long spread = (budget != INT_MAX && ctx->gen_budget_spread > 0) ? ctx->gen_budget_spread : 0;
@@ -798,13 +826,17 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
                 do {
                     const long long n = std::min(count, chunk_cap);
                     rc = run_batch(ctx, f0, world, n, bias, nodbg, false, ctx->budget);
-                    if (rc)
+                    if (rc) {
+                        ctx->n_carry = 0; /* nothing of a failed run is carried into the next one */
                         return rc;
+                    }
                     created += (unsigned long long)n;
                     f0 += n * world;
                     count -= n;
                 } while (count > 0);
                 ++ctx->stats.n_generations;
+                if (ctx->progress)
+                    ctx->progress(ctx->progress_user, std::min<long long>(g_end, last), ctx->total);
             }
         }
         g_start = g_end;
@@ -815,19 +847,28 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
         if (rc)
             return rc;
         rc = run_batch(ctx, 0, 1, 0, bias, nodbg, false, INT_MAX);
-        if (rc)
+        if (rc) {
+            ctx->n_carry = 0;
             return rc;
+        }
         ++ctx->stats.n_generations;
     }
     /* counters[0] = created (host-side count; the reference counts primaries only, harm_model.cpp:395) */
-    unsigned long long c0;
-    CK(cudaMemcpy(&c0, ctx->d_counters, sizeof(c0), cudaMemcpyDeviceToHost));
-    c0 += created;
-    CK(cudaMemcpy(ctx->d_counters, &c0, sizeof(c0), cudaMemcpyHostToDevice));
+    add_u64_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_counters, created);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
     return GRMONTY_B200_OK;
 }
 
 int grmonty_b200_run(grmonty_b200_ctx *ctx) { return grmonty_b200_run_range(ctx, 0, -1); }
+
+int grmonty_b200_set_progress(grmonty_b200_ctx *ctx, grmonty_b200_progress_fn cb, void *user) {
+    if (!ctx)
+        return GRMONTY_B200_EINVAL;
+    ctx->progress = cb;
+    ctx->progress_user = user;
+    return GRMONTY_B200_OK;
+}
 
 int grmonty_b200_device_accumulators(grmonty_b200_ctx *ctx, void **spectrum, void **counters, void **max_tau) {
     if (!ctx)
@@ -843,7 +884,114 @@ int grmonty_b200_device_accumulators(grmonty_b200_ctx *ctx, void **spectrum, voi
 }
 
 /* NCCL is resolved at run time so that the library has no link-time NCCL dependency and, inside a process
- * that already loaded NCCL (e.g. PyTorch's bundled copy), uses that very copy. */
+ * that already loaded NCCL (e.g. PyTorch's bundled copy), uses that very copy.  Types and enum values come from
+ * <nccl.h> at build time. */
+struct NcclApi {
+    decltype(&ncclAllReduce) all_reduce = nullptr;
+    decltype(&ncclGroupStart) group_start = nullptr;
+    decltype(&ncclGroupEnd) group_end = nullptr;
+    decltype(&ncclGetUniqueId) get_unique_id = nullptr;
+    decltype(&ncclCommInitRank) comm_init_rank = nullptr;
+    decltype(&ncclCommInitAll) comm_init_all = nullptr;
+    decltype(&ncclCommDestroy) comm_destroy = nullptr;
+    decltype(&ncclGetErrorString) error_string = nullptr;
+    bool ok = false;
+    std::string why;
+};
+static const NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        /* a copy already in the process (same soname) is what dlopen returns; GRMONTY_B200_NCCL_LIB overrides */
+        std::vector<std::string> names;
+        if (const char *e = getenv("GRMONTY_B200_NCCL_LIB"))
+            names.push_back(e);
+        names.push_back("libnccl.so.2");
+        names.push_back("libnccl.so");
+        void *h = nullptr;
+        for (const std::string &n : names)
+            if ((h = dlopen(n.c_str(), RTLD_NOW | RTLD_GLOBAL)))
+                break;
+        if (!h) {
+            api.why = std::string("libnccl.so.2 not loadable: ") + dlerror();
+            return;
+        }
+#define GM_NCCL_SYM(field, name)                                     \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name)); \
+    if (!api.field) {                                                \
+        api.why = std::string(name) + " not found in libnccl";       \
+        return;                                                      \
+    }
+        GM_NCCL_SYM(all_reduce, "ncclAllReduce")
+        GM_NCCL_SYM(group_start, "ncclGroupStart")
+        GM_NCCL_SYM(group_end, "ncclGroupEnd")
+        GM_NCCL_SYM(get_unique_id, "ncclGetUniqueId")
+        GM_NCCL_SYM(comm_init_rank, "ncclCommInitRank")
+        GM_NCCL_SYM(comm_init_all, "ncclCommInitAll")
+        GM_NCCL_SYM(comm_destroy, "ncclCommDestroy")
+        GM_NCCL_SYM(error_string, "ncclGetErrorString")
+#undef GM_NCCL_SYM
+        api.ok = true;
+    });
+    return api;
+}
+
+int grmonty_b200_nccl_unique_id(void *id) {
+    static_assert(sizeof(ncclUniqueId) == GRMONTY_B200_NCCL_ID_BYTES, "ncclUniqueId size");
+    if (!id)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "null id");
+    const NcclApi &N = nccl_api();
+    if (!N.ok)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "%s", N.why.c_str());
+    const ncclResult_t r = N.get_unique_id(static_cast<ncclUniqueId *>(id));
+    if (r != ncclSuccess)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "ncclGetUniqueId: %s", N.error_string(r));
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_nccl_comm_init_rank(void **comm, const void *id, int rank, int world, int device) {
+    grmonty_b200_ctx *ctx = nullptr; /* for the CK macro */
+    if (!comm || !id || world < 1 || rank < 0 || rank >= world)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "bad communicator arguments (rank %d of %d)", rank, world);
+    const NcclApi &N = nccl_api();
+    if (!N.ok)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "%s", N.why.c_str());
+    CK(cudaSetDevice(device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t c = nullptr;
+    const ncclResult_t r = N.comm_init_rank(&c, world, uid, rank);
+    if (r != ncclSuccess)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "ncclCommInitRank: %s", N.error_string(r));
+    *comm = c;
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_nccl_comm_init_all(void **comms, int n_devices, const int *devices) {
+    if (!comms || n_devices < 1)
+        return fail(nullptr, GRMONTY_B200_EINVAL, "bad communicator arguments (%d devices)", n_devices);
+    const NcclApi &N = nccl_api();
+    if (!N.ok)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "%s", N.why.c_str());
+    std::vector<ncclComm_t> c((size_t)n_devices, nullptr);
+    const ncclResult_t r = N.comm_init_all(c.data(), n_devices, devices);
+    if (r != ncclSuccess)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "ncclCommInitAll: %s", N.error_string(r));
+    for (int i = 0; i < n_devices; ++i)
+        comms[i] = c[(size_t)i];
+    return GRMONTY_B200_OK;
+}
+
+int grmonty_b200_nccl_comm_destroy(void *comm) {
+    if (!comm)
+        return GRMONTY_B200_OK;
+    const NcclApi &N = nccl_api();
+    if (!N.ok)
+        return fail(nullptr, GRMONTY_B200_ENCCL, "%s", N.why.c_str());
+    const ncclResult_t r = N.comm_destroy(static_cast<ncclComm_t>(comm));
+    return r == ncclSuccess ? GRMONTY_B200_OK : fail(nullptr, GRMONTY_B200_ENCCL, "ncclCommDestroy: %s", N.error_string(r));
+}
+
 int grmonty_b200_allreduce(grmonty_b200_ctx *ctx, void *nccl_comm, void *cuda_stream) {
     if (!ctx)
         return GRMONTY_B200_EINVAL;
@@ -851,37 +999,24 @@ int grmonty_b200_allreduce(grmonty_b200_ctx *ctx, void *nccl_comm, void *cuda_st
         return GRMONTY_B200_OK;
     if (!nccl_comm)
         return fail(ctx, GRMONTY_B200_EINVAL, "world > 1 needs an ncclComm_t");
-    typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
-    typedef int (*GroupFn)(void);
-    static AllReduceFn all_reduce = nullptr;
-    static GroupFn group_start = nullptr, group_end = nullptr;
-    if (!all_reduce) {
-        void *h = dlopen(nullptr, RTLD_NOW);
-        all_reduce = h ? (AllReduceFn)dlsym(h, "ncclAllReduce") : nullptr;
-        if (!all_reduce) {
-            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-            if (!h)
-                h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-            all_reduce = h ? (AllReduceFn)dlsym(h, "ncclAllReduce") : nullptr;
-        }
-        if (!all_reduce)
-            return fail(ctx, GRMONTY_B200_ENCCL, "ncclAllReduce not found (libnccl.so.2 not loadable)");
-        group_start = (GroupFn)dlsym(h, "ncclGroupStart");
-        group_end = (GroupFn)dlsym(h, "ncclGroupEnd");
-    }
+    const NcclApi &N = nccl_api();
+    if (!N.ok)
+        return fail(ctx, GRMONTY_B200_ENCCL, "%s", N.why.c_str());
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
     const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
-    enum { kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 }; /* nccl.h ncclDataType_t / ncclRedOp_t */
-    if (group_start)
-        group_start();
-    int r0 = all_reduce(ctx->d_spectrum, ctx->d_spectrum, nspec, kNcclFloat64, kNcclSum, nccl_comm, s);
-    int r1 = all_reduce(ctx->d_counters, ctx->d_counters, 3, kNcclUint64, kNcclSum, nccl_comm, s);
-    /* non-negative doubles order like their bit patterns, so max over uint64 is max over the doubles */
-    int r2 = all_reduce(ctx->d_maxtau, ctx->d_maxtau, 1, kNcclUint64, kNcclMax, nccl_comm, s);
-    int r3 = group_end ? group_end() : 0;
-    if (r0 || r1 || r2 || r3)
-        return fail(ctx, GRMONTY_B200_ENCCL, "ncclAllReduce failed (%d %d %d %d)", r0, r1, r2, r3);
+    /* one group: spectrum (sum), the three counters (sum), max_tau_scatt (max; non-negative doubles order like their
+     * bit patterns, so a max over uint64 is the max over the doubles) */
+    ncclResult_t r[4];
+    N.group_start();
+    r[0] = N.all_reduce(ctx->d_spectrum, ctx->d_spectrum, nspec, ncclFloat64, ncclSum, comm, s);
+    r[1] = N.all_reduce(ctx->d_counters, ctx->d_counters, 3, ncclUint64, ncclSum, comm, s);
+    r[2] = N.all_reduce(ctx->d_maxtau, ctx->d_maxtau, 1, ncclUint64, ncclMax, comm, s);
+    r[3] = N.group_end();
+    for (ncclResult_t e : r)
+        if (e != ncclSuccess)
+            return fail(ctx, GRMONTY_B200_ENCCL, "ncclAllReduce failed: %s", N.error_string(e));
     CK(cudaStreamSynchronize(s));
     ctx->h_bias_valid = false;
     return GRMONTY_B200_OK;
@@ -1105,4 +1240,6 @@ int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops) {
 
 } /* extern "C" */
 
+#ifdef GRMONTY_B200_TEST_EXPORTS
 #include "gm_test_exports.inc"
+#endif

@@ -260,6 +260,9 @@ __global__ void carry_copy_kernel(PhotonPool dst, unsigned int dst0, PhotonPool 
         ready_entries[d] = d + 1u;
 }
 
+/* counters[0] += created, in stream order (the host counts primaries; harm_model.cpp:395) */
+__global__ void add_u64_kernel(unsigned long long *p, unsigned long long v) { *p += v; }
+
 /* ---- the persistent transport kernel ------------------------------------------------------------------- */
 extern __shared__ double gm_smem[];
 

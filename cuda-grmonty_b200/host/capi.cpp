@@ -92,6 +92,14 @@ int gmh_set_options(void *h, uint64_t seed, int rank, int world, int device, int
     o.cuda_library = cuda_library ? cuda_library : "";
     return 0;
 }
+int gmh_set_gpus(void *h, int gpus) {
+    static_cast<HARMModel *>(h)->options.gpus = gpus;
+    return 0;
+}
+int gmh_set_external_reduce(void *h, int on) {
+    static_cast<HARMModel *>(h)->options.external_reduce = on != 0;
+    return 0;
+}
 int gmh_run_simulation(void *h) { GUARD(static_cast<HARMModel *>(h)->run_simulation()) }
 int gmh_report_spectrum(void *h, const char *path) { GUARD(static_cast<HARMModel *>(h)->report_spectrum(path)) }
 

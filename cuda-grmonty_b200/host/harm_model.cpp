@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <barrier>
 #include <charconv>
 #include <chrono>
 #include <cmath>
@@ -22,6 +23,7 @@
 #include <cstring>
 #include <filesystem>
 #include <format>
+#include <functional>
 #include <fstream>
 #include <numbers>
 #include <stdexcept>
@@ -786,6 +788,9 @@ struct CudaLib {
     void *h = nullptr;
     decltype(&grmonty_b200_create) create = nullptr;
     decltype(&grmonty_b200_run) run = nullptr;
+    decltype(&grmonty_b200_set_progress) set_progress = nullptr;
+    decltype(&grmonty_b200_nccl_comm_init_all) nccl_comm_init_all = nullptr;
+    decltype(&grmonty_b200_nccl_comm_destroy) nccl_comm_destroy = nullptr;
     decltype(&grmonty_b200_allreduce) allreduce = nullptr;
     decltype(&grmonty_b200_result) result = nullptr;
     decltype(&grmonty_b200_destroy) destroy = nullptr;
@@ -823,7 +828,7 @@ CudaLib load_cuda_lib(const std::string &hint) {
     L.name = reinterpret_cast<decltype(L.name)>(dlsym(L.h, "grmonty_b200_" #name)); \
     if (!L.name)                                                                  \
         throw std::runtime_error("libgrmonty_b200.so lacks grmonty_b200_" #name);
-    SYM(create) SYM(run) SYM(allreduce) SYM(result) SYM(destroy) SYM(last_error) SYM(hotcross_table) SYM(init_tables)
+    SYM(create) SYM(run) SYM(set_progress) SYM(allreduce) SYM(nccl_comm_init_all) SYM(nccl_comm_destroy) SYM(result) SYM(destroy) SYM(last_error) SYM(hotcross_table) SYM(init_tables)
 #undef SYM
     return L;
 }
@@ -925,32 +930,63 @@ void HARMModel::init() {
     init_nint_table();
 }
 
-void HARMModel::run_simulation() {
+/* One GPU's share of the run through the C ABI: create -> run -> (all-reduce) -> result -> destroy.  `collect`: this
+ * rank's results (after the all-reduce: the whole job's) go into spectrum_ / stats_.  `sync` (multi-GPU in one
+ * process): every rank calls it once between the run and the collective and learns whether all ranks are still
+ * alive -- a rank that failed must not leave the others blocked inside NCCL. */
+void HARMModel::run_share(int rank, int world, int device, void *nccl_comm, bool collect,
+                          const std::function<bool(bool)> &sync) {
     const auto start = std::chrono::steady_clock::now();
-    log_info("Starting main loop");
     CudaLib L = load_cuda_lib(options.cuda_library);
-
     grmonty_b200_config cfg;
     fill_config(cfg);
+    cfg.rank = rank;
+    cfg.world = world;
+    cfg.device = device;
 
     grmonty_b200_ctx *ctx = nullptr;
+    std::string error;
     if (L.create(&ctx, &cfg) != 0)
-        throw std::runtime_error(std::string("grmonty_b200_create: ") + L.last_error(nullptr));
-    auto fail = [&](const char *what) {
-        const std::string msg = std::string(what) + ": " + L.last_error(ctx);
-        L.destroy(ctx);
-        throw std::runtime_error(msg);
-    };
-    if (L.run(ctx) != 0)
+        error = std::string("grmonty_b200_create: ") + L.last_error(nullptr);
+    auto fail = [&](const char *what) { error = std::string(what) + ": " + L.last_error(ctx); };
+    /* progress like the reference's once-a-second "Rate" line (harm_model.cpp:397-403): the library calls back after
+     * every generation; runs shorter than a second never print */
+    struct Progress {
+        std::chrono::steady_clock::time_point t_last;
+        int64_t done_last = 0;
+    } prog{start, 0};
+    if (error.empty() && options.progress && collect)
+        L.set_progress(ctx, [](void *user, int64_t done, int64_t total) {
+            auto *p = static_cast<Progress *>(user);
+            const auto now = std::chrono::steady_clock::now();
+            const double dt = std::chrono::duration<double>(now - p->t_last).count();
+            if (dt > 1.0) {
+                log_info("Rate %.2f ph/s, position %lld of %lld", (double)(done - p->done_last) / dt, (long long)done,
+                         (long long)total);
+                p->t_last = now;
+                p->done_last = done;
+            }
+        }, &prog);
+    if (error.empty() && L.run(ctx) != 0)
         fail("grmonty_b200_run");
-    if (options.world > 1 && options.nccl_comm && L.allreduce(ctx, options.nccl_comm, nullptr) != 0)
+    const bool all_ok = sync ? sync(error.empty()) : error.empty();
+    if (all_ok && world > 1 && nccl_comm && L.allreduce(ctx, nccl_comm, nullptr) != 0)
         fail("grmonty_b200_allreduce");
-    uint64_t counts[3];
-    grmonty_b200_stats st;
-    if (L.result(ctx, spectrum_.data(), counts, &stats_.max_tau_scatt, &st) != 0)
+    uint64_t counts[3] = {0, 0, 0};
+    grmonty_b200_stats st{};
+    double max_tau = 0.0;
+    if (all_ok && error.empty() && collect &&
+        L.result(ctx, spectrum_.data(), counts, &max_tau, &st) != 0)
         fail("grmonty_b200_result");
-    L.destroy(ctx);
-
+    if (ctx)
+        L.destroy(ctx);
+    if (!error.empty())
+        throw std::runtime_error(error);
+    if (!all_ok)
+        throw std::runtime_error("another rank of the job failed");
+    if (!collect)
+        return;
+    stats_.max_tau_scatt = max_tau;
     stats_.created = counts[0];
     stats_.scattered = counts[1];
     stats_.recorded = counts[2];
@@ -963,6 +999,52 @@ void HARMModel::run_simulation() {
     stats_.n_scatter_events = st.n_scatter_events;
     stats_.n_generations = st.n_generations;
     stats_.n_kernel_launches = st.n_kernel_launches;
+}
+
+void HARMModel::run_simulation() {
+    const auto start = std::chrono::steady_clock::now();
+    log_info("Starting main loop");
+    if (options.gpus > 1) {
+        /* one host thread per GPU of this box, each with its own context (rank g of options.gpus on device g) and a
+         * communicator from ncclCommInitAll; rank 0 collects the all-reduced result */
+        if (options.world != 1)
+            throw std::runtime_error("run_simulation: options.gpus > 1 and options.world > 1 are mutually exclusive");
+        CudaLib L = load_cuda_lib(options.cuda_library);
+        const int n = options.gpus;
+        std::vector<void *> comms((size_t)n, nullptr);
+        if (L.nccl_comm_init_all(comms.data(), n, nullptr) != 0)
+            throw std::runtime_error(std::string("grmonty_b200_nccl_comm_init_all: ") + L.last_error(nullptr));
+        std::atomic<int> n_failed{0};
+        std::barrier gate(n);
+        std::vector<std::string> errors((size_t)n);
+        std::vector<std::thread> pool;
+        for (int g = 0; g < n; ++g)
+            pool.emplace_back([&, g] {
+                try {
+                    run_share(g, n, g, comms[(size_t)g], g == 0, [&](bool ok) {
+                        if (!ok)
+                            n_failed.fetch_add(1);
+                        gate.arrive_and_wait();
+                        return n_failed.load() == 0;
+                    });
+                } catch (const std::exception &e) {
+                    errors[(size_t)g] = e.what();
+                }
+            });
+        for (auto &t : pool)
+            t.join();
+        for (void *c : comms)
+            L.nccl_comm_destroy(c);
+        for (int g = 0; g < n; ++g)
+            if (!errors[(size_t)g].empty() && errors[(size_t)g] != "another rank of the job failed")
+                throw std::runtime_error("GPU " + std::to_string(g) + ": " + errors[(size_t)g]);
+    } else {
+        if (options.world > 1 && !options.nccl_comm && !options.external_reduce)
+            throw std::runtime_error(
+                "run_simulation: world > 1 needs options.nccl_comm (or options.external_reduce if the caller sums the "
+                "per-rank spectra itself): refusing to report a rank-partial spectrum");
+        run_share(options.rank, options.world, options.device, options.nccl_comm, true, nullptr);
+    }
     stats_.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     /* same final summary as the reference (harm_model.cpp:409-413) */
     log_info("Final rate %.2f ph/s", stats_.created / stats_.seconds);

@@ -17,6 +17,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -58,10 +59,19 @@ constexpr int kNESamp = 200, kNint = 20000, kHcNW = 220, kHcNT = 80;
 struct RunOptions {
     uint64_t seed = 123; /* reference consts::rng_seed, main.cpp:49 */
     int rank = 0, world = 1, device = 0;
+    /* > 1: run_simulation() shards the run over devices 0..gpus-1 of this box, one host thread per GPU, and
+     * all-reduces the spectrum at the end (the command line's --gpus N); needs world == 1 */
+    int gpus = 1;
     int threads_per_block = 0, blocks_per_sm = 0;
     int64_t queue_capacity = 0, gen0 = 0, gen_cap = 0, gen_budget = 0, gen_fine_from = 0, gen_fine_div = 0;
     bool device_tables = false; /* init(): geometry / weight / nint / hot cross-section tables on the GPU */
-    void *nccl_comm = nullptr; /* ncclComm_t for world > 1 (optional: the caller may reduce by other means) */
+    void *nccl_comm = nullptr; /* ncclComm_t for world > 1: run_simulation() ends with grmonty_b200_allreduce */
+    /* world > 1 without a communicator is an error (the spectrum would silently be one rank's share) unless the
+     * caller states that it reduces the per-rank spectra itself */
+    bool external_reduce = false;
+    /* log a "Rate ... ph/s" line about once a second while the run is in progress (reference harm_model.cpp:397-403);
+     * only runs longer than a second ever print one */
+    bool progress = true;
     std::string cuda_library;  /* path of libgrmonty_b200.so; empty: $GRMONTY_B200_LIB or next to this library */
 };
 
@@ -140,6 +150,8 @@ private:
     void store_hotcross_cache() const;
 
     void fill_config(struct grmonty_b200_config &cfg) const;
+    void run_share(int rank, int world, int device, void *nccl_comm, bool collect,
+                   const std::function<bool(bool)> &sync);
     void apply_header(const double h[26], const std::string &filepath);
     bool load_dump_cache(const std::string &filepath);
     void store_dump_cache(const std::string &filepath, const double h[26]) const;

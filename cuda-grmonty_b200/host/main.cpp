@@ -2,7 +2,8 @@
  * main.cpp -- command-line driver with the reference's flags (cuda_grmonty/main.cpp:20-56):
  *     --photon_n N   --mass_unit M   --harm_dump_path FILE   --spectrum_path FILE   --verbosity LEVEL
  * Both `--flag value`, `--flag=value` and the single-dash spellings abseil accepts (`-photon_n 5000000`,
- * reference README.md:30) work.  Extra flags of the B200 path: --seed, --device, --init_threads, --dump_cache 0|1
+ * reference README.md:30) work.  Extra flags of the B200 path: --seed, --device, --gpus N (shard the run over N GPUs
+ * of this box, one host thread each, NCCL all-reduce of the spectrum at the end), --init_threads, --dump_cache 0|1
  * --device_tables 0|1 (build the init tables on the GPU), --hotcross_cache FILE (on-disk hot cross-section table),
  * (binary cache next to the dump, or under --dump_cache_dir), --spectrum_bin_path FILE (all 13 accumulated fields).
  * Call order is the reference's: HARMModel(photon_n, mass_unit) -> read_file -> init -> run_simulation ->
@@ -67,6 +68,8 @@ int main(int argc, char **argv) {
             model.options.seed = std::strtoull(v.c_str(), nullptr, 10);
         if (flag_value(argc, argv, "device", v))
             model.options.device = std::atoi(v.c_str());
+        if (flag_value(argc, argv, "gpus", v))
+            model.options.gpus = std::atoi(v.c_str());
         if (flag_value(argc, argv, "init_threads", v))
             model.init_threads = std::atoi(v.c_str());
         if (flag_value(argc, argv, "device_tables", v))

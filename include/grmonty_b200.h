@@ -40,7 +40,7 @@ extern "C" {
 #define GRMONTY_B200_HOTCROSS_N (221 * 81)
 #define GRMONTY_B200_TABLE_N 201
 #define GRMONTY_B200_NINT_N 20001
-#define GRMONTY_B200_PHOTON_FLAT 25  /* test exports: reference photon.hpp:19-36 order, n_scatt last */
+#define GRMONTY_B200_NCCL_ID_BYTES 128 /* sizeof(ncclUniqueId) */
 
 enum {
     GRMONTY_B200_OK = 0,
@@ -152,9 +152,27 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last);
 /* = run_range(ctx, 0, -1) */
 int grmonty_b200_run(grmonty_b200_ctx *ctx);
 
+/* Optional progress callback: called on the host thread of grmonty_b200_run / run_range after every generation with
+ * the number of positions of the processing sequence completed so far and their total (all ranks).  What the
+ * reference logs once a second from its CPU loop (harm_model.cpp:397-403).  cb == NULL: off. */
+typedef void (*grmonty_b200_progress_fn)(void *user, int64_t positions_done, int64_t positions_total);
+int grmonty_b200_set_progress(grmonty_b200_ctx *ctx, grmonty_b200_progress_fn cb, void *user);
+
 /* Sum the spectrum and counters (and max the scattering depth) over the ranks of `nccl_comm`
- * (an ncclComm_t passed as void*).  NCCL is resolved at run time (dlopen); world == 1: no-op. */
+ * (an ncclComm_t passed as void*), in place on the device accumulators: the path's only collective.
+ * NCCL is resolved at run time (dlopen; the copy already loaded in the process if there is one); world == 1: no-op. */
 int grmonty_b200_allreduce(grmonty_b200_ctx *ctx, void *nccl_comm, void *cuda_stream);
+
+/* Communicators for grmonty_b200_allreduce, for hosts that do not have an ncclComm_t of their own (the reference's
+ * GPU build is single-GPU and has none).  Thin forwards to ncclGetUniqueId / ncclCommInitRank / ncclCommInitAll /
+ * ncclCommDestroy of the NCCL copy grmonty_b200_allreduce uses:
+ *   one process per GPU (torchrun, MPI): rank 0 calls nccl_unique_id, ships the GRMONTY_B200_NCCL_ID_BYTES bytes to
+ *     the other ranks by whatever means the launcher offers, every rank calls nccl_comm_init_rank;
+ *   one process, one host thread per GPU (the command line's --gpus N): nccl_comm_init_all (devices == NULL: 0..n-1). */
+int grmonty_b200_nccl_unique_id(void *id);
+int grmonty_b200_nccl_comm_init_rank(void **comm, const void *id, int rank, int world, int device);
+int grmonty_b200_nccl_comm_init_all(void **comms, int n_devices, const int *devices);
+int grmonty_b200_nccl_comm_destroy(void *comm);
 
 /* Device pointers of the accumulators, for hosts that do the reduction with their own collective library
  * (e.g. torch.distributed):  spectrum: double[6*200*13]; counters: uint64[3] = created, scattered, recorded;
@@ -176,7 +194,7 @@ int grmonty_b200_reset(grmonty_b200_ctx *ctx);
 void grmonty_b200_destroy(grmonty_b200_ctx *ctx);
 void grmonty_b200_trim_cache(void);
 
-/* Message of the last error on this context (ctx == NULL: of the last failed create on this thread). */
+/* Message of the last error on this context (ctx == NULL: of the last failed context-free call on this thread). */
 const char *grmonty_b200_last_error(grmonty_b200_ctx *ctx);
 
 /* Hot Compton cross-section table on the device: table[221][81] = log10 of the numeric integral of reference
@@ -197,55 +215,6 @@ int grmonty_b200_init_tables(const grmonty_b200_config *cfg, double *geom_det, d
 /* FP64 FMA throughput micro-benchmark on the context's device (TFLOP/s, FMA = 2 flop); the roofline
  * denominator of this path (MEASURED_PEAKS.json has no FP64 entry). */
 int grmonty_b200_fp64_peak(grmonty_b200_ctx *ctx, double *tflops);
-
-/* ---- test-only batch exports (host arrays in / out), used by the parity tests --------------------------- */
-
-/* x: [n][4] -> gcov [n][16], gcon [n][16], conn [n][64] (full symmetric); any output may be NULL */
-int grmonty_b200_test_geometry(grmonty_b200_ctx *ctx, int64_t n, const double *x, double *gcov, double *gcon,
-                               double *conn);
-/* x,k: [n][4] -> dkdlam [n][4] (init_dkdlam), step [n] (step_size) */
-int grmonty_b200_test_dkdlam_step(grmonty_b200_ctx *ctx, int64_t n, const double *x, const double *k,
-                                  double *dkdlam, double *step);
-/* photons: [n][25] in/out, dl: [n]; one full push_photon (with halving) per photon; attempts [n] may be NULL */
-int grmonty_b200_test_push_photon(grmonty_b200_ctx *ctx, int64_t n, double *photons, const double *dl,
-                                  int32_t *attempts);
-/* photons: [n][25] in/out; nsteps x (step_size + push_photon) or until the photon leaves [r_h, 100];
- * every `stride` steps x[4] k[4] e_0_s are written to trace [n][nsteps/stride][9] (NaN where not reached) */
-int grmonty_b200_test_trajectory(grmonty_b200_ctx *ctx, int64_t n, double *photons, int32_t nsteps,
-                                 int32_t stride, double *trace);
-/* x: [n][4] -> out [n][19]: n_e theta_e b u_con[4] u_cov[4] b_con[4] b_cov[4] (zeros if outside the grid) */
-int grmonty_b200_test_fluid_params(grmonty_b200_ctx *ctx, int64_t n, const double *x, double *out);
-/* args: [n][5] = nu theta_e n_e b theta -> out [n][5] = alpha_inv_scatt alpha_inv_abs synch k2_eval f_eval */
-int grmonty_b200_test_radiation(grmonty_b200_ctx *ctx, int64_t n, const double *args, double *out);
-/* args: [n][2] = w theta_e -> sigma [n] (total_compton_cross_lkup) */
-int grmonty_b200_test_hotcross(grmonty_b200_ctx *ctx, int64_t n, const double *args, double *sigma);
-/* k: [n][4], fluid: [n][19] (layout of test_fluid_params) -> theta [n], nu [n] */
-int grmonty_b200_test_angles(grmonty_b200_ctx *ctx, int64_t n, const double *k, const double *fluid, double *theta,
-                             double *nu);
-/* in: [n][24] = gcov[16] u_con[4] trial[4] -> e_con [n][16], e_cov [n][16] */
-int grmonty_b200_test_tetrad(grmonty_b200_ctx *ctx, int64_t n, const double *in, double *e_con, double *e_cov);
-/* per-zone emission data computed at create: nz [n0*n1] (may be NULL), dn_max, num_to_gen */
-int grmonty_b200_test_zones(grmonty_b200_ctx *ctx, double *nz, double *dn_max, int64_t *num_to_gen);
-/* bias_func(theta_e, w) with the given frozen statistics; args [n][2] */
-int grmonty_b200_test_bias(grmonty_b200_ctx *ctx, int64_t n, const double *args, double max_tau_scatt,
-                           double n_scatt, double n_recorded, double *out);
-/* birth state of primaries idx[n] -> photons [n][25] (dkdlam zero), rng [n][4] = id0 id1 id2 ctr */
-int grmonty_b200_test_make_primaries(grmonty_b200_ctx *ctx, int64_t n, const int64_t *idx, double *photons,
-                                     uint32_t *rng);
-/* Track n given photons (and all their descendants) to completion with frozen bias statistics, recording into
- * the context's accumulators.  photons [n][25] in -> end state of each given photon out;
- * rng [n][4] = id0 id1 id2 ctr in/out; status [n]: bit0 recorded, bit1 scattered at least once, bit2 absorbed
- * or dropped. */
-int grmonty_b200_test_track(grmonty_b200_ctx *ctx, int64_t n, double *photons, uint32_t *rng,
-                            double max_tau_scatt, double n_scatt, double n_recorded, int32_t *status);
-/* which: 0 uniform, 3..6 chi_sq(dof), 10 sample_y(p0), 11 sample_mu(p0), 12 klein_nishina(p0), 13 thomson,
- * 20 electron gamma, 21 electron mu (p0 = k0, p1 = theta_e), 22 scattered energy ratio, 23 scattered cosine.
- * Stream of sample i: primary stream `first_stream + i`. */
-int grmonty_b200_test_samplers(grmonty_b200_ctx *ctx, int32_t which, double p0, double p1, int64_t first_stream,
-                               int64_t n, double *out);
-/* raw Philox4x32-10 blocks: ctr [n][4], key [n][2] -> out [n][4] */
-int grmonty_b200_test_philox(grmonty_b200_ctx *ctx, int64_t n, const uint32_t *ctr, const uint32_t *key,
-                             uint32_t *out);
 
 #ifdef __cplusplus
 }

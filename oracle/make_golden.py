@@ -300,14 +300,14 @@ if __name__ == "__main__":
         gen_samplers()
     elif what == "spectrum":
         gen_spectrum()
-    elif what in ("spectrum_1e6", "spectrum_1e6_more"):
+    elif what in ("spectrum_1e6", "spectrum_1e6_more", "spectrum_1e6_more2"):
         pass  # handled at the end of the file
     elif what == "spectrum_4e20":  # configs[3]: Compton-dominated regime, 8 seeds at photon_n = 2e4
         gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e20,))
     elif what == "spectrum_more":  # spectrum_more <first_seed> <n> [mass_unit]
         gen_spectrum(first_seed=int(sys.argv[2]), seeds=int(sys.argv[3]), merge=True,
                      mass_units=(float(sys.argv[4]),) if len(sys.argv) > 4 else (4e19,))
-    elif what == "spectrum_file":
+    elif what in ("spectrum_file", "spectrum_grid", "functions_grid"):
         pass  # handled at the end of the file
     else:
         raise SystemExit(__doc__)
@@ -372,3 +372,88 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6
     # eight further seeds (506..513) of the configs[1] ensemble, kept in their own file until a GPU run has confirmed
     # the parity test against the enlarged ensemble
     gen_spectrum_big(seeds=8, first_seed=6, name="spectrum_192_4e19_1e6_more.npz")
+
+
+def _grid_dump(n, tmp=None):
+    """the deterministic synthetic dump at n x n, cached under /tmp (0.9 GB of text at 1024^2)"""
+    p = os.path.join(tmp or tempfile.gettempdir(), f"grmonty_golden_dump_{n}.txt")
+    if not os.path.exists(p):
+        make_harm_dump.write_dump(p + ".tmp", *make_harm_dump.make_dump(n0=n, n1=n))
+        os.replace(p + ".tmp", p)
+    return p
+
+
+def gen_spectrum_grid(n=1024, photon_n=20000, seeds=8, first_seed=0, mu=4e19):
+    """BASELINE.json configs[4] grid (1024 x 1024): complete runs of the reference CLI at a photon_n one core finishes
+    in about a minute (the grid, not photon_n, is what this config is about: get_fluid_params / x_to_ij at another
+    stride, harm_model.cpp:595-671,1406-1434, and a 67 MB footprint).  Same fixture layout as gen_spectrum."""
+    dump = _grid_dump(n)
+    tmp = tempfile.mkdtemp()
+    procs = []
+    for s in range(first_seed, first_seed + seeds):
+        sb = os.path.join(tmp, f"spec_{s}.bin")
+        cmd = [rh.CLI_PATH, "--harm_dump_path", dump, "--photon_n", str(photon_n), "--mass_unit", repr(mu),
+               "--seed", str(700 + s), "--hotcross_cache", rh.HOTCROSS_CACHE, "--spectrum_bin", sb]
+        procs.append((subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True), sb))
+    specs, metas = [], []
+    for p, sb in procs:
+        o, _ = p.communicate()
+        metas.append(json.loads(o.strip().splitlines()[-1]))
+        specs.append(np.fromfile(sb).reshape(6, 200, 13))
+    specs = np.array(specs)
+    name = f"spectrum_{n}_{mu:.0e}.npz".replace("+", "")
+    out = dict(photon_n=np.array(photon_n), mass_unit=np.array(mu), grid=np.array([n, n]), first_seed=np.array(700),
+               created=np.array([m["created"] for m in metas]), scattered=np.array([m["scattered"] for m in metas]),
+               recorded=np.array([m["recorded"] for m in metas]), run_s=np.array([m["run_s"] for m in metas]),
+               max_tau_scatt=np.array([m["max_tau_scatt"] for m in metas]),
+               spec=specs[:, :, :, [0, 1, 2, 3, 7, 8]].astype(np.float64))
+    if first_seed > 0:  # further seeds of the same ensemble: append to the fixture
+        old = dict(np.load(os.path.join(GOLD, name)))
+        assert int(old["photon_n"]) == photon_n and len(old["created"]) == first_seed
+        for k in ("created", "scattered", "recorded", "run_s", "max_tau_scatt", "spec"):
+            out[k] = np.concatenate([old[k], out[k]])
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print("wrote", name, "rates", [m["created"] / m["run_s"] for m in metas], file=sys.stderr)
+
+
+def gen_functions_grid(n):
+    """Function-level vectors on the n x n bench dumps (192, 1024): get_fluid_params at random and edge points,
+    get_fluid_zone / init_zone on a sample of zones, plus the model scalars the lookups depend on.  The grids
+    themselves are not stored: tests rebuild the same dump with tools/make_harm_dump.py and load it through the
+    product's own loader."""
+    rng = np.random.default_rng(1000 + n)
+    R = rh.Ref(_grid_dump(n), 100000, 4e19, seed=123)
+    d = R.model_dict()
+    out = {k: np.asarray(d[k]) for k in ("x_start1", "x_start2", "dx1", "dx2", "x_stop1", "x_stop2", "bias_norm",
+                                          "n0", "n1")}
+    nf = 600
+    X = np.zeros((nf, 4))
+    X[:, 1] = rng.uniform(d["x_start1"] - 0.02, d["x_stop1"] + 0.05, nf)
+    X[:, 2] = rng.uniform(-0.01, 1.01, nf)
+    # cell edges, first / last half cells, the poles and the outer boundary (x_to_ij clamps, harm_model.cpp:1406-1434)
+    e1, e2 = d["x_start1"], d["x_stop1"]
+    X[:12, 1] = [e1 + 1e-9, e1 + 0.4 * d["dx1"], e2 - 1e-9, e2 - 0.3 * d["dx1"], 0.5 * (e1 + e2), e1 + 3.5 * d["dx1"],
+                 e1 + 0.5 * d["dx1"], e1 + 1.5 * d["dx1"] - 1e-13, e2 - 0.5 * d["dx1"], e1 + 100.5 * d["dx1"],
+                 e1 + (n - 1.5) * d["dx1"], e1 + (n // 2) * d["dx1"]]
+    X[:12, 2] = [0.5, 0.2 * d["dx2"], 1 - 0.2 * d["dx2"], 0.5, 1e-9, 1 - 1e-9, 0.5 * d["dx2"], 1.5 * d["dx2"],
+                 1 - 0.5 * d["dx2"], (n // 2) * d["dx2"], (n - 1.5) * d["dx2"], 0.5]
+    out["fluid_x"] = X
+    out["fluid_params"] = np.array([R.fluid_params(x) for x in X])
+    zi = rng.integers(0, n, 400)
+    zj = rng.integers(0, n, 400)
+    zi[:4], zj[:4] = [0, 0, n - 1, n - 1], [0, n - 1, 0, n - 1]
+    out["zone_ij"] = np.stack([zi, zj], 1)
+    out["zone_fluid"] = np.array([R.fluid_zone(int(i), int(j)) for i, j in zip(zi, zj)])
+    out["zone_init"] = np.array([R.init_zone(int(i), int(j)) for i, j in zip(zi, zj)])
+    np.savez_compressed(os.path.join(GOLD, f"functions_grid_{n}.npz"), **out)
+    print(f"wrote functions_grid_{n}.npz", file=sys.stderr)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_grid":
+    # spectrum_grid [n] [photon_n] [seeds] [first_seed]: configs[4] (1024 x 1024) reference ensemble
+    gen_spectrum_grid(*(int(float(v)) for v in sys.argv[2:6]))
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "functions_grid":
+    gen_functions_grid(int(sys.argv[2]))  # one model per process: functions_grid 192, then functions_grid 1024
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6_more2":
+    # six further seeds (514..519): 20 complete reference runs at the bench's photon_n in total
+    gen_spectrum_big(seeds=6, first_seed=14, name="spectrum_192_4e19_1e6_more2.npz")

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <chrono>
+#include <cmath>
 #include <fstream>
 #include <memory>
 #include <string>
@@ -494,6 +495,59 @@ double ref_run_simulation() {
     std::chrono::duration<double> dt = std::chrono::steady_clock::now() - t0;
     return dt.count();
 }
+/* A BOUNDED SAMPLE of a run at the model's own photon_n (bench.py --impl reference / cpu_baseline): every zone is
+ * visited in the reference's order and handled exactly as the reference's CPU loop handles it -- init_zone +
+ * stochastic rounding (get_zone, harm_model.cpp:673-704), sample_zone_photon per primary (make_super_photon
+ * :794-811), the InitPhoton -> Photon copy and track_super_photon (run_simulation :366-393) -- except that the
+ * zone's expected photon count is divided by `thin` before the rounding, so the sample holds 1/thin of the run's
+ * primaries spread over all zones like the run itself.  Weights and tables are those of the full-photon_n run;
+ * nothing is re-implemented, every call is a reference function.  Returns wall seconds; out[0] = primaries created,
+ * out[1] = zones that emitted. */
+double ref_run_thinned(double thin, uint64_t *out) {
+    const harm::Header &h = FIELD(D_header);
+    const int n0 = static_cast<int>(h.n[0]), n1 = static_cast<int>(h.n[1]);
+    uint64_t created = 0, emitting = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n0; ++i)
+        for (int j = 0; j < n1; ++j) {
+            auto [d_full, dn_max] = CALL(T_init_zone)(i, j);
+            const double d_num = d_full / thin;
+            int num = static_cast<int>(d_num);
+            if (std::fmod(d_num, 1.0) > monty_rand::uniform())
+                ++num;
+            if (num > 0)
+                ++emitting;
+            harm::Zone z{.x_1 = i, .x_2 = j, .num_to_gen = num, .dn_max = dn_max, .first_photon = true};
+            for (; z.num_to_gen > 0; --z.num_to_gen) {
+                photon::InitPhoton ip = CALL(T_sample_zone)(z);
+                photon::Photon ph;
+                for (int m = 0; m < consts::n_dim; ++m) {
+                    ph.x[m] = ip.x[m];
+                    ph.k[m] = ip.k[m];
+                }
+                ph.w = ip.w;
+                ph.e = ip.e;
+                ph.e_0 = ip.e_0;
+                ph.e_0_s = ip.e;
+                ph.l = ip.l;
+                ph.tau_scatt = 0.0;
+                ph.tau_abs = 0.0;
+                ph.x1i = ip.x[1];
+                ph.x2i = ip.x[2];
+                ph.n_e_0 = ip.n_e_0;
+                ph.b_0 = ip.b_0;
+                ph.theta_e_0 = ip.theta_e_0;
+                ph.n_scatt = 0;
+                CALL(T_track)(ph);
+                ++created;
+            }
+        }
+    FIELD(D_ncreated) += created;
+    out[0] = created;
+    out[1] = emitting;
+    std::chrono::duration<double> dt = std::chrono::steady_clock::now() - t0;
+    return dt.count();
+}
 int ref_report_spectrum(const char *path) {
     MM.report_spectrum(path);
     return 0;
@@ -525,6 +579,15 @@ int main(int argc, char **argv) {
     std::string cache = arg_value(argc, argv, "hotcross_cache", "");
     int seed = std::atoi(arg_value(argc, argv, "seed", "123"));
     int verbose = std::atoi(arg_value(argc, argv, "verbose", "0"));
+    /* --thin T: a bounded sample of the run, 1/T of its primaries over all zones (ref_run_thinned) */
+    double thin = std::atof(arg_value(argc, argv, "thin", "0"));
+    /* --bias_stats MAX_TAU,N_SCATT,N_REC: start the running bias statistics (harm_model.cpp:1296-1320,1391-1404) from
+     * the end state of a complete run instead of from an empty one -- a bounded sample then does the per-primary work
+     * of the full run's late phase.  The two counts are subtracted again from the counters printed below. */
+    std::string bias_stats = arg_value(argc, argv, "bias_stats", "");
+    double bs_tau = 0.0;
+    unsigned long long bs_scatt = 0, bs_rec = 0;
+    const bool seeded = std::sscanf(bias_stats.c_str(), "%lf,%llu,%llu", &bs_tau, &bs_scatt, &bs_rec) == 3;
     ref_create(photon_n, mass_unit, verbose);
     if (ref_read_file(dump.c_str()) != 0)
         return 1;
@@ -532,11 +595,18 @@ int main(int argc, char **argv) {
     ref_init(cache.c_str());
     std::chrono::duration<double> t_init = std::chrono::steady_clock::now() - t0;
     ref_rng_init(seed);
-    double t_run = ref_run_simulation();
+    if (seeded)
+        ref_set_bias_stats(bs_tau, bs_scatt, bs_rec);
+    uint64_t thin_out[2] = {0, 0};
+    double t_run = thin > 0.0 ? ref_run_thinned(thin, thin_out) : ref_run_simulation();
     if (!spec.empty())
         ref_report_spectrum(spec.c_str());
     uint64_t c[3];
     ref_get_counters(c);
+    if (seeded) {
+        c[1] -= bs_scatt;
+        c[2] -= bs_rec;
+    }
     double sc[5];
     ref_get_scalars(sc);
     if (!spec_bin.empty()) {
@@ -547,9 +617,9 @@ int main(int argc, char **argv) {
     }
     std::printf("{\"impl\": \"reference-cpu\", \"photon_n\": %d, \"mass_unit\": %.17g, \"seed\": %d, "
                 "\"created\": %llu, \"scattered\": %llu, \"recorded\": %llu, \"max_tau_scatt\": %.17g, "
-                "\"init_s\": %.6f, \"run_s\": %.6f}\n",
+                "\"init_s\": %.6f, \"run_s\": %.6f, \"thin\": %g, \"seeded_bias_stats\": %d}\n",
                 photon_n, mass_unit, seed, (unsigned long long)c[0], (unsigned long long)c[1],
-                (unsigned long long)c[2], sc[2], t_init.count(), t_run);
+                (unsigned long long)c[2], sc[2], t_init.count(), t_run, thin, seeded ? 1 : 0);
     return 0;
 }
 #endif

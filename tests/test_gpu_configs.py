@@ -3,10 +3,11 @@
 configs[3]  M_unit = 4e20 (Compton-dominated regime): ensemble of CUDA runs against complete runs of the UNMODIFIED
             reference CPU build (tests/golden/spectrum_192_4e20.npz: 8 seeds at photon_n = 2e4, written by
             `oracle/make_golden.py spectrum_4e20`).
-configs[4]  1024 x 1024 grid (67 MB of primitives, the L2 / HBM stress case): the CPU reference cannot be run at
-            this size inside a test, so the checks are size-independent properties -- every recorded photon is in
-            the spectrum exactly once, counters are consistent, and the luminosity of the analytic torus profile
-            agrees between the 192^2 and the 1024^2 discretisation.
+configs[4]  1024 x 1024 grid (67 MB of primitives, the L2 / HBM stress case): ensemble of CUDA runs against
+            complete runs of the UNMODIFIED reference CPU build on the same 1024^2 dump
+            (tests/golden/spectrum_1024_4e19.npz: 32 seeds at photon_n = 2e4, `oracle/make_golden.py spectrum_grid`;
+            the function-level vectors on that grid are in tests/test_grids.py), plus size-independent properties:
+            every recorded photon is in the spectrum exactly once, counters are consistent.
 """
 import os
 
@@ -79,6 +80,50 @@ def test_compton_dominated_vs_reference(tmp_path):
     chi2 = float((z ** 2).mean())
     print("bins", int(mask.sum()), "chi2/bin", chi2, "max |z|", float(np.abs(z).max()))
     assert chi2 < 2.0 and np.abs(z).max() < 7.0   # E[z^2] ~ 1.4 with variances from 8 + 16 samples
+
+
+def ensemble_vs_reference(runs, ref, min_photons_per_bin):
+    """relative differences of ensemble means (CUDA vs reference fixture) with their standard errors, and the per-bin
+    chi-square of nu L_nu over the bins holding enough superphotons"""
+    rep = {}
+    g_lum = np.array([r["spectrum"][:, :, 1].sum() for r in runs])
+    r_lum = ref["spec"][..., 1].sum(axis=(1, 2))
+    for name, g, rr in (("luminosity", g_lum, r_lum),
+                        ("recorded", np.array([r["recorded"] for r in runs], float), ref["recorded"].astype(float)),
+                        ("scattered", np.array([r["scattered"] for r in runs], float), ref["scattered"].astype(float))):
+        d = g.mean() / rr.mean() - 1
+        se = np.hypot(g.std(ddof=1) / np.sqrt(len(g)) / g.mean(), rr.std(ddof=1) / np.sqrt(len(rr)) / rr.mean())
+        rep[name] = (float(d), float(se))
+    gs = np.array([r["spectrum"][:, :, 1] for r in runs])
+    rs = ref["spec"][..., 1]
+    mask = ref["spec"][..., 2].mean(0) >= min_photons_per_bin
+    var = gs.var(0, ddof=1) / len(gs) + rs.var(0, ddof=1) / len(rs)
+    z = (gs.mean(0) - rs.mean(0))[mask] / np.sqrt(var[mask])
+    rep["bins"] = int(mask.sum())
+    rep["chi2_per_bin"] = float((z ** 2).mean())
+    rep["max_abs_z"] = float(np.abs(z).max())
+    rep["l1"] = float(np.abs(gs.mean(0) - rs.mean(0))[mask].sum() / rs.mean(0)[mask].sum())
+    return rep
+
+
+def test_large_grid_vs_reference(tmp_path):
+    """configs[4]: the CUDA path on the 1024 x 1024 dump against the reference CPU build on the same dump"""
+    ref = dict(np.load(os.path.join(ROOT, "tests", "golden", "spectrum_1024_4e19.npz")))
+    assert list(ref["grid"]) == [1024, 1024] and len(ref["recorded"]) >= 8
+    model = model_for(str(tmp_path), 1024, int(ref["photon_n"]), float(ref["mass_unit"]))
+    runs = run_seeds(model, range(3000, 3032))
+    for r in runs:
+        consistent(r)
+    assert abs(np.mean([r["created"] for r in runs]) / ref["created"].mean() - 1) < 1e-3
+    rep = ensemble_vs_reference(runs, ref, 300)
+    print(rep)
+    for name in ("luminosity", "recorded", "scattered"):
+        d, se = rep[name]
+        assert se < 0.006, (name, se)
+        assert abs(d) < 0.01 + 2 * se, (name, d, se)      # photon_n is small here: the bar plus the ensemble noise
+    assert rep["bins"] > 100
+    assert rep["chi2_per_bin"] < 1.6 and rep["max_abs_z"] < 6.0
+    assert rep["l1"] < 0.03                                # ~300 photons per bin and run: noisier than configs[0]
 
 
 def test_large_grid_properties(tmp_path):

@@ -1,5 +1,5 @@
 """Two-GPU test of the path's only collective through the C ABI: grmonty_b200_allreduce with a real ncclComm_t
-(created here with ctypes on the NCCL library torch bundles).  Skipped on boxes with fewer than two GPUs.
+(created through grmonty_b200_nccl_unique_id / grmonty_b200_nccl_comm_init_rank of the same ABI).  Skipped on boxes with fewer than two GPUs.
 Checks: the two ranks' shares add up to the single-GPU run's primaries, after the all-reduce both ranks hold the same
 spectrum and counters, and those equal the sum of the per-rank results read before the reduction."""
 import os
@@ -23,28 +23,18 @@ WORKER = textwrap.dedent("""
     rank, world, port, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=port, RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)       # only to hand the NCCL unique id around
-    nccl = C.CDLL(glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib",
-                                         "libnccl.so.2"))[0], mode=C.RTLD_GLOBAL)
-    class UniqueId(C.Structure):
-        _fields_ = [("internal", C.c_char * 128)]
-    uid = UniqueId()
-    if rank == 0:
-        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
-    t = torch.frombuffer(bytearray(C.string_at(C.byref(uid), 128) if rank == 0 else bytes(128)),
-                         dtype=torch.uint8).clone()
+    # the communicator comes from the product ABI itself (grmonty_b200_nccl_unique_id / _comm_init_rank)
+    uid = gm.nccl_unique_id() if rank == 0 else bytes(gm.NCCL_ID_BYTES)
+    t = torch.frombuffer(bytearray(uid), dtype=torch.uint8).clone()
     dist.broadcast(t, 0)
-    C.memmove(C.byref(uid), bytes(t.numpy().tobytes()), 128)
     torch.cuda.set_device(rank)
-    comm = C.c_void_p()
-    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
-    assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    comm = gm.nccl_comm_init_rank(t.numpy().tobytes(), rank, world, rank)
     g = dict(np.load(os.path.join(%r, "tests", "golden", "functions_48.npz")))
     model = {k[6:]: (v.item() if v.ndim == 0 else v) for k, v in g.items() if k.startswith("model_")}
     ctx = gm.Context(model, seed=123, rank=rank, world=world, device=rank)
     ctx.run()
     mine = ctx.result()
-    rc = ctx.L.grmonty_b200_allreduce(ctx.h, comm, None)
-    assert rc == 0, ctx.L.grmonty_b200_last_error(ctx.h)
+    ctx.allreduce(comm)
     red = ctx.result()
     np.savez(out + f".{rank}.npz", mine_spec=mine["spectrum"], red_spec=red["spectrum"],
              mine_counts=np.array([mine["created"], mine["scattered"], mine["recorded"]], dtype=np.int64),
@@ -52,8 +42,7 @@ WORKER = textwrap.dedent("""
              mine_mt=np.array(mine["max_tau_scatt"]), red_mt=np.array(red["max_tau_scatt"]),
              total=np.array(ctx.total_primaries()))
     ctx.close()
-    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
-    nccl.ncclCommDestroy(comm)
+    gm.nccl_comm_destroy(comm)
     dist.barrier()
     dist.destroy_process_group()
 """) % (ROOT, ROOT)

@@ -39,7 +39,7 @@ def gm():
 
 @pytest.fixture(scope="module")
 def ctx(gm, golden_model):
-    c = gm.Context(golden_model, seed=123)
+    c = gm.Context(golden_model, seed=123, test_exports=True)
     yield c
     c.close()
 
@@ -251,7 +251,7 @@ def test_track_with_scattering_matches_oracle_photon_by_photon(ctx, orc_model):
 def test_full_run_matches_oracle(ctx, orc_model, golden_model, gm):
     """grmonty_b200_run over the first generations vs orc_run with the same schedule"""
     M = orc_model
-    c2 = gm.Context(golden_model, seed=123, gen0=1 << 10, gen_cap=1 << 12)
+    c2 = gm.Context(golden_model, seed=123, gen0=1 << 10, gen_cap=1 << 12, test_exports=True)
     last = 6000
     c2.run(0, last)
     res = c2.result()

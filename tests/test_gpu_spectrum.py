@@ -8,9 +8,14 @@ Philox seeds 1000, 1001, ...  The two use different random streams, so the compa
   * per-bin nu L_nu (the de_dle accumulator, reference harm_model.cpp:1324) chi-square consistent over the bins
     holding >= 1e3 superphotons per run, with the bin variances measured from the seed-to-seed spread;
   * L1 distance of the ensemble-mean spectra over those bins < 2 %;
-  * integrated luminosity, recorded and scattered counts within 1 % (plus twice the standard error of the
-    ensemble difference: the reference's own seed-to-seed spread of these counts is 2.5 %, because its scattering
-    bias divides by a running maximum, harm_model.cpp:1296,1391-1404).
+  * integrated luminosity, recorded and scattered counts within 1 %, as HARD bars: the ensembles are large enough
+    (64 CUDA seeds against 60 reference runs) that the standard error of every difference is below 0.5 %, which the
+    test asserts too.  (The reference's own seed-to-seed spread of the counts is 2.5 % at this photon_n, because its
+    scattering bias divides by a running maximum, harm_model.cpp:1296,1391-1404.)
+
+configs[1] (photon_n = 1e6, the bench workload) is compared the same way against all 14 complete reference runs
+(two fixture files); there the counts are compared CONDITIONAL on the running maximum they are driven by, see
+test_bench_workload_photon_n_1e6_vs_reference.
 """
 import os
 
@@ -20,7 +25,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N_GPU_SEEDS = 24
+N_GPU_SEEDS = 64
 
 
 def report(section, values):
@@ -81,7 +86,8 @@ def test_counts_and_luminosity_within_1pct(ref, gpu_runs):
     report("counts_configs0", {k: {"rel_diff": float(v[0]), "std_err": float(v[1])} for k, v in rep.items()} |
            {"n_gpu_seeds": len(gpu_runs), "n_ref_seeds": int(len(r_rec))})
     for name, (d, se) in rep.items():
-        assert abs(d) < 0.01 + 2 * se, (name, d, se)
+        assert se < 0.005, (name, se)       # the comparison has the power to see a 1 % difference at two sigma
+        assert abs(d) < 0.01, (name, d, se)  # north-star bar, no statistical allowance
 
 
 def test_spectrum_chi_square_and_l1(ref, gpu_runs):
@@ -132,21 +138,51 @@ def test_run_is_deterministic(gpu_runs, ref):
     assert np.allclose(r["spectrum"][:, :, 1], r0["spectrum"][:, :, 1], rtol=1e-9, atol=0)
 
 
+def conditional_residual(g_tau, g_val, r_tau, r_val, n_boot=2000):
+    """Counts at a given value of the running maximum they are driven by.  ln(count) = a + b ln(max_tau_scatt) is fitted
+    to the CUDA ensemble; returns the median residual of the reference runs about that line, its bootstrap standard
+    error (resampling both ensembles, fixed generator) and the fitted exponent b."""
+    lg_t, lg_v, lr_t, lr_v = np.log(g_tau), np.log(g_val), np.log(r_tau), np.log(r_val)
+
+    def med(lgt, lgv, lrt, lrv):
+        b, a = np.polyfit(lgt, lgv, 1)
+        return float(np.median(lrv - (a + b * lrt))), float(b)
+    m, b = med(lg_t, lg_v, lr_t, lr_v)
+    rng = np.random.default_rng(7)
+    boots = []
+    for _ in range(n_boot):
+        ig, ir = rng.integers(0, len(lg_t), len(lg_t)), rng.integers(0, len(lr_t), len(lr_t))
+        boots.append(med(lg_t[ig], lg_v[ig], lr_t[ir], lr_v[ir])[0])
+    return m, float(np.std(boots)), b
+
+
 def test_bench_workload_photon_n_1e6_vs_reference():
-    """configs[1] (the bench workload, photon_n = 1e6): 6 CUDA runs against 6 complete runs of the reference CLI
-    (36 minutes each on one core; tests/golden/spectrum_192_4e19_1e6.npz, `oracle/make_golden.py spectrum_1e6`)."""
+    """configs[1] (the bench workload, photon_n = 1e6): 24 CUDA runs against all 14 complete runs of the reference CLI
+    (31 - 40 minutes each on one core; tests/golden/spectrum_192_4e19_1e6.npz + ..._1e6_more.npz, written by
+    `oracle/make_golden.py spectrum_1e6` / `spectrum_1e6_more`).
+
+    Luminosity and the spectrum are bias-independent observables and get hard bars.  The recorded / scattered COUNTS
+    are not: the reference's scattering bias is ~ 1 / (running maximum of tau_scatt) (harm_model.cpp:1296,1391-1404),
+    so a run whose maximum jumped early ends with fewer, heavier scattered superphotons -- one of the 14 reference runs
+    ends 32 % below the others for exactly that reason, and the per-run spread of the scattered count is 10 %.  The
+    CUDA path keeps the same statistic and has the same tail.  Comparing ensemble means would therefore be decided by
+    whether such a run is in the sample; the counts are compared at equal max_tau_scatt instead (median residual of the
+    reference runs about the CUDA ensemble's count-vs-maximum relation), which has a standard error below 0.6 %."""
     import tempfile
     import cuda_grmonty_b200 as gm
     from tools import make_harm_dump
-    ref = dict(np.load(os.path.join(ROOT, "tests", "golden", "spectrum_192_4e19_1e6.npz")))
+    parts = [dict(np.load(os.path.join(ROOT, "tests", "golden", f))) for f in
+             ("spectrum_192_4e19_1e6.npz", "spectrum_192_4e19_1e6_more.npz")]
+    ref = {k: np.concatenate([p[k] for p in parts]) for k in ("created", "recorded", "scattered", "max_tau_scatt", "spec")}
+    assert len(ref["recorded"]) == 14
     dump = os.path.join(tempfile.mkdtemp(), "dump192.txt")
     make_harm_dump.write_dump(dump, *make_harm_dump.make_dump(n0=192, n1=192))
-    hm = gm.HarmModel(int(ref["photon_n"]), float(ref["mass_unit"]))
+    hm = gm.HarmModel(int(parts[0]["photon_n"]), float(parts[0]["mass_unit"]))
     hm.read_file(dump)
     hm.init()
     model = hm.model_dict()
     runs = []
-    for s in range(len(ref["recorded"])):
+    for s in range(24):
         ctx = gm.Context(model, seed=4000 + s)
         ctx.run()
         runs.append(ctx.result())
@@ -154,12 +190,17 @@ def test_bench_workload_photon_n_1e6_vs_reference():
     rep = {}
     g_lum = np.array([r["spectrum"][:, :, 1].sum() for r in runs])
     r_lum = ref["spec"][..., 1].sum(axis=(1, 2))
+    g_tau = np.array([r["max_tau_scatt"] for r in runs])
     for name, g, r in (("luminosity", g_lum, r_lum),
                        ("recorded", np.array([r["recorded"] for r in runs], float), ref["recorded"].astype(float)),
                        ("scattered", np.array([r["scattered"] for r in runs], float), ref["scattered"].astype(float))):
         d = g.mean() / r.mean() - 1
         se = np.hypot(g.std(ddof=1) / np.sqrt(len(g)) / g.mean(), r.std(ddof=1) / np.sqrt(len(r)) / r.mean())
-        rep[name] = {"rel_diff": float(d), "std_err": float(se)}
+        rep[name] = {"rel_diff_of_means": float(d), "std_err": float(se),
+                     "rel_diff_of_medians": float(np.median(g) / np.median(r) - 1)}
+        if name != "luminosity":
+            m, mse, b = conditional_residual(g_tau, g, ref["max_tau_scatt"], r)
+            rep[name] |= {"ref_minus_cuda_at_equal_max_tau": m, "std_err_conditional": mse, "exponent": b}
     gs = np.array([r["spectrum"][:, :, 1] for r in runs])
     rs = ref["spec"][..., 1]
     mask = ref["spec"][..., 2].mean(0) >= 1e3
@@ -170,7 +211,11 @@ def test_bench_workload_photon_n_1e6_vs_reference():
                        "max_abs_z": float(np.abs(z).max())}
     print(rep)
     report("configs1_photon_n_1e6", rep | {"n_gpu_seeds": len(runs), "n_ref_seeds": int(len(r_lum))})
-    for name in ("luminosity", "recorded", "scattered"):
-        assert abs(rep[name]["rel_diff"]) < 0.01 + 2 * rep[name]["std_err"], (name, rep[name])
-    assert rep["spectrum"]["chi2_per_bin"] < 2.0          # variances from 6 + 6 samples: E[z^2] ~ 1.6
+    assert abs(rep["luminosity"]["rel_diff_of_means"]) < 0.01 and rep["luminosity"]["std_err"] < 0.005
+    for name in ("recorded", "scattered"):
+        assert rep[name]["std_err_conditional"] < 0.006, (name, rep[name])
+        assert abs(rep[name]["ref_minus_cuda_at_equal_max_tau"]) < 0.01, (name, rep[name])
+        # the unconditional means are heavy-tailed (see above): reported, and held to the bar within their own error
+        assert abs(rep[name]["rel_diff_of_means"]) < 0.01 + 2 * rep[name]["std_err"], (name, rep[name])
+    assert rep["spectrum"]["chi2_per_bin"] < 1.6          # variances from 24 + 14 samples
     assert l1 < 0.02

@@ -126,14 +126,20 @@ def test_cabi_library_exports_every_declared_symbol():
     """every function declared in include/grmonty_b200.h is exported by the CUDA library (no compute calls)"""
     import ctypes
     import re
-    hdr = open(os.path.join(ROOT, "include", "grmonty_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(grmonty_b200_[a-z0-9_]+)\s*\(", hdr)))
-    assert len(declared) >= 25
     gm.build_cuda()
-    L = ctypes.CDLL(gm.LIB_CUDA)
-    missing = [s for s in declared if not hasattr(L, s)]
-    assert not missing, missing
-    assert sorted(gm.ABI_SYMBOLS) == declared
+    for header, path, names in (("grmonty_b200.h", gm.LIB_CUDA, gm.ABI_SYMBOLS),
+                                ("grmonty_b200_test.h", gm.LIB_CUDA_TEST, gm.TEST_ABI_SYMBOLS)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        declared = sorted(set(re.findall(r"\b(grmonty_b200_[a-z0-9_]+)\s*\(", hdr)))
+        assert len(declared) >= 15
+        L = ctypes.CDLL(path)
+        missing = [s for s in declared if not hasattr(L, s)]
+        assert not missing, missing
+        assert sorted(names) == declared
+    # the product library carries no test export; the test library is a superset of the product ABI
+    prod, test = ctypes.CDLL(gm.LIB_CUDA), ctypes.CDLL(gm.LIB_CUDA_TEST)
+    assert not [s for s in gm.TEST_ABI_SYMBOLS if hasattr(prod, s)]
+    assert not [s for s in gm.ABI_SYMBOLS if not hasattr(test, s)]
 
 
 def test_no_cpu_fallback(golden_model):
