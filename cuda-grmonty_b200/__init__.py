@@ -35,6 +35,7 @@ CLI = os.path.join(PKG_DIR, "grmonty_b200")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--cudart=shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
 
+ABI_VERSION = 3
 N_TH, N_E, N_F = 6, 200, 13
 SPEC_FIELDS = ["dn_dle", "de_dle", "nph", "nscatt", "x1i_av", "x2i_sq", "x3f_sq", "tau_abs", "tau_scatt",
                "ne_0", "theta_e_0", "b_0", "e_0"]
@@ -111,6 +112,7 @@ class Config(C.Structure):
         ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
         ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64), ("gen_budget", C.c_int64),
         ("gen_budget_spread", C.c_int64), ("gen_fine_from", C.c_int64), ("gen_ramp", C.c_int64), ("gen_fine_div", C.c_int64),
+        ("kernel", C.c_int32), ("slots_per_thread", C.c_int32), ("wf_thr_interact", C.c_int32), ("wf_thr_service", C.c_int32),
     ]
 
 
@@ -142,8 +144,12 @@ TEST_ABI_SYMBOLS = [
     "grmonty_b200_test_track", "grmonty_b200_test_samplers", "grmonty_b200_test_philox",
 ]
 
-# launch geometries (threads per block, blocks per SM) compiled into the library: csrc/gm_api.cu kVariants
-KERNEL_VARIANTS = [(256, 1), (64, 4), (128, 2), (128, 3), (384, 1), (512, 1)]
+# launch geometries compiled into the library (csrc/gm_api.cu): (kernel, threads per block, blocks per SM or slots per
+# thread).  kernel 1 = the fused loop (the default, also selected by 0), 2 = wavefront (third number: photon slots
+# per thread)
+KERNEL_FUSED, KERNEL_WAVEFRONT = 1, 2
+KERNEL_VARIANTS = [(1, 256, 1), (1, 64, 4), (1, 128, 2), (1, 384, 1),
+                   (2, 384, 2), (2, 256, 2), (2, 256, 3), (2, 512, 1), (2, 384, 1), (2, 128, 2)]
 
 _libs = {}
 
@@ -231,14 +237,17 @@ class Context:
     def __init__(self, model: dict, seed: int = 123, rank: int = 0, world: int = 1, device: int = 0,
                  threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
                  gen_cap: int = 0, gen_budget: int = 0, gen_fine_from: int = 0, gen_fine_div: int = 0,
-                 gen_ramp: int = 0, gen_budget_spread: int = 0, test_exports: bool = False):
+                 gen_ramp: int = 0, gen_budget_spread: int = 0, kernel: int = 0, slots_per_thread: int = 0,
+                 wf_thr_interact: int = 0, wf_thr_service: int = 0, test_exports: bool = False):
         # test_exports: create the context in libgrmonty_b200_test.so so that the t_* batch exports can be called on it
         self.L = lib(test_exports)
         cfg, self._keep = make_config(model, seed=seed, rank=rank, world=world, device=device,
                                       threads_per_block=threads_per_block, blocks_per_sm=blocks_per_sm,
                                       queue_capacity=queue_capacity, gen0=gen0, gen_cap=gen_cap, gen_budget=gen_budget,
                                       gen_fine_from=gen_fine_from, gen_fine_div=gen_fine_div, gen_ramp=gen_ramp,
-                                      gen_budget_spread=gen_budget_spread)
+                                      gen_budget_spread=gen_budget_spread, kernel=kernel,
+                                      slots_per_thread=slots_per_thread, wf_thr_interact=wf_thr_interact,
+                                      wf_thr_service=wf_thr_service)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))
@@ -405,7 +414,7 @@ def make_config(model: dict, **options):
     """grmonty_b200_config for `model` (see Context) + the arrays it points into (keep them alive as long as the
     config is in use).  `options`: the integer fields of the config tail (seed, rank, world, device, gen0, ...)."""
     cfg = Config()
-    cfg.abi_version = 2
+    cfg.abi_version = ABI_VERSION
     cfg.struct_size = C.sizeof(Config)
     cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
     for k in Context.SCALARS:
@@ -446,7 +455,7 @@ def init_tables(model: dict, device: int = 0) -> dict:
     """geom_det [n0][n1], weight [201], nint [20001], dndlnu_max [20001] built on the GPU (grmonty_b200_init_tables)
     from the grids, units, photon_n and the F(K) / K2 tables of `model`; also `device_ms` of the three kernels."""
     cfg = Config()
-    cfg.abi_version = 2
+    cfg.abi_version = ABI_VERSION
     cfg.struct_size = C.sizeof(Config)
     cfg.n0, cfg.n1 = int(model["n0"]), int(model["n1"])
     for k in Context.SCALARS:

@@ -27,6 +27,7 @@
 
 #include "gm_kernels.cuh"
 #include "gm_tables.cuh"
+#include "gm_wavefront.cuh"
 
 using namespace gm;
 
@@ -42,6 +43,8 @@ struct DeviceArena {
 };
 static std::mutex g_arena_mutex;
 static std::vector<DeviceArena> g_arena_cache;
+
+struct WfVariant;
 
 struct grmonty_b200_ctx {
     grmonty_b200_config cfg;
@@ -92,6 +95,11 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
+    int kernel = 0;                 /* 0: wavefront, 1: fused loop of round 1 */
+    const WfVariant *wf = nullptr;  /* the wavefront variant in use */
+    double *d_snap = nullptr;       /* wavefront pre-step snapshots [13][snap_stride] */
+    unsigned int snap_stride = 0;
+    int wf_thr_interact = 192, wf_thr_service = 32;
     long long gen0 = 32, gen_cap = 1 << 20, gen_fine_from = 16384, gen_fine_div = 6, gen_ramp = 8, gen_budget_spread = 0;
     grmonty_b200_stats stats{};
     grmonty_b200_progress_fn progress = nullptr;
@@ -157,6 +165,25 @@ static const Variant kVariants[] = {
 static const Variant *find_variant(int block, int min_blocks) {
     for (const Variant &v : kVariants)
         if (v.block == block && v.min_blocks == min_blocks)
+            return &v;
+    return nullptr;
+}
+/* wavefront kernel (gm_wavefront.cuh): threads per block x photon slots per thread, one block per SM */
+struct WfVariant {
+    int block, slots, min_blocks;
+    TransportFn fn;
+    size_t smem;
+};
+#define GM_WF(B, R, M) {B, R, M, wavefront_kernel<B, R, M>, wavefront_smem_bytes<B, R>()}
+/* the third number is the __launch_bounds__ minimum of blocks per SM (register cap); blocks actually resident follow
+ * from registers and the shared-memory slots (228 bytes per slot) */
+static const WfVariant kWfVariants[] = {GM_WF(384, 2, 1), GM_WF(256, 2, 1), GM_WF(256, 3, 1), GM_WF(512, 1, 1),
+                                        GM_WF(384, 1, 1), GM_WF(128, 2, 2), GM_WF(128, 3, 2), GM_WF(128, 2, 3),
+                                        GM_WF(192, 2, 2)};
+#undef GM_WF
+static const WfVariant *find_wf_variant(int block, int slots, int min_blocks) {
+    for (const WfVariant &v : kWfVariants)
+        if (v.block == block && v.slots == slots && (min_blocks <= 0 || v.min_blocks == min_blocks))
             return &v;
     return nullptr;
 }
@@ -290,6 +317,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
                                             (int)ctx->sort_cap, 0, 8, ctx->stream);
             need += (size_t)ctx->sort_cap * 2 * (1 + sizeof(long long)) + ctx->sort_tmp_bytes +
                     (size_t)cfg->n0 * (2 * sizeof(unsigned long long) + 1);
+            need += (size_t)13 * ctx->sm_count * 1024 * sizeof(double); /* wavefront snapshot rows: <= 1024 slots / SM */
             need += 64 * 256; /* alignment padding of the ~40 sub-allocations */
             {
                 std::lock_guard<std::mutex> lock(g_arena_mutex);
@@ -477,7 +505,7 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         CK(arena_alloc(ctx, &ctx->d_spectrum, nspec));
         CK(arena_alloc(ctx, &ctx->d_counters, 3));
         CK(arena_alloc(ctx, &ctx->d_maxtau, 1));
-        CK(arena_alloc(ctx, &ctx->d_work, 8));
+        CK(arena_alloc(ctx, &ctx->d_work, 24));
         CK(arena_alloc(ctx, &ctx->d_error, 1));
         CK(arena_alloc(ctx, &ctx->d_args, 1));
         ctx->A.spectrum = ctx->d_spectrum;
@@ -488,20 +516,54 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
 
         mark("pool and queues");
         /* ---- launch geometry ---- */
-        ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;
-        int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 1;
-        const Variant *v = find_variant(ctx->threads, want_bps);
-        if (!v)
-            return fail(ctx, GRMONTY_B200_EINVAL, "no compiled kernel variant for %d threads x %d blocks/SM",
-                        ctx->threads, want_bps);
-        const size_t smem = transport_smem_bytes(ctx->threads);
-        CK(cudaFuncSetAttribute((const void *)v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)v->fn, ctx->threads, smem));
-        if (occ < 1)
-            return fail(ctx, GRMONTY_B200_ECUDA, "transport kernel does not fit on an SM");
-        ctx->blocks_per_sm = std::min(occ, want_bps);
-        ctx->grid_blocks = ctx->blocks_per_sm * ctx->sm_count;
+        /* config: 0 = default (the fused loop, the faster of the two on B200), 1 = fused, 2 = wavefront;
+         * ctx->kernel: 0 = wavefront, 1 = fused */
+        if (cfg->kernel < 0 || cfg->kernel > 2)
+            return fail(ctx, GRMONTY_B200_EINVAL, "kernel must be 0 (default), 1 (fused) or 2 (wavefront)");
+        ctx->kernel = cfg->kernel == 2 ? 0 : 1;
+        if (const char *e = getenv("GRMONTY_B200_KERNEL")) /* A/B switch for tools/: "fused" or "wavefront" */
+            ctx->kernel = strcmp(e, "wavefront") == 0 ? 0 : 1;
+        if (ctx->kernel == 0) {
+            ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 384;
+            const int slots = cfg->slots_per_thread > 0 ? cfg->slots_per_thread : 2;
+            ctx->wf = find_wf_variant(ctx->threads, slots, cfg->blocks_per_sm);
+            if (!ctx->wf)
+                return fail(ctx, GRMONTY_B200_EINVAL,
+                            "no compiled wavefront variant for %d threads x %d slots (x %d blocks/SM)", ctx->threads,
+                            slots, cfg->blocks_per_sm);
+            CK(cudaFuncSetAttribute((const void *)ctx->wf->fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ctx->wf->smem));
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)ctx->wf->fn, ctx->threads,
+                                                             ctx->wf->smem));
+            if (occ < 1)
+                return fail(ctx, GRMONTY_B200_ECUDA, "wavefront kernel does not fit on an SM");
+            ctx->blocks_per_sm = occ;
+            ctx->grid_blocks = occ * ctx->sm_count;
+            ctx->snap_stride = (unsigned int)(ctx->grid_blocks * ctx->threads * slots);
+            CK(arena_alloc(ctx, &ctx->d_snap, (size_t)13 * ctx->snap_stride));
+            if (cfg->wf_thr_interact > 0)
+                ctx->wf_thr_interact = cfg->wf_thr_interact;
+            if (cfg->wf_thr_service > 0)
+                ctx->wf_thr_service = cfg->wf_thr_service;
+            if (const char *e = getenv("GRMONTY_B200_WF_THR")) /* "interact,service" in 1/256 (tools/ sweeps) */
+                sscanf(e, "%d,%d", &ctx->wf_thr_interact, &ctx->wf_thr_service);
+        } else {
+            ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;
+            int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 1;
+            const Variant *v = find_variant(ctx->threads, want_bps);
+            if (!v)
+                return fail(ctx, GRMONTY_B200_EINVAL, "no compiled kernel variant for %d threads x %d blocks/SM",
+                            ctx->threads, want_bps);
+            const size_t smem = transport_smem_bytes(ctx->threads);
+            CK(cudaFuncSetAttribute((const void *)v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)v->fn, ctx->threads, smem));
+            if (occ < 1)
+                return fail(ctx, GRMONTY_B200_ECUDA, "transport kernel does not fit on an SM");
+            ctx->blocks_per_sm = std::min(occ, want_bps);
+            ctx->grid_blocks = ctx->blocks_per_sm * ctx->sm_count;
+        }
         if (cfg->gen0 > 0)
             ctx->gen0 = cfg->gen0;
         if (cfg->gen_cap > 0)
@@ -539,7 +601,7 @@ int grmonty_b200_reset(grmonty_b200_ctx *ctx) {
     const size_t nspec = (size_t)kNThBins * kNEBins * kSpecFields;
     CK(cudaMemsetAsync(ctx->d_spectrum, 0, nspec * sizeof(double), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 24 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_error, 0, sizeof(unsigned int), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_zone_cost, 0, (size_t)2 * ctx->P.n0 * sizeof(unsigned long long), ctx->stream));
     std::fill(ctx->h_zone_cost.begin(), ctx->h_zone_cost.end(), 0ull);
@@ -591,6 +653,10 @@ static void fill_args(grmonty_b200_ctx *ctx, const GmBiasStats &bias, const Debu
     args.A = ctx->A;
     args.D = dbg;
     args.zone_cost = ctx->d_zone_cost;
+    args.snap = ctx->d_snap;
+    args.snap_stride = ctx->snap_stride;
+    args.wf_thr_interact = ctx->wf_thr_interact;
+    args.wf_thr_service = ctx->wf_thr_service;
     args.self = ctx->d_args;
 }
 
@@ -617,7 +683,8 @@ static int begin_batch(grmonty_b200_ctx *ctx, long long count) {
  * budget: attempts a lineage may make in this batch before it is suspended and carried over. */
 static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, long long count,
                      const GmBiasStats &bias, const DebugOut &dbg, bool preloaded, int budget) {
-    const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
+    const Variant *v = ctx->kernel == 0 ? nullptr
+                                        : find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
     /* the device-global copy of the arguments is written on the batch's own stream, ahead of the kernels that read it
      * through A.self; the source lives in the context and is rewritten only after the batch's final synchronisation */
     TransportArgs &args = ctx->h_args;
@@ -688,7 +755,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         }
         CK(cudaEventRecord(ctx->ev3, ctx->stream)); /* read after the batch's one synchronisation below */
     }
-    const size_t smem = transport_smem_bytes(ctx->threads);
+    const size_t smem = ctx->kernel == 0 ? ctx->wf->smem : transport_smem_bytes(ctx->threads);
     /* do not launch far more threads than there are photons to start with (tiny generations / test batches) */
     long long blocks = std::min<long long>(ctx->grid_blocks,
                                            std::max<long long>(1, (n_start * 2 + ctx->threads - 1) / ctx->threads));
@@ -711,7 +778,7 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
     if (prof)
         cudaProfilerStart();
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    v->fn<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
+    (ctx->kernel == 0 ? ctx->wf->fn : v->fn)<<<(unsigned)blocks, ctx->threads, smem, ctx->stream>>>(args);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     /* one host synchronisation per batch: error word, queue counters and the accumulators the next generation's
@@ -741,10 +808,30 @@ static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, l
         static int trace = -1; /* GRMONTY_B200_TRACE=1: one line per transport launch on stderr */
         if (trace < 0)
             trace = getenv("GRMONTY_B200_TRACE") ? 1 : 0;
-        if (trace)
+        if (trace) {
             fprintf(stderr, "[grmonty_b200] batch first=%lld count=%lld carried_in=%lld budget=%d blocks=%lld: %.3f ms, "
                             "records=%llu ready=%llu scatter=%llu carried_out=%llu\n",
                     first, count, n_carry, budget, blocks, ms, qc[0], qc[3], qc[5], qc[7]);
+            if (ctx->kernel == 0) { /* wavefront phase statistics of this launch (differences of the run totals) */
+                static unsigned long long prev[24] = {0};
+                unsigned long long w[24];
+                CK(cudaMemcpy(w, ctx->d_work, sizeof(w), cudaMemcpyDeviceToHost));
+                unsigned long long d[24];
+                for (int i = 0; i < 24; ++i)
+                    d[i] = w[i] >= prev[i] ? w[i] - prev[i] : w[i];
+                memcpy(prev, w, sizeof(w));
+                const double lanes = (double)blocks * ctx->threads;
+                fprintf(stderr, "    phases/block: push %.0f interact %.0f service %.0f scatter %.0f idle %.0f; lane "
+                                "efficiency push %.3f interact %.3f; us/phase push %.2f interact %.2f service %.2f "
+                                "scatter %.2f idle %.2f\n",
+                        d[8] / (double)blocks, d[9] / (double)blocks, d[10] / (double)blocks, d[11] / (double)blocks,
+                        d[12] / (double)blocks, d[13] / std::max(1.0, d[8] * (double)ctx->threads),
+                        d[14] / std::max(1.0, d[9] * (double)ctx->threads), d[16] / 1965.0 / std::max(1.0, (double)d[8]),
+                        d[17] / 1965.0 / std::max(1.0, (double)d[9]), d[18] / 1965.0 / std::max(1.0, (double)d[10]),
+                        d[19] / 1965.0 / std::max(1.0, (double)d[11]), d[20] / 1965.0 / std::max(1.0, (double)d[12]));
+                (void)lanes;
+            }
+        }
     }
     if (!preloaded) {
         CK(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
@@ -1043,8 +1130,14 @@ int grmonty_b200_result(grmonty_b200_ctx *ctx, double *spectrum, uint64_t counts
         memcpy(max_tau_scatt, &bits, sizeof(double));
     }
     if (stats) {
-        unsigned long long w[8];
+        unsigned long long w[24];
         CK(cudaMemcpy(w, ctx->d_work, sizeof(w), cudaMemcpyDeviceToHost));
+        if (getenv("GRMONTY_B200_TRACE"))
+            fprintf(stderr, "[grmonty_b200] wavefront block-phases: push %llu interact %llu service %llu scatter %llu idle "
+                            "%llu; lane-phases with work: push %llu interact %llu; Mcycles of thread 0 per phase kind (sum "
+                            "over blocks): push %.0f interact %.0f service %.0f scatter %.0f idle %.0f\n",
+                    w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[16] * 1e-6, w[17] * 1e-6, w[18] * 1e-6, w[19] * 1e-6,
+                    w[20] * 1e-6);
         ctx->stats.n_tracked = w[0] + ctx->host_tracked;
         ctx->stats.n_steps = w[1];
         ctx->stats.n_push_attempts = w[2];

@@ -95,6 +95,12 @@ struct TransportArgs {
     /* [2][n0]: sum of steps and number of finished PRIMARIES per radial bin of their birth zone: what the host
      * sorts the next generations' issue order by (long-lived zones first; see gm_api.cu run_batch) */
     unsigned long long *zone_cost;
+    /* wavefront kernel (gm_wavefront.cuh): pre-step snapshots [13][snap_stride] of its resident photons, and its
+     * phase thresholds in 1/256: the interaction phase runs when that share of the lanes holding work have a step
+     * pending, the service phase when that share of all lanes has a finished photon or an empty slot to refill */
+    double *snap;
+    unsigned int snap_stride;
+    int wf_thr_interact, wf_thr_service;
     /* device-global copy of this very struct: out-of-line (cold) stages take it by pointer so that the kernel
      * parameter itself never has its address taken and stays in the constant bank for the hot loop */
     const TransportArgs *self;
@@ -420,6 +426,11 @@ enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_S
 /* Interaction with the fluid after an accepted step (reference harm_model.cpp:936-1056).
  * If the photon scatters in this step it is parked for the scattering stage (STEP_SCATTER).
  * Single exit, no early returns: the lanes of a warp must leave this function together (see advance). */
+/* DEFER_PARK (wavefront kernel): a photon that scatters is not written to its pool record here -- the lane returns
+ * STEP_SCATTER with the parked record's values in L (w attenuated, tau_abs / tau_scatt at the scattering point,
+ * alpha_scatt = dl * frac, alpha_abs = weight of the child, rng before the child-identity draw) and the record is
+ * written by the service phase (wf_park), where all lanes that have something rare to do are together. */
+template <bool DEFER_PARK = false>
 __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const GeoPoint &q,
                                                const double *snap, int snap_stride, Work &wk) {
     const GmParams &P = A.P;
@@ -476,7 +487,23 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
         scatters = bd > x1r && w_child > kWeightMin;
     }
     StepResult res = STEP_CONTINUE;
-    if (scatters) {
+    if (DEFER_PARK && scatters) {
+        const double frac = fm::div(x1r, bd);
+        d_tau_abs *= frac;
+        if (d_tau_abs > 100) {
+            L.rng.ctr += 1u; /* the child-identity draw of the fused form (rng_child), never used */
+            L.status |= 4;
+            res = STEP_FINISHED; /* absorbed before scattering */
+        } else {
+            d_tau_scatt *= frac;
+            L.w *= attenuation(d_tau_abs + d_tau_scatt, d_tau_abs < 1.0e-3);
+            L.tau_abs += d_tau_abs;
+            L.tau_scatt += d_tau_scatt;
+            L.alpha_scatt = L.dl * frac;
+            L.alpha_abs = w_child;
+            res = STEP_SCATTER;
+        }
+    } else if (scatters) {
         /* ---- the photon scatters in this step (reference :985-1005): park it ---- */
         const Rng crng = rng_child(P, L.rng);
         const double frac = fm::div(x1r, bd);
@@ -600,7 +627,7 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, u
             st = STEP_FINISHED;
         } else {
             if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos)
-                st = interact(A, L, q, snap, snap_stride, wk);
+                st = interact<false>(A, L, q, snap, snap_stride, wk);
             if (st == STEP_CONTINUE) {
                 ++L.n_step;
                 if (L.n_step > kMaxNStep)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRMONTY_B200_ABI_VERSION 2
+#define GRMONTY_B200_ABI_VERSION 3
 
 #define GRMONTY_B200_N_TH_BINS 6     /* reference consts.hpp:26 */
 #define GRMONTY_B200_N_E_BINS 200    /* reference consts.hpp:25 */
@@ -116,6 +116,16 @@ typedef struct grmonty_b200_config {
                                Measured at configs[0] against 20 reference runs (profiles/r1_bias_schedule.txt):
                                doubling with budget 256 gives +5.8 % scattered / +2.5 % recorded counts,
                                div 6 with budget 384 gives +0.6 % / +0.1 %. */
+    /* Transport kernel.  0 (default) or 1: the fused per-lane loop (threads_per_block x blocks_per_sm as compiled in
+     * csrc/gm_api.cu; default 256 x 1).  2: the state-compacting wavefront kernel (csrc/gm_wavefront.cuh) -- photons
+     * resident in shared memory, `slots_per_thread` of them per thread (default 2), the block runs push / interact /
+     * service / scatter phases chosen by lane counts; threads_per_block 128 ... 512 (default 384).  The wavefront
+     * kernel is the slower of the two on B200 (profiles/r2_wavefront_vs_fused.txt) and is kept as a selectable
+     * alternative.  Results do not depend on the choice (tests/test_gpu_invariance.py). */
+    int32_t kernel;
+    int32_t slots_per_thread;
+    /* wavefront phase thresholds in 1/256 (0 = default): see TransportArgs in csrc/gm_transport.cuh */
+    int32_t wf_thr_interact, wf_thr_service;
 } grmonty_b200_config;
 
 /* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */

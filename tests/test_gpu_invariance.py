@@ -33,16 +33,17 @@ WORK = ("n_tracked", "n_steps", "n_push_attempts", "n_interactions", "n_scatter_
 def test_results_do_not_depend_on_launch_geometry(golden_model):
     import cuda_grmonty_b200 as gm
     base = None
-    for threads, blocks in gm.KERNEL_VARIANTS:
-        r = small_run(gm, golden_model, threads_per_block=threads, blocks_per_sm=blocks)
+    for kernel, threads, third in gm.KERNEL_VARIANTS:
+        kw = dict(slots_per_thread=third) if kernel == gm.KERNEL_WAVEFRONT else dict(blocks_per_sm=third)
+        r = small_run(gm, golden_model, kernel=kernel, threads_per_block=threads, **kw)
         assert r["scattered"] > 1000 and r["stats"]["n_scatter_events"] > 1000   # scattering, children and carry-over ran
         if base is None:
             base = r
             continue
         for k in INTS:
-            assert r[k] == base[k], (threads, blocks, k)
+            assert r[k] == base[k], (kernel, threads, third, k)
         for k in WORK:
-            assert r["stats"][k] == base["stats"][k], (threads, blocks, k)
+            assert r["stats"][k] == base["stats"][k], (kernel, threads, third, k)
         assert r["max_tau_scatt"] == base["max_tau_scatt"]
         assert np.array_equal(r["spectrum"][:, :, 2], base["spectrum"][:, :, 2])     # photons per bin
         assert np.array_equal(r["spectrum"][:, :, 3], base["spectrum"][:, :, 3])     # scatterings per bin
@@ -69,6 +70,9 @@ def test_world_dependence_is_statistical_only(golden_model):
         r = c.result()
         c.close()
         return r
+    c = gm.Context(golden_model, seed=77)
+    last = min(last, c.total_primaries())        # the 48 x 48 golden model emits ~32 k primaries at its photon_n
+    c.close()
     one = run(0, 1)
     parts = [run(r, 3) for r in range(3)]
     # shares are disjoint and complete: the same primaries are tracked

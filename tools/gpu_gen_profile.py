@@ -8,7 +8,9 @@ import cuda_grmonty_b200 as gm
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 100.0
 budget = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 grid = int(sys.argv[3]) if len(sys.argv) > 3 else 48
-tb = [int(v) for v in sys.argv[4].split("x")] if len(sys.argv) > 4 else [0, 0]
+spec = sys.argv[4] if len(sys.argv) > 4 else "w0x0"   # w384x2: wavefront 384 threads x 2 slots; f256x1: fused loop
+tb = [int(v) for v in spec[1:].split("x")]
+kw = dict(kernel=2, slots_per_thread=tb[1]) if spec[0] == "w" else dict(kernel=1, blocks_per_sm=tb[1])
 if grid == 48:
     d = dict(np.load(os.path.join(ROOT, "tests/golden/functions_48.npz")))
     m = {k[6:]: (v.item() if v.ndim == 0 else v) for k, v in d.items() if k.startswith("model_")}
@@ -21,7 +23,7 @@ else:
         make_harm_dump.write_dump(p, *make_harm_dump.make_dump(n0=grid, n1=grid))
     gm.build_host()
     hm = gm.HarmModel(int(2000 * scale), 4e19); hm.read_file(p); hm.init(); m = hm.model_dict()
-c = gm.Context(m, gen_budget=budget, threads_per_block=tb[0], blocks_per_sm=tb[1])
+c = gm.Context(m, gen_budget=budget, threads_per_block=tb[0], **kw)
 tot = c.total_primaries()
 c.run(0, 2000); c.reset()
 gs, g = 0, 0
