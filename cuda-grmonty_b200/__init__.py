@@ -35,7 +35,7 @@ CLI = os.path.join(PKG_DIR, "grmonty_b200")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--cudart=shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 N_TH, N_E, N_F = 6, 200, 13
 SPEC_FIELDS = ["dn_dle", "de_dle", "nph", "nscatt", "x1i_av", "x2i_sq", "x3f_sq", "tau_abs", "tau_scatt",
                "ne_0", "theta_e_0", "b_0", "e_0"]
@@ -113,6 +113,7 @@ class Config(C.Structure):
         ("queue_capacity", C.c_int64), ("gen0", C.c_int64), ("gen_cap", C.c_int64), ("gen_budget", C.c_int64),
         ("gen_budget_spread", C.c_int64), ("gen_fine_from", C.c_int64), ("gen_ramp", C.c_int64), ("gen_fine_div", C.c_int64),
         ("kernel", C.c_int32), ("slots_per_thread", C.c_int32), ("wf_thr_interact", C.c_int32), ("wf_thr_service", C.c_int32),
+        ("gen_overlap", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -148,6 +149,7 @@ TEST_ABI_SYMBOLS = [
 # thread).  kernel 1 = the fused loop (the default, also selected by 0), 2 = wavefront (third number: photon slots
 # per thread)
 KERNEL_FUSED, KERNEL_WAVEFRONT = 1, 2
+OVERLAP_ON, OVERLAP_OFF = 1, 2     # grmonty_b200_config.gen_overlap
 KERNEL_VARIANTS = [(1, 256, 1), (1, 64, 4), (1, 128, 2), (1, 384, 1),
                    (2, 384, 2), (2, 256, 2), (2, 256, 3), (2, 512, 1), (2, 384, 1), (2, 128, 2)]
 
@@ -238,7 +240,7 @@ class Context:
                  threads_per_block: int = 0, blocks_per_sm: int = 0, queue_capacity: int = 0, gen0: int = 0,
                  gen_cap: int = 0, gen_budget: int = 0, gen_fine_from: int = 0, gen_fine_div: int = 0,
                  gen_ramp: int = 0, gen_budget_spread: int = 0, kernel: int = 0, slots_per_thread: int = 0,
-                 wf_thr_interact: int = 0, wf_thr_service: int = 0, test_exports: bool = False):
+                 wf_thr_interact: int = 0, wf_thr_service: int = 0, gen_overlap: int = 0, test_exports: bool = False):
         # test_exports: create the context in libgrmonty_b200_test.so so that the t_* batch exports can be called on it
         self.L = lib(test_exports)
         cfg, self._keep = make_config(model, seed=seed, rank=rank, world=world, device=device,
@@ -247,7 +249,7 @@ class Context:
                                       gen_fine_from=gen_fine_from, gen_fine_div=gen_fine_div, gen_ramp=gen_ramp,
                                       gen_budget_spread=gen_budget_spread, kernel=kernel,
                                       slots_per_thread=slots_per_thread, wf_thr_interact=wf_thr_interact,
-                                      wf_thr_service=wf_thr_service)
+                                      wf_thr_service=wf_thr_service, gen_overlap=gen_overlap)
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.L.grmonty_b200_create(C.byref(self.h), C.byref(cfg))

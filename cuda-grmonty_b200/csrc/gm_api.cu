@@ -26,6 +26,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gm_kernels.cuh"
+#include "gm_pipeline.cuh"
 #include "gm_tables.cuh"
 #include "gm_wavefront.cuh"
 
@@ -96,6 +97,15 @@ struct grmonty_b200_ctx {
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
     int kernel = 0;                 /* 0: wavefront, 1: fused loop of round 1 */
+    /* pipelined generations (gm_pipeline.cuh): device-side generation clock, one launch per window of generations */
+    int overlap = 1;
+    GenCtl *d_ctl = nullptr;
+    GenDesc *d_desc = nullptr; /* own allocation, grown on demand (one entry per generation of a run) */
+    size_t desc_cap = 0;
+    unsigned int *d_qent = nullptr; /* runnable queues R0 R1 and limbo queues L0 L1, qcap entries each */
+    unsigned int qcap = 0;
+    bool q_dirty = false; /* a launch did not end cleanly: clear the rings before the next one */
+    unsigned long long *h_pin = nullptr;         /* pinned staging: control line + error word + n_alloc read-back */
     const WfVariant *wf = nullptr;  /* the wavefront variant in use */
     double *d_snap = nullptr;       /* wavefront pre-step snapshots [13][snap_stride] */
     unsigned int snap_stride = 0;
@@ -156,12 +166,12 @@ static size_t transport_smem_bytes(int threads) { return (size_t)13 * threads * 
 typedef void (*TransportFn)(const TransportArgs);
 struct Variant {
     int block, min_blocks;
-    TransportFn fn;
+    TransportFn fn;      /* one launch per generation (round 1) */
+    TransportFn pipe_fn; /* overlapping generations (gm_pipeline.cuh) */
 };
-static const Variant kVariants[] = {
-    {128, 2, transport_kernel<128, 2>}, {128, 3, transport_kernel<128, 3>}, {256, 1, transport_kernel<256, 1>},
-    {64, 4, transport_kernel<64, 4>},   {384, 1, transport_kernel<384, 1>}, {512, 1, transport_kernel<512, 1>},
-};
+#define GM_V(B, M) {B, M, transport_kernel<B, M>, pipeline_kernel<B, M>}
+static const Variant kVariants[] = {GM_V(128, 2), GM_V(128, 3), GM_V(256, 1), GM_V(64, 4), GM_V(384, 1), GM_V(512, 1)};
+#undef GM_V
 static const Variant *find_variant(int block, int min_blocks) {
     for (const Variant &v : kVariants)
         if (v.block == block && v.min_blocks == min_blocks)
@@ -294,11 +304,42 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         mark("streams and events");
         /* ---- one device arena for everything (reused from the cache when possible) ---- */
         const size_t nz = (size_t)cfg->n0 * cfg->n1;
-        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity : (1ull << 22);
+        /* kernel / scheduler choice first: the pool is sized for it.  config: kernel 0 = default (the fused loop, the
+         * faster of the two on B200), 1 = fused, 2 = wavefront; gen_overlap 0 = default (on, fused loop only), 1 = on,
+         * 2 = off (one launch per generation, the round-1 scheduler) */
+        if (cfg->kernel < 0 || cfg->kernel > 2)
+            return fail(ctx, GRMONTY_B200_EINVAL, "kernel must be 0 (default), 1 (fused) or 2 (wavefront)");
+        if (cfg->gen_overlap < 0 || cfg->gen_overlap > 2)
+            return fail(ctx, GRMONTY_B200_EINVAL, "gen_overlap must be 0 (default), 1 (on) or 2 (off)");
+        ctx->kernel = cfg->kernel == 2 ? 0 : 1;
+        if (const char *e = getenv("GRMONTY_B200_KERNEL")) /* A/B switch for tools/: "fused" or "wavefront" */
+            ctx->kernel = strcmp(e, "wavefront") == 0 ? 0 : 1;
+        ctx->overlap = cfg->gen_overlap == 2 ? 0 : 1;
+        if (const char *e = getenv("GRMONTY_B200_OVERLAP")) /* A/B switch for tools/ */
+            ctx->overlap = atoi(e) != 0;
+        if (ctx->kernel == 0) {
+            if (cfg->gen_overlap == 1)
+                return fail(ctx, GRMONTY_B200_EINVAL, "gen_overlap = 1 needs the fused kernel");
+            ctx->overlap = 0;
+        }
+        /* pool records: a launch of the pipelined scheduler holds a window of generations (a third of the pool in
+         * primaries), the round-1 scheduler one generation */
+        unsigned long long cap = cfg->queue_capacity > 0 ? (unsigned long long)cfg->queue_capacity
+                                                         : (ctx->overlap ? 32ull << 20 : 1ull << 22);
         if (cap > 0x3fffffffull)
             cap = 0x3fffffffull; /* slots are addressed with 32 bits */
-        const unsigned long long stage_cap = std::max<unsigned long long>(1024, cap / 2);
-        ctx->ready.capacity = (unsigned int)std::min<unsigned long long>(2 * cap, 0x7fffffffull);
+        const unsigned long long stage_cap = std::max<unsigned long long>(1024, ctx->overlap ? cap / 4 : cap / 2);
+        /* rings R0 R1 L0 L1 + scatter of the pipelined kernel: a power of two >= the pool (live entries never exceed
+         * the records) and well above the number of lanes (tickets outstanding) */
+        ctx->qcap = 0u;
+        if (ctx->overlap) {
+            unsigned long long q = 1ull << 17;
+            while (q < cap)
+                q <<= 1;
+            ctx->qcap = (unsigned int)q;
+        }
+        /* (the per-generation queues serve the test exports' preloaded batches in overlap mode: a quarter will do) */
+        ctx->ready.capacity = (unsigned int)std::min<unsigned long long>(ctx->overlap ? cap / 2 : 2 * cap, 0x7fffffffull);
         ctx->scatter.capacity = (unsigned int)cap;
         ctx->carry.capacity = (unsigned int)stage_cap;
         {
@@ -307,8 +348,8 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
                           (size_t)(GRMONTY_B200_HOTCROSS_N + 3 * GRMONTY_B200_TABLE_N + 2 * GRMONTY_B200_NINT_N) *
                               sizeof(double) +
                           per_slot * (cap + stage_cap) +
-                          ((size_t)ctx->ready.capacity + ctx->scatter.capacity + ctx->carry.capacity) *
-                              sizeof(unsigned int) +
+                          ((size_t)ctx->ready.capacity + ctx->scatter.capacity + ctx->carry.capacity +
+                           (size_t)5 * ctx->qcap) * sizeof(unsigned int) + sizeof(GenCtl) +
                           (size_t)kNThBins * kNEBins * kSpecFields * sizeof(double) + sizeof(TransportArgs) + 4096;
             /* issue-order sort buffers for one batch (keys 1 B, values 8 B, double-buffered) + cub temporary storage */
             ctx->sort_cap = (long long)std::max<unsigned long long>(1024, cap / 4);
@@ -487,6 +528,13 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         ctx->h_zone_cost.assign((size_t)2 * cfg->n0, 0ull);
         if (const char *e = getenv("GRMONTY_B200_ORDER"))
             ctx->order_mode = atoi(e);
+        if (ctx->overlap) {
+            CK(arena_alloc(ctx, &ctx->d_qent, (size_t)5 * ctx->qcap));
+            CK(cudaMemsetAsync(ctx->d_qent, 0, (size_t)5 * ctx->qcap * sizeof(unsigned int), ctx->stream));
+            CK(arena_alloc(ctx, &ctx->d_ctl, 1));
+            CK(cudaMemsetAsync(ctx->d_ctl, 0, sizeof(GenCtl), ctx->stream));
+            CK(cudaMallocHost(&ctx->h_pin, (CW_WORDS + 8) * sizeof(unsigned long long)));
+        }
         CK(arena_alloc(ctx, &ctx->d_qctr, 8));
         CK(cudaMemsetAsync(ctx->d_qctr, 0, 8 * sizeof(unsigned long long), ctx->stream));
         ctx->pool.n_alloc = ctx->d_qctr;
@@ -516,13 +564,6 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
 
         mark("pool and queues");
         /* ---- launch geometry ---- */
-        /* config: 0 = default (the fused loop, the faster of the two on B200), 1 = fused, 2 = wavefront;
-         * ctx->kernel: 0 = wavefront, 1 = fused */
-        if (cfg->kernel < 0 || cfg->kernel > 2)
-            return fail(ctx, GRMONTY_B200_EINVAL, "kernel must be 0 (default), 1 (fused) or 2 (wavefront)");
-        ctx->kernel = cfg->kernel == 2 ? 0 : 1;
-        if (const char *e = getenv("GRMONTY_B200_KERNEL")) /* A/B switch for tools/: "fused" or "wavefront" */
-            ctx->kernel = strcmp(e, "wavefront") == 0 ? 0 : 1;
         if (ctx->kernel == 0) {
             ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 384;
             const int slots = cfg->slots_per_thread > 0 ? cfg->slots_per_thread : 2;
@@ -557,8 +598,12 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
                             ctx->threads, want_bps);
             const size_t smem = transport_smem_bytes(ctx->threads);
             CK(cudaFuncSetAttribute((const void *)v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int occ = 0;
+            CK(cudaFuncSetAttribute((const void *)v->pipe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0, occ_pipe = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)v->fn, ctx->threads, smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pipe, (const void *)v->pipe_fn, ctx->threads, smem));
+            if (ctx->overlap)
+                occ = std::min(occ, occ_pipe); /* all blocks of the persistent launches must be co-resident */
             if (occ < 1)
                 return fail(ctx, GRMONTY_B200_ECUDA, "transport kernel does not fit on an SM");
             ctx->blocks_per_sm = std::min(occ, want_bps);
@@ -657,6 +702,9 @@ static void fill_args(grmonty_b200_ctx *ctx, const GmBiasStats &bias, const Debu
     args.snap_stride = ctx->snap_stride;
     args.wf_thr_interact = ctx->wf_thr_interact;
     args.wf_thr_service = ctx->wf_thr_service;
+    args.ctl = ctx->d_ctl;
+    args.qent = ctx->d_qent;
+    args.qcap = ctx->qcap;
     args.self = ctx->d_args;
 }
 
@@ -880,6 +928,255 @@ static int read_bias_stats(grmonty_b200_ctx *ctx, GmBiasStats *b) {
     return GRMONTY_B200_OK;
 }
 
+/* The pipelined scheduler (gm_pipeline.cuh): the generations of [first, last) in windows of as many generations as
+ * the pool holds, ONE persistent launch per window.  The host only prepares a window (birth of its primaries, queue
+ * reset, carried-over lineages) and collects it; the generation clock -- statistics, completion, opening of the next
+ * generations -- runs on the device and continues across windows. */
+static int run_range_pipelined(grmonty_b200_ctx *ctx, long long first, long long last) {
+    const long long world = ctx->cfg.world, rank = ctx->cfg.rank;
+    const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
+    /* ---- the generations of this call (same partition as the round-1 scheduler and the oracle) ---- */
+    struct Gen {
+        long long f0, count, pos_end;
+    };
+    std::vector<Gen> gens;
+    for (long long g_start = 0; g_start < last;) {
+        const long long g_end =
+            g_start + world * generation_size(g_start / world, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from,
+                                              ctx->gen_fine_div, ctx->gen_ramp);
+        const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
+        if (lo < hi) {
+            const long long f0 = lo + ((rank - lo % world) % world + world) % world;
+            gens.push_back({f0, f0 < hi ? (hi - f0 + world - 1) / world : 0, hi});
+        }
+        g_start = g_end;
+    }
+    const int n_real = (int)gens.size();
+    if (n_real == 0)
+        return GRMONTY_B200_OK;
+    const int n_desc = n_real + 1; /* + the final drain generation: no primaries, no attempt budget */
+    const long long spread = ctx->gen_budget_spread > 0 ? ctx->gen_budget_spread : 0;
+    std::vector<GenDesc> desc((size_t)n_desc);
+    for (int g = 0; g < n_real; ++g) {
+        desc[g].count = (unsigned long long)gens[g].count;
+        desc[g].prim_end = 0ull;
+        desc[g].carry_clock0 = spread > 0 ? -(int)(gens[g].count / spread) : 0;
+        desc[g].pad = 0;
+    }
+    desc[n_real] = GenDesc{0ull, 0ull, kClockForever, 0};
+    if ((size_t)n_desc > ctx->desc_cap) {
+        if (ctx->d_desc)
+            CK(cudaFree(ctx->d_desc));
+        ctx->d_desc = nullptr;
+        ctx->desc_cap = std::max<size_t>(1024, (size_t)n_desc * 2);
+        CK(cudaMalloc(&ctx->d_desc, ctx->desc_cap * sizeof(GenDesc)));
+    }
+    /* ---- generation clock: the first two generations use the statistics as they stand (lag 1 from there on) ---- */
+    GmBiasStats bias;
+    ctx->h_bias_valid = false;
+    int rc = read_bias_stats(ctx, &bias);
+    if (rc)
+        return rc;
+    GenCtl h;
+    memset(&h, 0, sizeof(h));
+    for (int i = 0; i < 4; ++i) {
+        h.alloc[i] = i < n_desc ? desc[i].count : 0ull;
+        h.bias_den[i] = bias.bias_den;
+    }
+    h.n_desc = n_desc;
+    h.bias_norm = ctx->P.bias_norm;
+    h.desc = ctx->d_desc;
+    {
+        const char *e = getenv("GRMONTY_B200_WATCHDOG_S"); /* a launch that lost a record ends itself after this long */
+        h.t_limit = (unsigned long long)((e ? atof(e) : 120.0) * 1e9);
+    }
+    TransportArgs &args = ctx->h_args;
+    const DebugOut nodbg = {nullptr, nullptr, 0};
+    fill_args(ctx, bias, nodbg, ctx->budget, args);
+    /* the scatter queue of this scheduler: the fifth ring, its counters in the control line */
+    args.scatter.entries = ctx->d_qent + (size_t)4 * ctx->qcap;
+    args.scatter.capacity = ctx->qcap;
+    args.scatter.head = ctx->d_ctl->line + CW_SC_HEAD;
+    args.scatter.tail = ctx->d_ctl->line + CW_SC_TAIL;
+    args.zone_cost = nullptr;
+    CK(cudaMemcpyAsync(ctx->d_args, &args, sizeof(args), cudaMemcpyHostToDevice, ctx->stream));
+    static int trace = -1; /* GRMONTY_B200_TRACE=1: one line per launch on stderr */
+    if (trace < 0)
+        trace = getenv("GRMONTY_B200_TRACE") ? 1 : 0;
+
+    /* Primaries per window.  A window's records are its primaries, the lineages carried in and the scattered children
+     * it creates; how many children a primary has depends on the model (0.46 on the bench dump, 3 on the small test
+     * model, 9 in its first generations).  The first window assumes 15 per primary, later ones the measured ratio of
+     * the run so far with a margin of 1.5. */
+    long long w_cap = std::max<long long>(1024, (long long)(ctx->pool.capacity / 16));
+    unsigned long long n_carry_in = 0, created = 0, children_so_far = 0;
+    const size_t smem = transport_smem_bytes(ctx->threads);
+    for (int g0 = 0; g0 < n_desc;) {
+        /* ---- the window: generations g0 .. g1 - 1 (at least one), then the drain generation if they are the last ---- */
+        long long W = 0;
+        int g1 = g0;
+        while (g1 < n_real && (g1 == g0 || W + gens[g1].count <= w_cap)) {
+            W += gens[g1].count;
+            desc[g1].prim_end = (unsigned long long)W;
+            ++g1;
+        }
+        const bool final_window = g1 == n_real;
+        const int g_end = final_window ? n_desc : g1;
+        if (final_window)
+            desc[n_real].prim_end = (unsigned long long)W;
+        if ((unsigned long long)W + n_carry_in + (unsigned long long)W / 8 > ctx->pool.capacity)
+            return fail(ctx, GRMONTY_B200_EQUEUE,
+                        "a generation of %lld primaries (+ %llu carried lineages) does not fit the photon pool "
+                        "(capacity %u): raise queue_capacity or lower gen_cap", W, n_carry_in, ctx->pool.capacity);
+        CK(cudaMemcpyAsync(ctx->d_desc, desc.data(), (size_t)n_desc * sizeof(GenDesc), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        /* ---- queues and control line (the rings clean themselves: a consumer writes 0 back) ---- */
+        if (ctx->q_dirty)
+            CK(cudaMemsetAsync(ctx->d_qent, 0, (size_t)5 * ctx->qcap * sizeof(unsigned int), ctx->stream));
+        ctx->q_dirty = true; /* until this launch has ended cleanly */
+        memset(h.line, 0, sizeof(h.line));
+        const int p0 = g0 & 1;
+        h.line[CW_L0_TAIL + kCwLStride * p0] = n_carry_in; /* lineages suspended into g0 by the previous window */
+        h.line[CW_L0_LIM + kCwLStride * p0] = n_carry_in;  /* frozen: what follows them will be for g0 + 2 */
+        h.line[CW_L0_LIM + kCwLStride * (p0 ^ 1)] = kGateLive;
+        h.line[CW_PRIM_LIM] = desc[std::min(g0 + 1, g_end - 1)].prim_end; /* g0 and g0 + 1 are open */
+        h.line[CW_COMPLETE] = (unsigned long long)g0;
+        h.g_end = g_end;
+        h.t_start = 0ull;
+        h.lock = 0u;
+        if (g0 == 0) {
+            CK(cudaMemcpyAsync(ctx->d_ctl, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        } else { /* the ring (alloc / done / statistics / denominators) lives on: only the line and the launch's end */
+            CK(cudaMemcpyAsync(ctx->d_ctl->line, h.line, sizeof(h.line), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(&ctx->d_ctl->lock, &h.lock, 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(&ctx->d_ctl->t_start, &h.t_start, sizeof(h.t_start), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        unsigned long long *qc = ctx->h_qc;
+        qc[0] = (unsigned long long)W + n_carry_in; /* records in use: primaries, then the carried lineages */
+        qc[1] = 0ull;
+        CK(cudaMemcpyAsync(ctx->d_qctr, qc, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+        /* ---- birth of the window's primaries, generation by generation (records only: lanes take them by index) ---- */
+        CK(cudaEventRecord(ctx->ev2, ctx->stream));
+        for (int g = g0; g < g1; ++g) {
+            if (gens[g].count <= 0)
+                continue;
+            const int bb = 128;
+            const int nb = (int)std::min<long long>((gens[g].count + bb - 1) / bb, (long long)ctx->sm_count * 16);
+            birth_kernel<<<nb, bb, 0, ctx->stream>>>(args, ctx->d_zones, ctx->d_prefix, gens[g].f0, world, gens[g].count,
+                                                     ctx->perm_mult, ctx->total, spread, nullptr,
+                                                     (unsigned int)(desc[g].prim_end - desc[g].count),
+                                                     (g & 3) << kTagShift, 0);
+            CK(cudaGetLastError());
+            ctx->stats.n_kernel_launches += 1;
+        }
+        if (n_carry_in > 0) {
+            carry_copy_kernel<<<(unsigned)((n_carry_in + 127) / 128), 128, 0, ctx->stream>>>(
+                ctx->pool, (unsigned int)W, ctx->stage, 0u, nullptr, (unsigned int)n_carry_in,
+                ctx->d_qent + (size_t)(2 + p0) * ctx->qcap, 0, true);
+            CK(cudaGetLastError());
+            ctx->stats.n_kernel_launches += 1;
+        }
+        CK(cudaEventRecord(ctx->ev3, ctx->stream));
+        /* ---- the launch ---- */
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        v->pipe_fn<<<(unsigned)ctx->grid_blocks, ctx->threads, smem, ctx->stream>>>(args);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        unsigned long long *pin = ctx->h_pin; /* control words, then the error word and the records allocated */
+        constexpr int kPinErr = CW_WORDS, kPinRec = CW_WORDS + 1;
+        pin[kPinErr] = 0ull;
+        CK(cudaMemcpyAsync(pin, ctx->d_ctl->line, CW_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(pin + kPinErr, ctx->d_error, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(pin + kPinRec, ctx->d_qctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f, ms_birth = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        CK(cudaEventElapsedTime(&ms_birth, ctx->ev2, ctx->ev3));
+        ctx->stats.kernel_ms += ms + ms_birth;
+        ctx->stats.transport_ms += ms;
+        ctx->stats.n_kernel_launches += 1;
+        ctx->stats.n_generations += (uint64_t)(g_end - g0);
+        ctx->stats.queue_high_water = std::max<uint64_t>(ctx->stats.queue_high_water, pin[kPinRec]);
+        const unsigned int err = (unsigned int)pin[kPinErr];
+        ctx->host_tracked += (unsigned long long)W;
+        created += (unsigned long long)W;
+        children_so_far += pin[kPinRec] > (unsigned long long)W + n_carry_in ? pin[kPinRec] - (unsigned long long)W - n_carry_in : 0ull;
+        {
+            const double per_primary = 1.0 + 1.5 * (double)children_so_far / (double)std::max<unsigned long long>(created, 1) + 0.15;
+            w_cap = std::max<long long>(1024, (long long)((double)ctx->pool.capacity / per_primary));
+        }
+        if (trace)
+            fprintf(stderr, "[grmonty_b200] window generations %d..%d (%lld primaries, %llu carried in): birth %.3f ms, "
+                            "transport %.3f ms, records %llu, runnable %llu + %llu, limbo %llu + %llu, scatter %llu, "
+                            "complete %llu, error %u\n",
+                    g0, g_end - 1, W, n_carry_in, ms_birth, ms, pin[kPinRec], pin[CW_R0_TAIL], pin[CW_R1_TAIL],
+                    pin[CW_L0_TAIL], pin[CW_L1_TAIL], pin[CW_SC_TAIL], pin[CW_COMPLETE], err);
+        if (err & 1u)
+            return fail(ctx, GRMONTY_B200_EQUEUE,
+                        "device photon pool/queue overflow: %llu records, queue tails %llu %llu %llu %llu, scatter %llu "
+                        "(capacity %u); raise queue_capacity or lower gen_cap", pin[kPinRec], pin[CW_R0_TAIL],
+                        pin[CW_R1_TAIL], pin[CW_L0_TAIL], pin[CW_L1_TAIL], pin[CW_SC_TAIL], ctx->pool.capacity);
+        if (err & 2u)
+            return fail(ctx, GRMONTY_B200_ECUDA, "device photon queue: entry publication timeout");
+        if ((err & 8u) || (long long)pin[CW_COMPLETE] < (long long)g_end) {
+            GenCtl dbg;
+            cudaMemcpy(&dbg, ctx->d_ctl, sizeof(dbg), cudaMemcpyDeviceToHost);
+            return fail(ctx, GRMONTY_B200_ECUDA,
+                        "generation pipeline stalled: %llu of %d generations complete (watchdog); ring alloc %llu %llu %llu "
+                        "%llu done %llu %llu %llu %llu; R %llu/%llu %llu/%llu L %llu/%llu<%llu %llu/%llu<%llu prim %llu/%llu "
+                        "scatter %llu/%llu", pin[CW_COMPLETE], g_end, dbg.alloc[0], dbg.alloc[1], dbg.alloc[2], dbg.alloc[3],
+                        dbg.done[0], dbg.done[1], dbg.done[2], dbg.done[3], pin[CW_R0_HEAD], pin[CW_R0_TAIL], pin[CW_R1_HEAD],
+                        pin[CW_R1_TAIL], pin[CW_L0_HEAD], pin[CW_L0_TAIL], pin[CW_L0_LIM], pin[CW_L1_HEAD], pin[CW_L1_TAIL],
+                        pin[CW_L1_LIM], pin[CW_PRIM_CUR], pin[CW_PRIM_LIM], pin[CW_SC_HEAD], pin[CW_SC_TAIL]);
+        }
+        /* ---- lineages suspended into the next window's first generation: to the staging pool ---- */
+        n_carry_in = 0;
+        if (!final_window) {
+            const int pe = g_end & 1;
+            /* from the frozen gate, not from the head: claims may have run ahead of the gate (tickets that never resolved) */
+            const unsigned long long lh = pin[CW_L0_LIM + kCwLStride * pe], lt = pin[CW_L0_TAIL + kCwLStride * pe];
+            const unsigned long long n = lt > lh ? lt - lh : 0ull;
+            if (n > ctx->stage.capacity)
+                return fail(ctx, GRMONTY_B200_EQUEUE, "carry-over staging pool overflow: %llu records (capacity %u)", n,
+                            ctx->stage.capacity);
+            /* the entries lh .. lt - 1 of the ring, in up to two contiguous pieces; they are cleared afterwards */
+            unsigned long long done_n = 0;
+            while (done_n < n) {
+                const unsigned long long at = (lh + done_n) & (unsigned long long)(ctx->qcap - 1u);
+                const unsigned long long piece = std::min<unsigned long long>(n - done_n, ctx->qcap - at);
+                unsigned int *list = ctx->d_qent + (size_t)(2 + pe) * ctx->qcap + at;
+                carry_copy_kernel<<<(unsigned)((piece + 127) / 128), 128, 0, ctx->stream>>>(
+                    ctx->stage, (unsigned int)done_n, ctx->pool, 0u, list, (unsigned int)piece, nullptr, 0, true);
+                CK(cudaGetLastError());
+                CK(cudaMemsetAsync(list, 0, piece * sizeof(unsigned int), ctx->stream));
+                ctx->stats.n_kernel_launches += 1;
+                done_n += piece;
+            }
+            n_carry_in = n;
+        }
+        ctx->q_dirty = false;
+        if (trace > 0) { /* per-generation timeline of the launch (device clock, ms since the first opening) */
+            CK(cudaMemcpy(desc.data(), ctx->d_desc, (size_t)n_desc * sizeof(GenDesc), cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (int g = g0; g < g_end; ++g)
+                if (desc[g].t_done)
+                    t0 = std::min(t0, desc[g].t_open ? desc[g].t_open : desc[g].t_done);
+            for (int g = g0; g < g_end; ++g)
+                fprintf(stderr, "    generation %d: %llu primaries, opened %.3f ms, complete %.3f ms\n", g, desc[g].count,
+                        desc[g].t_open ? (desc[g].t_open - t0) * 1e-6 : 0.0, (desc[g].t_done - t0) * 1e-6);
+        }
+        if (ctx->progress)
+            ctx->progress(ctx->progress_user, gens[g1 - 1].pos_end, ctx->total);
+        g0 = g_end;
+    }
+    ctx->h_bias_valid = false;
+    /* counters[0] = created (host-side count; the reference counts primaries only, harm_model.cpp:395) */
+    add_u64_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_counters, created);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GRMONTY_B200_OK;
+}
+
 int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
     if (!ctx)
         return GRMONTY_B200_EINVAL;
@@ -888,6 +1185,8 @@ int grmonty_b200_run_range(grmonty_b200_ctx *ctx, int64_t first, int64_t last) {
         last = ctx->total;
     if (first < 0)
         first = 0;
+    if (ctx->overlap && ctx->kernel == 1)
+        return run_range_pipelined(ctx, first, last);
     const long long world = ctx->cfg.world, rank = ctx->cfg.rank;
     const DebugOut nodbg = {nullptr, nullptr, 0};
     /* a batch never fills more than a quarter of the pool with primaries: the rest is room for carried
@@ -1168,6 +1467,10 @@ void grmonty_b200_destroy(grmonty_b200_ctx *ctx) {
         g_arena_cache.push_back(ctx->arena);
         ctx->arena = DeviceArena{};
     }
+    if (ctx->d_desc)
+        cudaFree(ctx->d_desc);
+    if (ctx->h_pin)
+        cudaFreeHost(ctx->h_pin);
     if (ctx->ev0)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)

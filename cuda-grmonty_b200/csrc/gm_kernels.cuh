@@ -178,18 +178,21 @@ __host__ __device__ __forceinline__ long long permute_position(long long j, long
 __device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigned int slot, const double x[4],
                                                  const double k[4], double w, double e, double x1i, double x2i,
                                                  double n_e_0, double theta_e_0, double b_0, double e_0,
-                                                 int n_scatt, const Rng &rng, int clock0) {
+                                                 int n_scatt, const Rng &rng, int clock0, int ns_bits = -1) {
+    /* ns_bits >= 0 (pipelined generations): generation tag bits of the record; the bias is left to the pick-up
+     * (kFreshBit), because the generation's statistics are not frozen yet when its primaries are born */
     const GmParams &P = A.P;
     const GeoPoint q = geo_point(P, x[1], x[2]);
     const MetricCov g = metric_cov(P, q);
     Fluid f;
     fluid_params(P, x[1], x[2], g, q, f);
-    const TrackInit t = track_init(P, A.bias, k, w, f);
+    const bool lazy = ns_bits >= 0;
+    const TrackInit t = track_init(P, A.bias.bias_den, k, w, f, lazy);
     Connection c;
     connection_eval(P, q, c);
     double dk[4];
     geodesic_rhs(c, k, dk);
-    pool_store_hot(A.pool, slot, x, k, dk, w, e, 0.0, 0.0, t, rng, 0);
+    pool_store_hot(A.pool, slot, x, k, dk, w, e, 0.0, 0.0, t, rng, lazy ? (ns_bits | (t.ne_pos ? kFreshBit : 0)) : 0);
     pstore(A.pool, P_E, slot, e);
     pstore(A.pool, P_X1I, slot, x1i);
     pstore(A.pool, P_X2I, slot, x2i);
@@ -208,17 +211,20 @@ __device__ __forceinline__ void store_new_photon(const TransportArgs &A, unsigne
 /* `order` (optional): the batch's primary indices sorted by the expected lifetime of their birth zone, longest first.
  * Lanes take pool slots in order, so the long-lived lineages start first and the generation's drain is short; the
  * results do not depend on the order (statistics are frozen within a generation). */
+/* `slot0`, `ns_bits` >= 0 (pipelined generations): the records go to pool slots slot0 .. slot0 + count - 1 with the
+ * generation tag in their n_step word, and there are no queue entries (lanes take them by index) */
 __global__ void birth_kernel(TransportArgs A, const ZoneData *zones, const long long *prefix, long long first,
                              long long stride, long long count, long long mult, long long total, long long spread,
-                             const long long *order) {
+                             const long long *order, unsigned int slot0 = 0u, int ns_bits = -1, int clock_base = 0) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count;
          t += (long long)gridDim.x * blockDim.x) {
         Birth B;
         make_primary(A.P, zones, prefix, order ? order[t] : permute_position(first + t * stride, mult, total), B);
-        const int clock0 = spread > 0 ? -(int)((count - 1 - t) / spread) : 0;
-        store_new_photon(A, (unsigned int)t, B.x, B.k, B.w, B.e, B.x[1], B.x[2], B.n_e, B.theta_e, B.b, B.e, 0,
-                         B.rng, clock0);
-        A.ready.entries[t] = (unsigned int)t + 1u;
+        const int clock0 = clock_base + (spread > 0 ? -(int)((count - 1 - t) / spread) : 0);
+        store_new_photon(A, slot0 + (unsigned int)t, B.x, B.k, B.w, B.e, B.x[1], B.x[2], B.n_e, B.theta_e, B.b, B.e, 0,
+                         B.rng, clock0, ns_bits);
+        if (ns_bits < 0)
+            A.ready.entries[t] = (unsigned int)t + 1u;
     }
 }
 
@@ -244,8 +250,11 @@ __global__ void order_key_kernel(const long long *prefix, int n0, int n1, const 
 
 /* copy carried records between pools: dst slot (dst0 + i) <- src slot (list ? list[i] - 1 : src0 + i);
  * when `ready` is given the destination slots are also published on that queue at position dst0 + i */
+/* keep_clock (pipelined generations): the record's own clock is copied (suspend_photon_pipe set it) and the queue
+ * entries are written from index 0 (the limbo queue of the next launch's first generation) */
 __global__ void carry_copy_kernel(PhotonPool dst, unsigned int dst0, PhotonPool src, unsigned int src0,
-                                  const unsigned int *list, unsigned int n, unsigned int *ready_entries, int clock0) {
+                                  const unsigned int *list, unsigned int n, unsigned int *ready_entries, int clock0,
+                                  bool keep_clock = false) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
@@ -255,9 +264,9 @@ __global__ void carry_copy_kernel(PhotonPool dst, unsigned int dst0, PhotonPool 
     dst.rng[d] = src.rng[s];
     dst.n_scatt[d] = src.n_scatt[s];
     dst.n_step[d] = src.n_step[s];
-    dst.gclock[d] = clock0;
+    dst.gclock[d] = keep_clock ? src.gclock[s] : clock0;
     if (ready_entries)
-        ready_entries[d] = d + 1u;
+        ready_entries[keep_clock ? i : d] = d + 1u;
 }
 
 /* counters[0] += created, in stream order (the host counts primaries; harm_model.cpp:395) */

@@ -222,13 +222,18 @@ __device__ __forceinline__ double alpha_inv_abs_sin(const GmParams &P, double nu
     return alpha_inv_abs_sin_l(P, nu, theta_e, n_e, b, sin_th, fm::log_(fm::max_(theta_e, 1.0e-300)));
 }
 
-/* reference bias_func, harm_model.cpp:1391-1404, with the generation's frozen statistics */
-__device__ __forceinline__ double bias_func(const GmParams &P, const GmBiasStats &s, double theta_e, double w) {
+/* reference bias_func, harm_model.cpp:1391-1404, with the generation's frozen statistics: `bias_den` is
+ * bias_norm * max_tau_scatt * (n_scatt / (n_recorded + 1) + 2), the same for every photon of a generation */
+__device__ __forceinline__ double bias_func_den(double theta_e, double w, double bias_den) {
     const double mx = w * (0.5 / kWeightMin);
-    double bias = fm::div(100.0 * theta_e * theta_e, s.bias_den);
+    double bias = fm::div(100.0 * theta_e * theta_e, bias_den);
     bias = fm::max_(bias, kTpOverTe);
     bias = fm::min_(bias, mx);
     return bias * (1.0 / kTpOverTe);
+}
+__device__ __forceinline__ double bias_func(const GmParams &P, const GmBiasStats &s, double theta_e, double w) {
+    (void)P;
+    return bias_func_den(theta_e, w, s.bias_den);
 }
 
 /* both opacities at once for a photon with wave-vector k in fluid f */

@@ -83,6 +83,48 @@ struct Accumulators {
     unsigned int *error;              /* bit0 pool/queue overflow, bit1 queue entry timeout */
 };
 
+/* ---- generation pipeline (gm_pipeline.cuh): device-side generation clock ---------------------------------- */
+/* the hot control words of the pipelined kernel, one 128-byte line per queue (the fetch-adds and polls of different
+ * queues then go to different L2 slices instead of serialising on one line) */
+enum CtlWord {
+    CW_R0_HEAD = 0, CW_R0_TAIL = 1,                   /* runnable queues by generation parity: lines 0 and 1 */
+    CW_R1_HEAD = 16, CW_R1_TAIL = 17,
+    CW_L0_HEAD = 32, CW_L0_TAIL = 33, CW_L0_LIM = 34, /* limbo queues (suspended lineages, next generation): 2 and 3 */
+    CW_L1_HEAD = 48, CW_L1_TAIL = 49, CW_L1_LIM = 50,
+    CW_PRIM_CUR = 64, CW_PRIM_LIM = 65, /* next primary record to issue / end of the open generations' records */
+    CW_COMPLETE = 80,                   /* number of complete generations = index of the oldest incomplete one */
+    CW_SC_HEAD = 96, CW_SC_TAIL = 97,   /* scatter queue */
+    CW_WORDS = 112
+};
+constexpr int kCwRStride = 16, kCwLStride = 16; /* word distance between the two parities of a queue kind */
+constexpr unsigned long long kGateLive = ~0ull; /* CW_L*_LIM: every published entry may be taken */
+constexpr int kClockForever = -(1 << 30);       /* lineage clock of the final drain generation: no budget */
+constexpr int kTagShift = 28;                   /* bits 28-29 of a record's n_step word: generation & 3 */
+constexpr int kFreshBit = 1 << 27;              /* n_step word: P_BI holds theta_e, bias to be taken at pick-up */
+constexpr int kNStepMask = (1 << 24) - 1;
+
+struct GenDesc {
+    unsigned long long count;    /* primaries of this rank in the generation */
+    unsigned long long prim_end; /* end (exclusive) of the generation's records in the current launch's pool */
+    int carry_clock0;            /* lineage clock a photon suspended into this generation starts with */
+    int pad;
+    unsigned long long t_open, t_done; /* %globaltimer when the generation was opened / completed (diagnostics) */
+};
+
+struct GenCtl {
+    unsigned long long line[CW_WORDS];
+    unsigned long long alloc[4], done[4]; /* ring by generation & 3: lineage records entered / left the generation */
+    unsigned long long acc_scatt[4], acc_rec[4], acc_maxtau[4]; /* statistics recorded in the generation */
+    double bias_den[4];                   /* frozen bias denominator of the generation (see GmBiasStats) */
+    unsigned int lock;
+    int g_end;  /* the launch ends when line[CW_COMPLETE] reaches this */
+    int n_desc; /* generations of the run (incl. the final drain generation) */
+    int pad;
+    double bias_norm;
+    const GenDesc *desc;
+    unsigned long long t_start, t_limit; /* watchdog: %globaltimer at launch, nanoseconds allowed */
+};
+
 struct TransportArgs {
     GmParams P;
     GmBiasStats bias;
@@ -101,6 +143,10 @@ struct TransportArgs {
     double *snap;
     unsigned int snap_stride;
     int wf_thr_interact, wf_thr_service;
+    /* pipelined kernel: control block, and the four queues R0 R1 L0 L1 (qcap entries each, contiguous) */
+    GenCtl *ctl;
+    unsigned int *qent;
+    unsigned int qcap;
     /* device-global copy of this very struct: out-of-line (cold) stages take it by pointer so that the kernel
      * parameter itself never has its address taken and stays in the constant bank for the hot loop */
     const TransportArgs *self;
@@ -148,6 +194,24 @@ __device__ __forceinline__ void queue_push(const TransportArgs &A, const SlotQue
         return;
     }
     *reinterpret_cast<volatile unsigned int *>(q.entries + pos) = slot + 1u;
+}
+
+/* Ring form of the same queue (pipelined kernel): head and tail count positions without bound, position p lives in
+ * entry p & (capacity - 1) (capacity is a power of two), and the consumer of a position writes 0 back.  The live
+ * entries of a queue never exceed the number of pool records, so with capacity >= pool capacity a producer finds its
+ * entry free; it waits for the 0 all the same (the consumer of the position one lap earlier may still be reading). */
+__device__ __forceinline__ void queue_push_ring(const TransportArgs &A, const SlotQueue &q, unsigned int slot) {
+    __threadfence();
+    const unsigned long long pos = atomicAdd(q.tail, 1ull);
+    unsigned int *e = q.entries + (pos & (unsigned long long)(q.capacity - 1u));
+    unsigned int spins = 0;
+    while (ld_volatile_u32(e) != 0u) {
+        if (++spins > (1u << 24)) {
+            atomicOr(A.A.error, 1u);
+            return;
+        }
+    }
+    *reinterpret_cast<volatile unsigned int *>(e) = slot + 1u;
 }
 
 /* Warp-collective pop: lanes with `want` set receive a slot (returns true) if the queue has one.
@@ -278,14 +342,16 @@ struct TrackInit {
     bool ne_pos;
 };
 
-__device__ __forceinline__ TrackInit track_init(const GmParams &P, const GmBiasStats &bias, const double k[4],
-                                                double w, const Fluid &f) {
+/* `lazy`: the bias is taken when the photon is picked up (pipelined generations: a primary is born before its
+ * generation's statistics are frozen); bi then holds theta_e */
+__device__ __forceinline__ TrackInit track_init(const GmParams &P, double bias_den, const double k[4],
+                                                double w, const Fluid &f, bool lazy = false) {
     TrackInit t;
     t.ne_pos = f.n_e > 0.0;
     if (t.ne_pos) {
         double nu;
         opacities(P, k, f, nu, t.alpha_scatt, t.alpha_abs);
-        t.bi = bias_func(P, bias, f.theta_e, w);
+        t.bi = lazy ? f.theta_e : bias_func_den(f.theta_e, w, bias_den);
     } else {
         t.alpha_scatt = 0.0;
         t.alpha_abs = 0.0;
@@ -296,15 +362,19 @@ __device__ __forceinline__ TrackInit track_init(const GmParams &P, const GmBiasS
 
 /* reference record_super_photon, harm_model.cpp:1291-1335.  Lanes of the calling (possibly partial) warp
  * that hit the same spectrum bin are combined before the global atomics. */
+/* PIPE: the bias statistics (maximum of tau_scatt, scatterings and records) go to the accumulators of the photon's
+ * generation `tag`; the generation clock folds them into the run totals when the generation is complete. */
+template <bool PIPE = false>
 __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsigned int slot, double x2, double x3,
-                                                    double w, double tau_abs, double tau_scatt) {
+                                                    double w, double tau_abs, double tau_scatt, int tag = 0) {
     const GmParams &P = A.P;
     const double e = pload(A.pool, P_E, slot);
     bool ok = !(isnan(w) || isnan(e));
     int bin = -1;
     int n_scatt = 0;
     if (ok) {
-        atomicMax(A.A.max_tau_bits, (unsigned long long)__double_as_longlong(fmax(tau_scatt, 0.0)));
+        atomicMax(PIPE ? A.ctl->acc_maxtau + tag : A.A.max_tau_bits,
+                  (unsigned long long)__double_as_longlong(fmax(tau_scatt, 0.0)));
         const double dx2 = (P.x_stop2 - P.x_start2) / (2.0 * kNThBins);
         int ix2;
         if (x2 < 0.5 * (P.x_start2 + P.x_stop2))
@@ -337,7 +407,8 @@ __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsi
     }
     /* warp-aggregate by bin among the lanes that are here together */
     const unsigned int active = __activemask();
-    const unsigned int peers = __match_any_sync(active, bin);
+    /* (pipelined: lanes of different generations in one bin are not combined -- the counters are per generation) */
+    const unsigned int peers = __match_any_sync(active, PIPE && bin >= 0 ? bin * 4 + tag : bin);
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
     unsigned long long cnt_scatt = (unsigned long long)n_scatt;
@@ -362,9 +433,9 @@ __device__ __forceinline__ void record_super_photon(const TransportArgs &A, unsi
 #pragma unroll
         for (int q = 0; q < 12; ++q)
             atomicAdd(s + q, v[q]);
-        atomicAdd(A.A.counters + 2, (unsigned long long)__popc(peers));
+        atomicAdd(PIPE ? A.ctl->acc_rec + tag : A.A.counters + 2, (unsigned long long)__popc(peers));
         if (cnt_scatt)
-            atomicAdd(A.A.counters + 1, cnt_scatt);
+            atomicAdd(PIPE ? A.ctl->acc_scatt + tag : A.A.counters + 1, cnt_scatt);
     }
 }
 
@@ -383,8 +454,9 @@ struct Live {
     int status;
 };
 
-/* take a photon from its pool record: loads only (the producer computed every derived quantity) */
-__device__ __forceinline__ void live_load(const TransportArgs &A, unsigned int slot, Live &L) {
+/* take a photon from its pool record: loads only (the producer computed every derived quantity); returns the
+ * record's n_step word (the pipelined kernel keeps its generation tag there) */
+__device__ __forceinline__ int live_load(const TransportArgs &A, unsigned int slot, Live &L) {
     const PhotonPool &pool = A.pool;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -413,6 +485,7 @@ __device__ __forceinline__ void live_load(const TransportArgs &A, unsigned int s
     L.level = 0;
     L.dl = 0.0;
     L.status = 0;
+    return ns;
 }
 
 /* work counters kept per thread and flushed once */
@@ -430,9 +503,12 @@ enum StepResult { STEP_CONTINUE = 0, STEP_FINISHED = 1, STEP_SCATTER = 2, STEP_S
  * STEP_SCATTER with the parked record's values in L (w attenuated, tau_abs / tau_scatt at the scattering point,
  * alpha_scatt = dl * frac, alpha_abs = weight of the child, rng before the child-identity draw) and the record is
  * written by the service phase (wf_park), where all lanes that have something rare to do are together. */
-template <bool DEFER_PARK = false>
+/* PIPE (pipelined generations): the bias denominator is the one of the photon's generation (sbias[tag], a copy of
+ * GenCtl::bias_den in shared memory; tag = bits 4-5 of L.status), and a parked record keeps the tag. */
+template <bool DEFER_PARK = false, bool PIPE = false>
 __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, const GeoPoint &q,
-                                               const double *snap, int snap_stride, Work &wk) {
+                                               const double *snap, int snap_stride, Work &wk,
+                                               const double *sbias = nullptr) {
     const GmParams &P = A.P;
     ++wk.interactions;
     /* q = geometry at the new position, already evaluated by the accepted push attempt */
@@ -454,7 +530,7 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
     const double l_nu = fm::log_(nu_e), l_theta = fm::log_(te_e);
     const double a_sf = alpha_inv_scatt_l(P, nu_e, te_e, ne_e, l_nu, l_theta);
     const double a_af = alpha_inv_abs_sin_l(P, nu_e, te_e, ne_e, b_e, fm::sqrt_(1.0 - mu * mu), l_theta);
-    const double bf = bias_func(P, A.bias, te_e, L.w);
+    const double bf = bias_func_den(te_e, L.w, PIPE ? sbias[(L.status >> 4) & 3] : A.bias.bias_den);
     double d_tau_scatt, d_tau_abs, bias;
     if (outside) {
         d_tau_scatt = 0.5 * L.alpha_scatt * P.d_tau_k * L.dl;
@@ -528,9 +604,12 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
             pstore(pool, P_ALPHA_ABS, s, w_child);
             __stcg(pool.rng + s, make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr));
             __stcg(pool.crng + s, make_uint4(crng.id0, crng.id1, crng.id2, crng.ctr));
-            __stcg(pool.n_step + s, L.n_step);
+            __stcg(pool.n_step + s, PIPE ? (L.n_step | (((L.status >> 4) & 3) << kTagShift)) : L.n_step);
             __stcg(pool.gclock + s, L.clock);
-            queue_push(A, A.scatter, s);
+            if (PIPE)
+                queue_push_ring(A, A.scatter, s);
+            else
+                queue_push(A, A.scatter, s);
             res = STEP_SCATTER;
         }
     } else if (d_tau_abs > 100) {
@@ -553,8 +632,9 @@ __device__ __forceinline__ StepResult interact(const TransportArgs &A, Live &L, 
  * next one.  (With early returns the compiler let the lanes that came through phase A and those that were in
  * the middle of a halved step run phase B separately: ncu showed 15.6 of ~27 live threads per instruction.)
  * `record` tells whether a finished photon escaped through r > r_max (reference :1066-1068). */
+template <bool PIPE = false>
 __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, unsigned int live, double *snap,
-                                              int snap_stride, Work &wk, bool &record) {
+                                              int snap_stride, Work &wk, bool &record, const double *sbias = nullptr) {
     const GmParams &P = A.P;
     record = false;
     StepResult st = STEP_CONTINUE;
@@ -627,7 +707,7 @@ __device__ __forceinline__ StepResult advance(const TransportArgs &A, Live &L, u
             st = STEP_FINISHED;
         } else {
             if (L.alpha_abs > 0.0 || L.alpha_scatt > 0.0 || L.ne_pos)
-                st = interact<false>(A, L, q, snap, snap_stride, wk);
+                st = interact<false, PIPE>(A, L, q, snap, snap_stride, wk, sbias);
             if (st == STEP_CONTINUE) {
                 ++L.n_step;
                 if (L.n_step > kMaxNStep)
@@ -685,12 +765,16 @@ __device__ __noinline__ void suspend_photon(const TransportArgs *Ag, unsigned in
 
 /* The scattering stage for one parked photon (reference harm_model.cpp:1005-1039 + scatter_super_photon).
  * Called with all lanes of a warp holding a parked photon (or idle).  The parent and the child that continue
- * are pushed on the ready queue. */
+ * are pushed on the ready queue.
+ * PIPE (pipelined generations): the record's n_step word carries the generation tag; statistics are those of that
+ * generation, the child is counted in it (GenCtl::alloc) and both go to the runnable queue of its parity. */
 struct ScatterStageResult {
     int done;                                  /* photons whose life ended here (0 or 1) */
     unsigned int attempts, scatters, children; /* work counters, returned by value (see stop_criterion_roulette) */
+    int tag;                                   /* PIPE: generation tag of the lineage */
 };
-__device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag, unsigned int slot) {
+template <bool PIPE>
+__device__ __noinline__ ScatterStageResult scatter_stage_t(const TransportArgs *Ag, unsigned int slot) {
     unsigned int n_attempts = 0, n_scatters = 0, n_children = 0;
     const TransportArgs &A = *Ag;
     const GmParams &P = A.P;
@@ -709,8 +793,15 @@ __device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag
     const double w_child = pload(pool, P_ALPHA_ABS, slot);
     const uint4 r4 = __ldcg(pool.rng + slot);
     Rng rng = {r4.x, r4.y, r4.z, r4.w};
-    int n_step = __ldcg(pool.n_step + slot) & (kNeposBit - 1);
+    const int ns_word = __ldcg(pool.n_step + slot);
+    const int tag = PIPE ? (ns_word >> kTagShift) & 3 : 0;
+    const int tag_bits = PIPE ? tag << kTagShift : 0;
+    int n_step = ns_word & (PIPE ? kNStepMask : kNeposBit - 1);
     int clock = __ldcg(pool.gclock + slot);
+    const double bias_den = PIPE ? __ldcg(A.ctl->bias_den + tag) : A.bias.bias_den;
+    const SlotQueue ready_q = PIPE ? SlotQueue{A.qent + (size_t)(tag & 1) * A.qcap, A.ctl->line + CW_R0_HEAD + kCwRStride * (tag & 1),
+                                               A.ctl->line + CW_R0_TAIL + kCwRStride * (tag & 1), A.qcap}
+                                   : A.ready;
 
     /* back up to the scattering point */
     {
@@ -730,8 +821,8 @@ __device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag
         if (w < 1.0e-100) {
             if (A.D.status && slot < A.D.n)
                 A.D.status[slot] = 4 | 2;
-            return ScatterStageResult{1, n_attempts, n_scatters, n_children}; /* k could not be put back on the light
-                                                                                * cone (:1018-1021): dropped */
+            return ScatterStageResult{1, n_attempts, n_scatters, n_children, tag}; /* k could not be put back on the
+                                                                                     * light cone (:1018-1021): dropped */
         }
         if (child_ok) {
             unsigned int cs;
@@ -742,8 +833,8 @@ __device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag
                 connection_eval(P, q, c);
                 double dkc[4];
                 geodesic_rhs(c, ch.k, dkc);
-                const TrackInit tc = track_init(P, A.bias, ch.k, w_child, f);
-                pool_store_hot(pool, cs, x, ch.k, dkc, w_child, ch.e, 0.0, 0.0, tc, crng, 0);
+                const TrackInit tc = track_init(P, bias_den, ch.k, w_child, f);
+                pool_store_hot(pool, cs, x, ch.k, dkc, w_child, ch.e, 0.0, 0.0, tc, crng, tag_bits);
                 pstore(pool, P_E, cs, ch.e);
                 pstore(pool, P_X1I, cs, x[1]);
                 pstore(pool, P_X2I, cs, x[2]);
@@ -754,10 +845,15 @@ __device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag
                 __stcg(pool.n_scatt + cs, __ldcg(pool.n_scatt + slot) + 1);
                 __stcg(pool.gclock + cs, clock); /* the child inherits its lineage's clock */
                 ++n_children;
-                queue_push(A, A.ready, cs);
+                if (PIPE) {
+                    atomicAdd(A.ctl->alloc + tag, 1ull); /* before the record is published */
+                    queue_push_ring(A, ready_q, cs);
+                } else {
+                    queue_push(A, ready_q, cs);
+                }
             }
         }
-        ti = track_init(P, A.bias, k, w, f);
+        ti = track_init(P, bias_den, k, w, f);
     } else {
         /* left the grid while backing up (the reference reads uninitialised data here, Appendix A.15) */
         ti.alpha_scatt = 0.0;
@@ -772,12 +868,49 @@ __device__ __noinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag
     if (n_step > kMaxNStep) {
         if (A.D.status && slot < A.D.n)
             atomicOr(A.D.status + slot, 4);
-        return ScatterStageResult{1, n_attempts, n_scatters, n_children};
+        return ScatterStageResult{1, n_attempts, n_scatters, n_children, tag};
     }
-    pool_store_hot(pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, ti, rng, n_step);
+    pool_store_hot(pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, ti, rng, n_step | tag_bits);
     __stcg(pool.gclock + slot, clock);
-    queue_push(A, A.ready, slot);
-    return ScatterStageResult{0, n_attempts, n_scatters, n_children};
+    if (PIPE)
+        queue_push_ring(A, ready_q, slot);
+    else
+        queue_push(A, ready_q, slot);
+    return ScatterStageResult{0, n_attempts, n_scatters, n_children, tag};
+}
+__device__ __forceinline__ ScatterStageResult scatter_stage(const TransportArgs *Ag, unsigned int slot) {
+    return scatter_stage_t<false>(Ag, slot);
+}
+
+/* Pipelined generations: suspend a photon of generation `g` (tag g & 3) at its attempt budget.  It continues in
+ * generation g + 1: the record is rewritten in place with that generation's tag and starting clock, counted in its
+ * alloc counter and put on the limbo queue of its parity, where it waits until the generation is open. */
+__device__ __noinline__ void suspend_photon_pipe(const TransportArgs *Ag, unsigned int slot, double x0, double x1,
+                                                 double x2, double x3, double k0, double k1, double k2, double k3,
+                                                 double dk0, double dk1, double dk2, double dk3, double w, double e_0_s,
+                                                 double tau_abs, double tau_scatt, double alpha_scatt, double alpha_abs,
+                                                 double bi, bool ne_pos, uint32_t id0, uint32_t id1, uint32_t id2,
+                                                 uint32_t ctr, int n_step, int tag) {
+    const TransportArgs &A = *Ag;
+    GenCtl *C = A.ctl;
+    TrackInit t;
+    t.alpha_scatt = alpha_scatt;
+    t.alpha_abs = alpha_abs;
+    t.bi = bi;
+    t.ne_pos = ne_pos;
+    const double x[4] = {x0, x1, x2, x3}, k[4] = {k0, k1, k2, k3}, dk[4] = {dk0, dk1, dk2, dk3};
+    const Rng rng = {id0, id1, id2, ctr};
+    /* the photon's generation: the one of [nc, nc + 3) with this tag (nc: oldest incomplete generation) */
+    const long long nc = (long long)ld_volatile_u64(C->line + CW_COMPLETE);
+    const long long g = nc + ((tag - (int)(nc & 3)) & 3);
+    const long long gn = g + 1 < C->n_desc ? g + 1 : C->n_desc - 1;
+    const int nt = (tag + 1) & 3;
+    pool_store_hot(A.pool, slot, x, k, dk, w, e_0_s, tau_abs, tau_scatt, t, rng, n_step | (nt << kTagShift));
+    __stcg(A.pool.gclock + slot, C->desc[gn].carry_clock0);
+    atomicAdd(C->alloc + nt, 1ull); /* before this photon is counted as done in its old generation */
+    const SlotQueue lq = {A.qent + (size_t)(2 + (nt & 1)) * A.qcap, C->line + CW_L0_HEAD + kCwLStride * (nt & 1),
+                          C->line + CW_L0_TAIL + kCwLStride * (nt & 1), A.qcap};
+    queue_push_ring(A, lq, slot);
 }
 
 } /* namespace gm */

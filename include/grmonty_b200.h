@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GRMONTY_B200_ABI_VERSION 3
+#define GRMONTY_B200_ABI_VERSION 4
 
 #define GRMONTY_B200_N_TH_BINS 6     /* reference consts.hpp:26 */
 #define GRMONTY_B200_N_E_BINS 200    /* reference consts.hpp:25 */
@@ -126,6 +126,15 @@ typedef struct grmonty_b200_config {
     int32_t slots_per_thread;
     /* wavefront phase thresholds in 1/256 (0 = default): see TransportArgs in csrc/gm_transport.cuh */
     int32_t wf_thr_interact, wf_thr_service;
+    /* Generation scheduler.  0 (default) or 1: OVERLAPPING generations (csrc/gm_pipeline.cuh; fused kernel only) --
+     * one persistent launch runs a window of generations, the generation clock lives on the device, generation g
+     * uses the bias statistics of the generations <= g - 2 and starts as soon as g - 2 is complete, so the drain of one
+     * generation is covered by the bulk of the next.  2: one launch per generation with the statistics of all earlier
+     * generations (the round-1 scheduler; the only one the wavefront kernel has).  Both are deterministic and
+     * independent of launch geometry, GPU scheduling and queue_capacity; they differ from each other statistically
+     * only (tests/test_gpu_spectrum.py holds both to the same bars against the reference ensembles). */
+    int32_t gen_overlap;
+    int32_t reserved0;
 } grmonty_b200_config;
 
 /* Device-side work counters and timings (filled by grmonty_b200_result when `stats` is not NULL). */

@@ -1535,9 +1535,18 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
     /* drain: photons still suspended after the last generation run to completion */
     while (m->n_carry > 0) {
         if (m->stats_mode == ORC_STATS_FROZEN) {
-            m->bias_max_tau_scatt = m->acc_max_tau_scatt;
-            m->bias_n_scatt = (double)m->acc_n_scatt;
-            m->bias_n_recorded = (double)m->acc_n_recorded;
+            if (m->stats_lag > 0) { /* the drain is one more generation of the pipeline (gm_pipeline.cuh): lag 1 */
+                m->bias_max_tau_scatt = lag_tau;
+                m->bias_n_scatt = lag_scatt;
+                m->bias_n_recorded = lag_rec;
+                lag_tau = m->acc_max_tau_scatt;
+                lag_scatt = (double)m->acc_n_scatt;
+                lag_rec = (double)m->acc_n_recorded;
+            } else {
+                m->bias_max_tau_scatt = m->acc_max_tau_scatt;
+                m->bias_n_scatt = (double)m->acc_n_scatt;
+                m->bias_n_recorded = (double)m->acc_n_recorded;
+            }
         }
         m->budget = INT_MAX;
         run_carried(m, 0);

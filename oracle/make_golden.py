@@ -304,9 +304,10 @@ if __name__ == "__main__":
         pass  # handled at the end of the file
     elif what == "spectrum_4e20":  # configs[3]: Compton-dominated regime, 8 seeds at photon_n = 2e4
         gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e20,))
-    elif what == "spectrum_more":  # spectrum_more <first_seed> <n> [mass_unit]
+    elif what == "spectrum_more":  # spectrum_more <first_seed> <n> [mass_unit [photon_n]]
         gen_spectrum(first_seed=int(sys.argv[2]), seeds=int(sys.argv[3]), merge=True,
-                     mass_units=(float(sys.argv[4]),) if len(sys.argv) > 4 else (4e19,))
+                     mass_units=(float(sys.argv[4]),) if len(sys.argv) > 4 else (4e19,),
+                     photon_n=int(float(sys.argv[5])) if len(sys.argv) > 5 else 100000)
     elif what in ("spectrum_file", "spectrum_grid", "functions_grid"):
         pass  # handled at the end of the file
     else:

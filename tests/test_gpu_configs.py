@@ -56,7 +56,8 @@ def consistent(r):
 def test_compton_dominated_vs_reference(tmp_path):
     ref = dict(np.load(os.path.join(ROOT, "tests", "golden", "spectrum_192_4e20.npz")))
     model = model_for(str(tmp_path), 192, int(ref["photon_n"]), float(ref["mass_unit"]))
-    runs = run_seeds(model, range(2000, 2016))
+    assert len(ref["recorded"]) >= 32                    # 32 complete runs of the reference CLI at photon_n = 2e4
+    runs = run_seeds(model, range(2000, 2048))
     for r in runs:
         consistent(r)
     g_lum = np.array([r["spectrum"][:, :, 1].sum() for r in runs])
@@ -67,7 +68,8 @@ def test_compton_dominated_vs_reference(tmp_path):
         d = g.mean() / rr.mean() - 1
         se = np.hypot(g.std(ddof=1) / np.sqrt(len(g)) / g.mean(), rr.std(ddof=1) / np.sqrt(len(rr)) / rr.mean())
         print(name, d, se)
-        assert abs(d) < 0.01 + 2.5 * se, (name, d, se)
+        assert se < 0.012, (name, se)                   # deep scattering chains: the counts are heavy-tailed
+        assert abs(d) < 0.01 + 2 * se, (name, d, se)
     # spectral shape: per-bin z scores with the variances measured from the two ensembles.  (At this optical depth the
     # weighted spectrum is dominated by rare heavy photons: the reference's own half-vs-half L1 over these bins is
     # 18 %, so an L1 bar would test nothing; chi-square does.)
@@ -79,7 +81,7 @@ def test_compton_dominated_vs_reference(tmp_path):
     z = (gs.mean(0) - rs.mean(0))[mask] / np.sqrt(var[mask])
     chi2 = float((z ** 2).mean())
     print("bins", int(mask.sum()), "chi2/bin", chi2, "max |z|", float(np.abs(z).max()))
-    assert chi2 < 2.0 and np.abs(z).max() < 7.0   # E[z^2] ~ 1.4 with variances from 8 + 16 samples
+    assert chi2 < 1.6 and np.abs(z).max() < 6.0   # variances from 32 + 48 samples
 
 
 def ensemble_vs_reference(runs, ref, min_photons_per_bin):
@@ -109,9 +111,9 @@ def ensemble_vs_reference(runs, ref, min_photons_per_bin):
 def test_large_grid_vs_reference(tmp_path):
     """configs[4]: the CUDA path on the 1024 x 1024 dump against the reference CPU build on the same dump"""
     ref = dict(np.load(os.path.join(ROOT, "tests", "golden", "spectrum_1024_4e19.npz")))
-    assert list(ref["grid"]) == [1024, 1024] and len(ref["recorded"]) >= 8
+    assert list(ref["grid"]) == [1024, 1024] and len(ref["recorded"]) >= 64
     model = model_for(str(tmp_path), 1024, int(ref["photon_n"]), float(ref["mass_unit"]))
-    runs = run_seeds(model, range(3000, 3032))
+    runs = run_seeds(model, range(3000, 3096))
     for r in runs:
         consistent(r)
     assert abs(np.mean([r["created"] for r in runs]) / ref["created"].mean() - 1) < 1e-3
@@ -119,7 +121,7 @@ def test_large_grid_vs_reference(tmp_path):
     print(rep)
     for name in ("luminosity", "recorded", "scattered"):
         d, se = rep[name]
-        assert se < 0.006, (name, se)
+        assert se < 0.007, (name, se)                     # 96 CUDA runs against 64 reference runs
         assert abs(d) < 0.01 + 2 * se, (name, d, se)      # photon_n is small here: the bar plus the ensemble noise
     assert rep["bins"] > 100
     assert rep["chi2_per_bin"] < 1.6 and rep["max_abs_z"] < 6.0

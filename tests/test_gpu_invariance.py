@@ -30,12 +30,17 @@ INTS = ("created", "recorded", "scattered")
 WORK = ("n_tracked", "n_steps", "n_push_attempts", "n_interactions", "n_scatter_events", "n_generations")
 
 
-def test_results_do_not_depend_on_launch_geometry(golden_model):
+@pytest.mark.parametrize("overlap", [1, 2])
+def test_results_do_not_depend_on_launch_geometry(golden_model, overlap):
+    """overlap 1: the pipelined scheduler (fused kernel, every compiled geometry); 2: one launch per generation (both
+    kernels, every compiled geometry).  Within a scheduler every integer output is identical."""
     import cuda_grmonty_b200 as gm
     base = None
     for kernel, threads, third in gm.KERNEL_VARIANTS:
+        if overlap == gm.OVERLAP_ON and kernel != gm.KERNEL_FUSED:
+            continue
         kw = dict(slots_per_thread=third) if kernel == gm.KERNEL_WAVEFRONT else dict(blocks_per_sm=third)
-        r = small_run(gm, golden_model, kernel=kernel, threads_per_block=threads, **kw)
+        r = small_run(gm, golden_model, kernel=kernel, threads_per_block=threads, gen_overlap=overlap, **kw)
         assert r["scattered"] > 1000 and r["stats"]["n_scatter_events"] > 1000   # scattering, children and carry-over ran
         if base is None:
             base = r
@@ -50,14 +55,35 @@ def test_results_do_not_depend_on_launch_geometry(golden_model):
         assert np.allclose(r["spectrum"], base["spectrum"], rtol=1e-10, atol=0)      # sums: order of the atomics
 
 
-def test_queue_capacity_and_budget_spread_do_not_change_results(golden_model):
-    """pool size (how many generations share a batch) is not an input of the physics either"""
+@pytest.mark.parametrize("overlap", [1, 2])
+def test_queue_capacity_does_not_change_results(golden_model, overlap):
+    """pool size (how many generations share a launch of the pipelined scheduler / how a generation is split into
+    batches by the round-1 scheduler) is not an input of the physics either"""
     import cuda_grmonty_b200 as gm
-    a = small_run(gm, golden_model)
-    b = small_run(gm, golden_model, queue_capacity=1 << 16)
-    for k in INTS:
-        assert a[k] == b[k], k
-    assert np.array_equal(a["spectrum"][:, :, 2], b["spectrum"][:, :, 2])
+    a = small_run(gm, golden_model, gen_overlap=overlap)
+    for cap in (1 << 17, 1 << 16):
+        b = small_run(gm, golden_model, queue_capacity=cap, gen_overlap=overlap)
+        for k in INTS:
+            assert a[k] == b[k], (cap, k)
+        for k in WORK:
+            assert a["stats"][k] == b["stats"][k], (cap, k)
+        assert a["max_tau_scatt"] == b["max_tau_scatt"]
+        assert np.array_equal(a["spectrum"][:, :, 2], b["spectrum"][:, :, 2])
+
+
+def test_split_runs_continue_the_generation_clock(golden_model):
+    """run(0, a) + run(a, b) on one context: same primaries as run(0, b); the two calls are separate pipelines (the
+    second starts from the statistics the first left), so the counts agree statistically"""
+    import cuda_grmonty_b200 as gm
+    c = gm.Context(golden_model, seed=77, gen0=64, gen_cap=1 << 12)
+    c.run(0, 8000)
+    c.run(8000, 20000)
+    r = c.result()
+    c.close()
+    one = small_run(gm, golden_model)
+    assert r["created"] == one["created"] == 20000
+    assert abs(r["recorded"] / one["recorded"] - 1) < 0.05
+    assert r["spectrum"][:, :, 2].sum() == r["recorded"]
 
 
 def test_world_dependence_is_statistical_only(golden_model):

@@ -248,10 +248,13 @@ def test_track_with_scattering_matches_oracle_photon_by_photon(ctx, orc_model):
         assert abs(a / b - 1) < 0.02, fld
 
 
-def test_full_run_matches_oracle(ctx, orc_model, golden_model, gm):
-    """grmonty_b200_run over the first generations vs orc_run with the same schedule"""
+@pytest.mark.parametrize("overlap,lag", [(1, 1), (2, 0)])
+def test_full_run_matches_oracle(ctx, orc_model, golden_model, gm, overlap, lag):
+    """grmonty_b200_run over the first generations vs orc_run with the same schedule: the pipelined scheduler
+    (overlapping generations, statistics one generation behind: gen_overlap = 1, the default) and the round-1
+    scheduler (one launch per generation: gen_overlap = 2)"""
     M = orc_model
-    c2 = gm.Context(golden_model, seed=123, gen0=1 << 10, gen_cap=1 << 12, test_exports=True)
+    c2 = gm.Context(golden_model, seed=123, gen0=1 << 10, gen_cap=1 << 12, gen_overlap=overlap, test_exports=True)
     last = 6000
     c2.run(0, last)
     res = c2.result()
@@ -259,7 +262,7 @@ def test_full_run_matches_oracle(ctx, orc_model, golden_model, gm):
     M.clear()
     M.m.stats_mode = 0
     M.m.acc_max_tau_scatt = float(golden_model["max_tau_scatt0"])
-    M.run(0, last, 0, 1, 1 << 10, 1 << 12)
+    M.run(0, last, 0, 1, 1 << 10, 1 << 12, stats_lag=lag)
     assert res["created"] == M.m.n_created == last
     assert abs(res["recorded"] - M.m.acc_n_recorded) <= 0.01 * M.m.acc_n_recorded + 2
     assert abs(res["scattered"] - M.m.acc_n_scatt) <= 0.02 * M.m.acc_n_scatt + 3
@@ -267,6 +270,7 @@ def test_full_run_matches_oracle(ctx, orc_model, golden_model, gm):
     a, b = res["spectrum"][:, :, 1].sum(), ospec[:, :, 1].sum()
     assert abs(a / b - 1) < 0.02
     assert abs(res["stats"]["n_steps"] / M.m.n_steps - 1) < 0.01
+    assert res["stats"]["n_tracked"] == M.m.n_tracked or abs(res["stats"]["n_tracked"] / M.m.n_tracked - 1) < 0.01
 
 
 def test_sharding_partitions_the_photons(golden_model, gm):

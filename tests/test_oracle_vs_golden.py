@@ -200,14 +200,17 @@ def test_stats_lag_knob(golden_model):
     a run of one generation cannot depend on it; a run of several generations does."""
     from oracle import orc
 
-    def run(last, lag, gen0):
+    def run(last, lag, gen0, budget=384):
         M = orc.Model(golden_model, seed=7)
         M.m.acc_max_tau_scatt = float(golden_model["max_tau_scatt0"])
-        M.run(0, last, 0, 1, gen0, 1 << 20, stats_lag=lag)
+        M.run(0, last, 0, 1, gen0, 1 << 20, budget, stats_lag=lag)
         return int(M.m.n_created), int(M.m.acc_n_recorded), int(M.m.acc_n_scatt), M.spectrum()[:, :, 1].sum()
 
-    # one generation: the lag cannot matter
-    assert run(300, 0, 512) == run(300, 1, 512)
+    # one generation without an attempt budget (nothing is carried into a drain generation): the lag cannot matter
+    assert run(300, 0, 512, 0) == run(300, 1, 512, 0)
+    # with the budget the suspended lineages finish in the drain generation, which is one more generation of the
+    # pipeline: lag 1 runs it on the initial statistics, lag 0 on those after the first generation
+    assert run(300, 0, 512)[0] == run(300, 1, 512)[0] == 300
     # several generations: same primaries, different bias history
     a, b = run(3000, 0, 64), run(3000, 1, 64)
     assert a[0] == b[0] == 3000
