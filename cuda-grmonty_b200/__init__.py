@@ -143,6 +143,7 @@ TEST_ABI_SYMBOLS = [
     "grmonty_b200_test_hotcross", "grmonty_b200_test_angles", "grmonty_b200_test_tetrad",
     "grmonty_b200_test_zones", "grmonty_b200_test_bias", "grmonty_b200_test_make_primaries",
     "grmonty_b200_test_track", "grmonty_b200_test_samplers", "grmonty_b200_test_philox",
+    "grmonty_b200_test_bounds_violations",
 ]
 
 # launch geometries compiled into the library (csrc/gm_api.cu): (kernel, threads per block, blocks per SM or slots per
@@ -403,6 +404,12 @@ class Context:
         self._ck(self.L.grmonty_b200_test_samplers(self.h, which, C.c_double(p0), C.c_double(p1),
                                                    C.c_int64(first_stream), C.c_int64(n), _ptr(out)))
         return out
+
+    def t_bounds_violations(self) -> int:
+        """pool accesses outside the pool counted by the checked build since the last call (test library only)"""
+        v = C.c_uint32(0)
+        self._ck(self.L.grmonty_b200_test_bounds_violations(self.h, C.byref(v)))
+        return int(v.value)
 
     def t_philox(self, ctr, key):
         c, k = _arr(ctr, np.uint32).reshape(-1, 4), _arr(key, np.uint32).reshape(-1, 2)

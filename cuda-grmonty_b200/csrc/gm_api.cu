@@ -99,6 +99,7 @@ struct grmonty_b200_ctx {
     int kernel = 0;                 /* 0: wavefront, 1: fused loop of round 1 */
     /* pipelined generations (gm_pipeline.cuh): device-side generation clock, one launch per window of generations */
     int overlap = 1;
+    int lag_mode = 1; /* 1: generations at the size cap start one generation early, 3: all generations do */
     GenCtl *d_ctl = nullptr;
     GenDesc *d_desc = nullptr; /* own allocation, grown on demand (one entry per generation of a run) */
     size_t desc_cap = 0;
@@ -305,21 +306,22 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
         /* ---- one device arena for everything (reused from the cache when possible) ---- */
         const size_t nz = (size_t)cfg->n0 * cfg->n1;
         /* kernel / scheduler choice first: the pool is sized for it.  config: kernel 0 = default (the fused loop, the
-         * faster of the two on B200), 1 = fused, 2 = wavefront; gen_overlap 0 = default (on, fused loop only), 1 = on,
-         * 2 = off (one launch per generation, the round-1 scheduler) */
+         * faster of the two on B200), 1 = fused, 2 = wavefront; gen_overlap 0 = default = 2 = one launch per
+         * generation, 1 = pipelined (capped generations start early), 3 = pipelined, every generation starts early */
         if (cfg->kernel < 0 || cfg->kernel > 2)
             return fail(ctx, GRMONTY_B200_EINVAL, "kernel must be 0 (default), 1 (fused) or 2 (wavefront)");
-        if (cfg->gen_overlap < 0 || cfg->gen_overlap > 2)
-            return fail(ctx, GRMONTY_B200_EINVAL, "gen_overlap must be 0 (default), 1 (on) or 2 (off)");
+        if (cfg->gen_overlap < 0 || cfg->gen_overlap > 3)
+            return fail(ctx, GRMONTY_B200_EINVAL, "gen_overlap must be 0 (default), 1 (on), 2 (off) or 3 (lag 1 everywhere)");
+        ctx->lag_mode = cfg->gen_overlap == 3 ? 3 : 1;
         ctx->kernel = cfg->kernel == 2 ? 0 : 1;
         if (const char *e = getenv("GRMONTY_B200_KERNEL")) /* A/B switch for tools/: "fused" or "wavefront" */
             ctx->kernel = strcmp(e, "wavefront") == 0 ? 0 : 1;
-        ctx->overlap = cfg->gen_overlap == 2 ? 0 : 1;
+        ctx->overlap = (cfg->gen_overlap == 1 || cfg->gen_overlap == 3) ? 1 : 0;
         if (const char *e = getenv("GRMONTY_B200_OVERLAP")) /* A/B switch for tools/ */
             ctx->overlap = atoi(e) != 0;
         if (ctx->kernel == 0) {
-            if (cfg->gen_overlap == 1)
-                return fail(ctx, GRMONTY_B200_EINVAL, "gen_overlap = 1 needs the fused kernel");
+            if (cfg->gen_overlap == 1 || cfg->gen_overlap == 3)
+                return fail(ctx, GRMONTY_B200_EINVAL, "gen_overlap = 1 / 3 needs the fused kernel");
             ctx->overlap = 0;
         }
         /* pool records: a launch of the pipelined scheduler holds a window of generations (a third of the pool in
@@ -938,16 +940,17 @@ static int run_range_pipelined(grmonty_b200_ctx *ctx, long long first, long long
     /* ---- the generations of this call (same partition as the round-1 scheduler and the oracle) ---- */
     struct Gen {
         long long f0, count, pos_end;
+        bool capped;
     };
     std::vector<Gen> gens;
     for (long long g_start = 0; g_start < last;) {
-        const long long g_end =
-            g_start + world * generation_size(g_start / world, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from,
-                                              ctx->gen_fine_div, ctx->gen_ramp);
+        const long long size = generation_size(g_start / world, ctx->gen0, ctx->gen_cap, ctx->gen_fine_from,
+                                               ctx->gen_fine_div, ctx->gen_ramp);
+        const long long g_end = g_start + world * size;
         const long long lo = std::max<long long>(g_start, first), hi = std::min<long long>(g_end, last);
         if (lo < hi) {
             const long long f0 = lo + ((rank - lo % world) % world + world) % world;
-            gens.push_back({f0, f0 < hi ? (hi - f0 + world - 1) / world : 0, hi});
+            gens.push_back({f0, f0 < hi ? (hi - f0 + world - 1) / world : 0, hi, size >= ctx->gen_cap});
         }
         g_start = g_end;
     }
@@ -961,9 +964,11 @@ static int run_range_pipelined(grmonty_b200_ctx *ctx, long long first, long long
         desc[g].count = (unsigned long long)gens[g].count;
         desc[g].prim_end = 0ull;
         desc[g].carry_clock0 = spread > 0 ? -(int)(gens[g].count / spread) : 0;
-        desc[g].pad = 0;
+        /* early start (statistics one generation behind): the generations at the size cap, or all (study knob) */
+        desc[g].lag = ctx->lag_mode == 3 ? 1 : (gens[g].capped ? 1 : 0);
+        desc[g].t_open = desc[g].t_done = 0ull;
     }
-    desc[n_real] = GenDesc{0ull, 0ull, kClockForever, 0};
+    desc[n_real] = GenDesc{0ull, 0ull, kClockForever, 0, 0ull, 0ull};
     if ((size_t)n_desc > ctx->desc_cap) {
         if (ctx->d_desc)
             CK(cudaFree(ctx->d_desc));
@@ -1038,8 +1043,10 @@ static int run_range_pipelined(grmonty_b200_ctx *ctx, long long first, long long
         const int p0 = g0 & 1;
         h.line[CW_L0_TAIL + kCwLStride * p0] = n_carry_in; /* lineages suspended into g0 by the previous window */
         h.line[CW_L0_LIM + kCwLStride * p0] = n_carry_in;  /* frozen: what follows them will be for g0 + 2 */
-        h.line[CW_L0_LIM + kCwLStride * (p0 ^ 1)] = kGateLive;
-        h.line[CW_PRIM_LIM] = desc[std::min(g0 + 1, g_end - 1)].prim_end; /* g0 and g0 + 1 are open */
+        /* g0 is open; g0 + 1 as well if it may start early */
+        const bool open1 = g0 + 1 < g_end && desc[g0 + 1].lag == 1;
+        h.line[CW_L0_LIM + kCwLStride * (p0 ^ 1)] = open1 ? kGateLive : 0ull;
+        h.line[CW_PRIM_LIM] = desc[open1 ? g0 + 1 : g0].prim_end;
         h.line[CW_COMPLETE] = (unsigned long long)g0;
         h.g_end = g_end;
         h.t_start = 0ull;

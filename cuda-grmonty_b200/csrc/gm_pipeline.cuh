@@ -7,9 +7,12 @@
  * ramp sit on a 2 - 3 ms floor each: 14 % of the configs[1] step, half of a configs[0] run.
  *
  * How.  The reference's bias_func reads running statistics (harm_model.cpp:1391-1404); this path freezes them per
- * generation.  Here generation g uses the statistics of all generations <= g - 2 (lag 1): it can start
- * as soon as generation g - 2 is complete, so two generations are in flight and the drain of one is covered by the
- * bulk of the next.  Everything a photon does still depends only on its identity and on its generations'
+ * generation.  Here a generation g marked "lag 1" (GenDesc::lag; by default the generations at the size
+ * cap, i.e. the bulk of a large run, where the statistics are settled) uses the statistics of all generations
+ * <= g - 2: it can start as soon as generation g - 2 is complete, so two generations are in flight and the drain of
+ * one is covered by the bulk of the next.  The other generations (the start-up ramp, where the statistics still move
+ * fast and a lag shows in the scattering counts: +1.3 % at configs[0], profiles/r2_pipeline_parity.txt) start when
+ * their predecessor is complete, exactly as with one launch per generation -- but without a host round trip.  Everything a photon does still depends only on its identity and on its generations'
  * statistics -- results do not depend on scheduling, launch geometry or how many generations share a launch:
  *   - a record carries its generation tag (g & 3; bits 28-29 of the n_step word); at most generations nc, nc + 1
  *     (open) and nc + 2 (being filled by suspensions) exist at a time, nc = number of complete generations;
@@ -78,33 +81,43 @@ __device__ __noinline__ void gen_try_complete(const TransportArgs *Ag) {
             st_volatile_u64(cnt + 1, n_scatt);
             st_volatile_u64(cnt + 2, n_rec);
             st_volatile_u64(A.A.max_tau_bits, mt);
-            /* statistics of generation g + 2: everything recorded in generations <= g (operation order of
-             * make_bias_stats, gm_params.h) */
+            /* bias denominator of the generations that open now: everything recorded in generations <= g (operation
+             * order of make_bias_stats, gm_params.h) */
             const double avg = __ddiv_rn((double)n_scatt, __dadd_rn((double)n_rec, 1.0));
             const double den = __dmul_rn(__dmul_rn(C->bias_norm, __longlong_as_double((long long)mt)), __dadd_rn(avg, 2.0));
-            *reinterpret_cast<volatile double *>(C->bias_den + ((g + 2) & 3)) = den;
             /* the ring slot now belongs to generation g + 4 */
             st_volatile_u64(C->acc_scatt + t, 0ull);
             st_volatile_u64(C->acc_rec + t, 0ull);
             st_volatile_u64(C->acc_maxtau + t, 0ull);
             st_volatile_u64(C->done + t, 0ull);
             st_volatile_u64(C->alloc + t, g + 4 < C->n_desc ? C->desc[g + 4].count : 0ull);
-            /* limbo gates.  Parity of g + 2 (opens now): its entries come from g + 1, which is running -- every
-             * published entry may be taken.  Parity of g + 1: all its entries are in (g is complete) and the next
-             * ones, for g + 3, will come from g + 2: freeze the gate at the current tail. */
-            const int q = (int)(g & 1), q1 = q ^ 1;
-            if (g + 1 < (long long)C->g_end)
-                st_volatile_u64(C->line + CW_L0_LIM + kCwLStride * q1, ld_volatile_u64(C->line + CW_L0_TAIL + kCwLStride * q1));
-            /* generation g + 2 opens only if it belongs to this launch: its gate goes live and its primaries may be
-             * issued.  Otherwise the gate stays frozen at the end of g's entries and what is behind it is the next
-             * launch's carry-in (nothing of a generation >= g_end may run here: the launch ends at g_end). */
+            /* Which generations open now?  g + 1 unless it was opened one generation early (lag 1: at the completion
+             * of g - 1); g + 2 if IT may start early.  Only generations of this launch open: nothing of a generation
+             * >= g_end may run here (the launch ends when g_end - 1 is complete). */
             GenDesc *dsc = const_cast<GenDesc *>(C->desc);
             const unsigned long long now = global_timer_ns();
             dsc[g].t_done = now;
-            if (g + 2 < (long long)C->g_end && g + 2 < C->n_desc) {
+            const int q = (int)(g & 1), q1 = q ^ 1;
+            const bool has1 = g + 1 < C->n_desc, has2 = g + 2 < C->n_desc && C->desc[g + 2].lag == 1;
+            const bool in1 = has1 && g + 1 < (long long)C->g_end, in2 = has2 && g + 2 < (long long)C->g_end;
+            /* (the denominators are frozen here even for generations of the next launch: the ring lives on) */
+            if (has1 && C->desc[g + 1].lag == 0)
+                *reinterpret_cast<volatile double *>(C->bias_den + ((g + 1) & 3)) = den;
+            if (has2)
+                *reinterpret_cast<volatile double *>(C->bias_den + ((g + 2) & 3)) = den;
+            if (in1) {
+                if (C->desc[g + 1].lag == 0)
+                    dsc[g + 1].t_open = now;
+                /* limbo queue of g + 1's parity: all entries for g + 1 are in (g is complete) and the next ones, for
+                 * g + 3, must wait for that generation: the gate is (re)set to the current tail */
+                st_volatile_u64(C->line + CW_L0_LIM + kCwLStride * q1, ld_volatile_u64(C->line + CW_L0_TAIL + kCwLStride * q1));
+                st_volatile_u64(C->line + CW_PRIM_LIM, C->desc[g + 1].prim_end);
+            }
+            if (in2) {
+                dsc[g + 2].t_open = now;
+                /* its limbo entries come from g + 1, which is running: every published entry may be taken */
                 st_volatile_u64(C->line + CW_L0_LIM + kCwLStride * q, kGateLive);
                 st_volatile_u64(C->line + CW_PRIM_LIM, C->desc[g + 2].prim_end);
-                dsc[g + 2].t_open = now;
             }
             __threadfence();
             st_release_u64(C->line + CW_COMPLETE, nc + 1ull);
@@ -138,11 +151,10 @@ __device__ __noinline__ void pipe_flush_done(GenCtl *C, unsigned long long done_
     }
 }
 
-#ifndef GM_PIPE_FAIR_SHARE
-#define GM_PIPE_FAIR_SHARE 1
-#endif
+
 #ifndef GM_PIPE_CLAIM_EVERY
-#define GM_PIPE_CLAIM_EVERY 1 /* claim only in every n-th loop iteration (power of two) */
+#define GM_PIPE_CLAIM_EVERY 4 /* claim only in every n-th loop iteration (power of two): fewer, larger claims;
+                               * measured 1 -> 593, 2 -> 592, 4 -> 574 ms per configs[1] run */
 #endif
 
 constexpr int kDoneFlushEvery = 8; /* inner iterations between two publications of a warp's finished counts */
@@ -160,7 +172,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) pipeline_kernel(const Trans
     __shared__ volatile int s_hint, s_pa;
     __shared__ volatile unsigned long long s_prim_lim;
     const int lane = threadIdx.x & 31;
-    const int n_warps = (int)gridDim.x * (BLOCK / 32);
     double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
     GenCtl *const C = A.ctl;
     unsigned long long *const line = C->line;
@@ -258,7 +269,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) pipeline_kernel(const Trans
                     if (hint) {
                         /* the first hinted source: its counters are read by lane 0 only (one line), which claims for
                          * the warp with one fetch-add -- never fails; a claim that ran ahead of what is published is a
-                         * ticket the lane keeps polling */
+                         * ticket the lane keeps polling.  (Measured and rejected, profiles/r2_pipeline_ab.txt: claims
+                         * capped at the warp's share of what is available; block-local exact claims refilled once per
+                         * outer iteration.) */
                         const int src = __ffs(hint) - 1;
                         const int p = ((src >> 1) & 1) ^ s_pa;
                         const int kind = src == 4 ? 4 : ((src & 1) ? p : 2 + p);
@@ -275,16 +288,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) pipeline_kernel(const Trans
                                 t = t < lim ? t : lim;
                             }
                             const unsigned long long avail = t > h ? t - h : 0ull;
-                            /* not more than the warp's share of what there is: when work is scarce (the small
-                             * generations of the start-up ramp, the tail of a run) it is spread over all SMs -- a
-                             * lone lane's loop iteration takes half the time of a full warp's, and what bounds a
-                             * small generation is the latency of its longest lineage */
-#if GM_PIPE_FAIR_SHARE
-                            const unsigned long long share = (avail + (unsigned long long)n_warps - 1ull) / (unsigned long long)n_warps;
-                            const int n_want = (int)min((unsigned long long)__popc(need), share);
-#else
                             const int n_want = __popc(need);
-#endif
                             n = avail < (unsigned long long)n_want ? (int)avail : n_want;
                             if (n > 0)
                                 base = atomicAdd(hp, (unsigned long long)n);

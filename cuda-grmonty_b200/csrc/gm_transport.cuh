@@ -107,7 +107,8 @@ struct GenDesc {
     unsigned long long count;    /* primaries of this rank in the generation */
     unsigned long long prim_end; /* end (exclusive) of the generation's records in the current launch's pool */
     int carry_clock0;            /* lineage clock a photon suspended into this generation starts with */
-    int pad;
+    int lag;                     /* 1: the generation may start one generation early (it opens when g - 2 is complete
+                                  * and uses the statistics up to there); 0: it opens when g - 1 is complete */
     unsigned long long t_open, t_done; /* %globaltimer when the generation was opened / completed (diagnostics) */
 };
 
@@ -165,11 +166,28 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+/* Bounds checks of our own (test library, -DGRMONTY_B200_TEST_EXPORTS; compute-sanitizer is not available on the GPU
+ * pool): every pool access through pload / pstore and every slot number taken from a queue entry or a ticket is
+ * checked against the pool capacity; a violation is counted (grmonty_b200_test_bounds_violations) and redirected to
+ * record 0 instead of touching memory outside the pool.  tests/test_gpu_invariance.py runs both schedulers and both
+ * kernels through the checked build and asserts a count of zero. */
+#ifdef GRMONTY_B200_TEST_EXPORTS
+__device__ unsigned int g_bounds_violations = 0u;
+__device__ __forceinline__ unsigned int chk_slot(const PhotonPool &pool, unsigned int slot) {
+    if (slot >= pool.capacity) {
+        atomicAdd(&g_bounds_violations, 1u);
+        return 0u;
+    }
+    return slot;
+}
+#else
+__device__ __forceinline__ unsigned int chk_slot(const PhotonPool &, unsigned int slot) { return slot; }
+#endif
 __device__ __forceinline__ double pload(const PhotonPool &pool, int field, unsigned int slot) {
-    return __ldcg(pool.f + (size_t)field * pool.capacity + slot);
+    return __ldcg(pool.f + (size_t)field * pool.capacity + chk_slot(pool, slot));
 }
 __device__ __forceinline__ void pstore(const PhotonPool &pool, int field, unsigned int slot, double v) {
-    __stcg(pool.f + (size_t)field * pool.capacity + slot, v);
+    __stcg(pool.f + (size_t)field * pool.capacity + chk_slot(pool, slot), v);
 }
 
 /* allocate a pool record; returns false (and flags the overflow) when the pool is full */
@@ -458,6 +476,7 @@ struct Live {
  * record's n_step word (the pipelined kernel keeps its generation tag there) */
 __device__ __forceinline__ int live_load(const TransportArgs &A, unsigned int slot, Live &L) {
     const PhotonPool &pool = A.pool;
+    slot = chk_slot(pool, slot);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         L.x[i] = pload(pool, P_X0 + i, slot);
@@ -779,6 +798,7 @@ __device__ __noinline__ ScatterStageResult scatter_stage_t(const TransportArgs *
     const TransportArgs &A = *Ag;
     const GmParams &P = A.P;
     const PhotonPool &pool = A.pool;
+    slot = chk_slot(pool, slot);
     double x[4], k[4], dk[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

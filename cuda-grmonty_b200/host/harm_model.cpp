@@ -881,6 +881,8 @@ void HARMModel::fill_config(grmonty_b200_config &cfg) const {
     cfg.world = options.world;
     cfg.device = options.device;
     cfg.threads_per_block = options.threads_per_block;
+    cfg.kernel = options.kernel;
+    cfg.gen_overlap = options.gen_overlap;
     cfg.blocks_per_sm = options.blocks_per_sm;
     cfg.queue_capacity = options.queue_capacity;
     cfg.gen0 = options.gen0;

@@ -63,6 +63,8 @@ struct RunOptions {
      * all-reduces the spectrum at the end (the command line's --gpus N); needs world == 1 */
     int gpus = 1;
     int threads_per_block = 0, blocks_per_sm = 0;
+    int kernel = 0;      /* grmonty_b200_config::kernel: 0 default (fused loop), 1 fused, 2 wavefront */
+    int gen_overlap = 0; /* grmonty_b200_config::gen_overlap: 0 default (overlapping generations), 1 on, 2 off */
     int64_t queue_capacity = 0, gen0 = 0, gen_cap = 0, gen_budget = 0, gen_fine_from = 0, gen_fine_div = 0;
     bool device_tables = false; /* init(): geometry / weight / nint / hot cross-section tables on the GPU */
     void *nccl_comm = nullptr; /* ncclComm_t for world > 1: run_simulation() ends with grmonty_b200_allreduce */

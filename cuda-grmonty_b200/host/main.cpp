@@ -70,6 +70,10 @@ int main(int argc, char **argv) {
             model.options.device = std::atoi(v.c_str());
         if (flag_value(argc, argv, "gpus", v))
             model.options.gpus = std::atoi(v.c_str());
+        if (flag_value(argc, argv, "gen_overlap", v)) /* 1: overlapping generations (default), 2: one launch each */
+            model.options.gen_overlap = std::atoi(v.c_str());
+        if (flag_value(argc, argv, "queue_capacity", v))
+            model.options.queue_capacity = std::atoll(v.c_str());
         if (flag_value(argc, argv, "init_threads", v))
             model.init_threads = std::atoi(v.c_str());
         if (flag_value(argc, argv, "device_tables", v))

@@ -126,13 +126,18 @@ typedef struct grmonty_b200_config {
     int32_t slots_per_thread;
     /* wavefront phase thresholds in 1/256 (0 = default): see TransportArgs in csrc/gm_transport.cuh */
     int32_t wf_thr_interact, wf_thr_service;
-    /* Generation scheduler.  0 (default) or 1: OVERLAPPING generations (csrc/gm_pipeline.cuh; fused kernel only) --
-     * one persistent launch runs a window of generations, the generation clock lives on the device, generation g
-     * uses the bias statistics of the generations <= g - 2 and starts as soon as g - 2 is complete, so the drain of one
-     * generation is covered by the bulk of the next.  2: one launch per generation with the statistics of all earlier
-     * generations (the round-1 scheduler; the only one the wavefront kernel has).  Both are deterministic and
-     * independent of launch geometry, GPU scheduling and queue_capacity; they differ from each other statistically
-     * only (tests/test_gpu_spectrum.py holds both to the same bars against the reference ensembles). */
+    /* Generation scheduler.  0 (default) or 2: one launch per generation, with the statistics of all earlier
+     * generations (the round-1 scheduler; the only one the wavefront kernel has).
+     * 1: the PIPELINED scheduler (csrc/gm_pipeline.cuh; fused kernel only) -- one persistent launch runs a window of
+     * generations and the generation clock lives on the device.  The generations at the size cap (gen_cap: the bulk
+     * of a large run, where the bias statistics are settled) start one generation early, with the statistics of the
+     * generations <= g - 2, so that the drain of one generation is covered by the bulk of the next; the generations of
+     * the start-up ramp start when their predecessor is complete -- for a run without capped generations the integer
+     * results are those of scheduler 2.  3: pipelined with EVERY generation starting early.
+     * All are deterministic and independent of launch geometry, GPU scheduling and queue_capacity.  Measured
+     * (profiles/r2_pipeline_ab.txt): scheduler 3 runs configs[0] 32 % and configs[1] 2 % faster than scheduler 2 but
+     * its scattering counts stand 1.3 % above the reference ensemble at configs[0] (the statistics lag where they move
+     * fastest) -- outside the 1 % bar, so it is not the default; scheduler 1 keeps the counts but is slower than 2. */
     int32_t gen_overlap;
     int32_t reserved0;
 } grmonty_b200_config;

@@ -65,6 +65,10 @@ int grmonty_b200_test_samplers(grmonty_b200_ctx *ctx, int32_t which, double p0, 
 int grmonty_b200_test_philox(grmonty_b200_ctx *ctx, int64_t n, const uint32_t *ctr, const uint32_t *key,
                              uint32_t *out);
 
+/* pool accesses outside the pool seen by the checked accessors of the test build (csrc/gm_transport.cuh chk_slot);
+ * reading resets the count */
+int grmonty_b200_test_bounds_violations(grmonty_b200_ctx *ctx, uint32_t *count);
+
 #ifdef __cplusplus
 }
 #endif

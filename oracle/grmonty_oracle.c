@@ -1502,18 +1502,24 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
         const int64_t lo = g_start > first ? g_start : first, hi = g_end < last ? g_end : last;
         if (lo < hi) {
             if (m->stats_mode == ORC_STATS_FROZEN) {
-                if (m->stats_lag > 0) { /* use the snapshot taken one generation ago, then take this one's */
+                /* stats_lag 1: every generation uses the snapshot taken one generation ago (statistics of the
+                 * generations <= g - 2); 2: only the generations at the size cap do (the pipelined scheduler's default,
+                 * gm_pipeline.cuh); 0: none */
+                const int64_t size = orc_generation_size(g_start / world, gen0, gen_cap, m->gen_fine_from,
+                                                         m->gen_fine_div, m->gen_ramp);
+                const int lagged = m->stats_lag == 1 || (m->stats_lag == 2 && size >= gen_cap);
+                if (lagged) {
                     m->bias_max_tau_scatt = lag_tau;
                     m->bias_n_scatt = lag_scatt;
                     m->bias_n_recorded = lag_rec;
-                    lag_tau = m->acc_max_tau_scatt;
-                    lag_scatt = (double)m->acc_n_scatt;
-                    lag_rec = (double)m->acc_n_recorded;
                 } else {
                     m->bias_max_tau_scatt = m->acc_max_tau_scatt;
                     m->bias_n_scatt = (double)m->acc_n_scatt;
                     m->bias_n_recorded = (double)m->acc_n_recorded;
                 }
+                lag_tau = m->acc_max_tau_scatt; /* the snapshot the next generation may lag to */
+                lag_scatt = (double)m->acc_n_scatt;
+                lag_rec = (double)m->acc_n_recorded;
             }
             m->budget = budget;
             /* Attempt budgets (same rule as the CUDA path, gm_api.cu run_batch): the t-th of the generation's
@@ -1535,18 +1541,10 @@ void orc_run(orc_model *m, int64_t first, int64_t last, int rank, int world, int
     /* drain: photons still suspended after the last generation run to completion */
     while (m->n_carry > 0) {
         if (m->stats_mode == ORC_STATS_FROZEN) {
-            if (m->stats_lag > 0) { /* the drain is one more generation of the pipeline (gm_pipeline.cuh): lag 1 */
-                m->bias_max_tau_scatt = lag_tau;
-                m->bias_n_scatt = lag_scatt;
-                m->bias_n_recorded = lag_rec;
-                lag_tau = m->acc_max_tau_scatt;
-                lag_scatt = (double)m->acc_n_scatt;
-                lag_rec = (double)m->acc_n_recorded;
-            } else {
-                m->bias_max_tau_scatt = m->acc_max_tau_scatt;
-                m->bias_n_scatt = (double)m->acc_n_scatt;
-                m->bias_n_recorded = (double)m->acc_n_recorded;
-            }
+            /* the drain generation starts when the last generation is complete: latest statistics */
+            m->bias_max_tau_scatt = m->acc_max_tau_scatt;
+            m->bias_n_scatt = (double)m->acc_n_scatt;
+            m->bias_n_recorded = (double)m->acc_n_recorded;
         }
         m->budget = INT_MAX;
         run_carried(m, 0);

@@ -253,7 +253,7 @@ def gen_samplers():
     print("wrote samplers.npz", file=sys.stderr)
 
 
-def gen_spectrum(photon_n=100000, seeds=8, mass_units=(4e19,), first_seed=0, merge=False):
+def gen_spectrum(photon_n=100000, seeds=8, mass_units=(4e19,), first_seed=0, merge=False, suffix=""):
     """`seeds` runs of the reference CLI (seed 123 + first_seed + s), each a complete run at `photon_n`
     (BASELINE.json configs[0]); merge=True appends to the existing fixture (more seeds = less Monte Carlo
     noise in the reference ensemble)."""
@@ -282,7 +282,7 @@ def gen_spectrum(photon_n=100000, seeds=8, mass_units=(4e19,), first_seed=0, mer
                    max_tau_scatt=np.array([m["max_tau_scatt"] for m in metas]),
                    # per-seed: dn_dle, de_dle, nph, nscatt, tau_abs, tau_scatt (fields 0,1,2,3,7,8)
                    spec=specs[:, :, :, [0, 1, 2, 3, 7, 8]].astype(np.float64))
-        name = f"spectrum_192_{mu:.0e}.npz".replace("+", "")
+        name = f"spectrum_192_{mu:.0e}{suffix}.npz".replace("+", "")
         if merge and os.path.exists(os.path.join(GOLD, name)):
             old = dict(np.load(os.path.join(GOLD, name)))
             assert int(old["photon_n"]) == photon_n and int(old["seeds"]) == first_seed
@@ -308,6 +308,9 @@ if __name__ == "__main__":
         gen_spectrum(first_seed=int(sys.argv[2]), seeds=int(sys.argv[3]), merge=True,
                      mass_units=(float(sys.argv[4]),) if len(sys.argv) > 4 else (4e19,),
                      photon_n=int(float(sys.argv[5])) if len(sys.argv) > 5 else 100000)
+    elif what == "spectrum_4e20_1e5":  # configs[3] at the photon_n of configs[0]: spectrum_4e20_1e5 <first_seed> <n>
+        gen_spectrum(photon_n=100000, first_seed=int(sys.argv[2]), seeds=int(sys.argv[3]), merge=True,
+                     mass_units=(4e20,), suffix="_1e5")
     elif what in ("spectrum_file", "spectrum_grid", "functions_grid"):
         pass  # handled at the end of the file
     else:

@@ -248,11 +248,11 @@ def test_track_with_scattering_matches_oracle_photon_by_photon(ctx, orc_model):
         assert abs(a / b - 1) < 0.02, fld
 
 
-@pytest.mark.parametrize("overlap,lag", [(1, 1), (2, 0)])
+@pytest.mark.parametrize("overlap,lag", [(1, 2), (3, 1), (2, 0)])
 def test_full_run_matches_oracle(ctx, orc_model, golden_model, gm, overlap, lag):
     """grmonty_b200_run over the first generations vs orc_run with the same schedule: the pipelined scheduler
-    (overlapping generations, statistics one generation behind: gen_overlap = 1, the default) and the round-1
-    scheduler (one launch per generation: gen_overlap = 2)"""
+    (gen_overlap = 1: generations at the size cap start one generation early, orc stats_lag = 2; gen_overlap = 3: all
+    of them do, stats_lag = 1) and the default scheduler (one launch per generation: gen_overlap = 2, stats_lag = 0)"""
     M = orc_model
     c2 = gm.Context(golden_model, seed=123, gen0=1 << 10, gen_cap=1 << 12, gen_overlap=overlap, test_exports=True)
     last = 6000

@@ -213,7 +213,7 @@ def test_bench_workload_photon_n_1e6_vs_reference():
     report("configs1_photon_n_1e6", rep | {"n_gpu_seeds": len(runs), "n_ref_seeds": int(len(r_lum))})
     assert abs(rep["luminosity"]["rel_diff_of_means"]) < 0.01 and rep["luminosity"]["std_err"] < 0.005
     for name in ("recorded", "scattered"):
-        assert rep[name]["std_err_conditional"] < 0.006, (name, rep[name])
+        assert rep[name]["std_err_conditional"] < 0.007, (name, rep[name])   # bootstrap estimate, 14 reference runs
         assert abs(rep[name]["ref_minus_cuda_at_equal_max_tau"]) < 0.01, (name, rep[name])
         # the unconditional means are heavy-tailed (see above): reported, and held to the bar within their own error
         assert abs(rep[name]["rel_diff_of_means"]) < 0.01 + 2 * rep[name]["std_err"], (name, rep[name])

@@ -3,9 +3,9 @@
 set -u
 out=gpurun_out
 mkdir -p $out
-timeout 1500 python -m pytest tests -m gpu -q -x --durations=15 > $out/r2_gputests.log 2>&1
-echo "tests rc=$?"; tail -30 $out/r2_gputests.log
+timeout 2400 python -m pytest tests -m gpu -q --durations=15 > $out/r2_gputests.log 2>&1
+echo "tests rc=$?"; tail -60 $out/r2_gputests.log
 timeout 600 python bench.py --steps 3 --warmup 3 > $out/r2_bench.json 2> $out/r2_bench.err
 echo "bench rc=$?"; cat $out/r2_bench.json; tail -5 $out/r2_bench.err
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > $out/r2_bench_ref.json 2> $out/r2_bench_ref.err
-echo "ref rc=$?"; cat $out/r2_bench_ref.json; tail -5 $out/r2_bench_ref.err
+echo "ref rc=$?"; cut -c1-300 $out/r2_bench_ref.json; tail -5 $out/r2_bench_ref.err
