@@ -9,3 +9,5 @@ timeout 600 python bench.py --steps 3 --warmup 3 > $out/r2_bench.json 2> $out/r2
 echo "bench rc=$?"; cat $out/r2_bench.json; tail -5 $out/r2_bench.err
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > $out/r2_bench_ref.json 2> $out/r2_bench_ref.err
 echo "ref rc=$?"; cut -c1-300 $out/r2_bench_ref.json; tail -5 $out/r2_bench_ref.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/r2_launches_bench.csv python bench.py --steps 1 --warmup 1 --no_cpu_baseline > $out/r2_launches_ncu.log 2>&1
+echo "launch list rc=$?"; wc -l $out/r2_launches_bench.csv
