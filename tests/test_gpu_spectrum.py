@@ -29,12 +29,12 @@ N_GPU_SEEDS = 64
 
 
 def report(section, values):
-    """measured parity numbers -> gpurun_out/parity_report.json (copied to profiles/ for the record)"""
+    """measured parity numbers -> the JSON file named by GRMONTY_B200_PARITY_REPORT, if set (tools/gpu_r2_check.sh sets
+    it; the file is copied to profiles/ for the record).  Without the variable the test writes nothing."""
     import json
-    out = os.path.join(ROOT, "gpurun_out")
-    if not os.path.isdir(out):
+    path = os.environ.get("GRMONTY_B200_PARITY_REPORT")
+    if not path:
         return
-    path = os.path.join(out, "parity_report.json")
     data = json.load(open(path)) if os.path.exists(path) else {}
     data[section] = values
     json.dump(data, open(path, "w"), indent=1)

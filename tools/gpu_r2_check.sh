@@ -3,7 +3,8 @@
 set -u
 out=gpurun_out
 mkdir -p $out
-timeout 2400 python -m pytest tests -m gpu -q --durations=15 > $out/r2_gputests.log 2>&1
+rm -f $out/parity_report.json
+GRMONTY_B200_PARITY_REPORT=$PWD/$out/parity_report.json timeout 2400 python -m pytest tests -m gpu -q --durations=15 > $out/r2_gputests.log 2>&1
 echo "tests rc=$?"; tail -60 $out/r2_gputests.log
 timeout 600 python bench.py --steps 3 --warmup 3 > $out/r2_bench.json 2> $out/r2_bench.err
 echo "bench rc=$?"; cat $out/r2_bench.json; tail -5 $out/r2_bench.err
