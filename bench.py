@@ -424,7 +424,7 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": "DFMA micro-benchmark in this process (grmonty_b200_fp64_peak); "
                                     "MEASURED_PEAKS.json has no FP64 entry",
-                     "kernel": "transport_kernel<256,1> (csrc/gm_kernels.cuh: the fused per-lane loop, one launch per generation)",
+                     "kernel": "transport_kernel<32,8> (csrc/gm_kernels.cuh: the fused per-lane loop, one launch per generation)",
                      "kernel_ms_per_step": transport_ms / args.steps},
         "device_ms_per_step": kernel_ms / args.steps, "init_s": init_s,
         "work_rates": {"tracked_photons_per_s": work_all[0] * args.steps / wall,

@@ -151,7 +151,7 @@ TEST_ABI_SYMBOLS = [
 # per thread)
 KERNEL_FUSED, KERNEL_WAVEFRONT = 1, 2
 OVERLAP_ON, OVERLAP_OFF = 1, 2     # grmonty_b200_config.gen_overlap
-KERNEL_VARIANTS = [(1, 256, 1), (1, 64, 4), (1, 128, 2), (1, 384, 1),
+KERNEL_VARIANTS = [(1, 32, 8), (1, 256, 1), (1, 64, 4), (1, 128, 2), (1, 384, 1),
                    (2, 384, 2), (2, 256, 2), (2, 256, 3), (2, 512, 1), (2, 384, 1), (2, 128, 2)]
 
 _libs = {}

@@ -96,6 +96,7 @@ struct grmonty_b200_ctx {
     long long perm_mult = 1; /* Weyl multiplier of the processing order */
     unsigned int gen_tag = 0;
     int threads = 128, blocks_per_sm = 0, grid_blocks = 0;
+    int want_bps = 1; /* blocks per SM of the compiled variant in use */
     int kernel = 0;                 /* 0: wavefront, 1: fused loop of round 1 */
     /* pipelined generations (gm_pipeline.cuh): device-side generation clock, one launch per window of generations */
     int overlap = 1;
@@ -171,7 +172,8 @@ struct Variant {
     TransportFn pipe_fn; /* overlapping generations (gm_pipeline.cuh) */
 };
 #define GM_V(B, M) {B, M, transport_kernel<B, M>, pipeline_kernel<B, M>}
-static const Variant kVariants[] = {GM_V(128, 2), GM_V(128, 3), GM_V(256, 1), GM_V(64, 4), GM_V(384, 1), GM_V(512, 1)};
+static const Variant kVariants[] = {GM_V(128, 2), GM_V(128, 3), GM_V(256, 1), GM_V(64, 4), GM_V(32, 8),
+                                    GM_V(384, 1), GM_V(512, 1)};
 #undef GM_V
 static const Variant *find_variant(int block, int min_blocks) {
     for (const Variant &v : kVariants)
@@ -592,8 +594,14 @@ int grmonty_b200_create(grmonty_b200_ctx **out, const grmonty_b200_config *cfg) 
             if (const char *e = getenv("GRMONTY_B200_WF_THR")) /* "interact,service" in 1/256 (tools/ sweeps) */
                 sscanf(e, "%d,%d", &ctx->wf_thr_interact, &ctx->wf_thr_service);
         } else {
-            ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;
-            int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : 1;
+            /* default geometry 32 x 8: 8 warps/SM like 256 x 1 (255 registers: two warps per scheduler is what the
+             * register file holds), each warp a block of its own -- no warp ever waits at a block barrier for another
+             * one's rare slow path.  Measured per configs[1] run: 578 (32 x 8), 586 (64 x 4), 589 (128 x 2), 593 ms
+             * (256 x 1); configs[0]: 113 against 128 ms; fewer warps lose in proportion (7: 619, 6: 668 ms), a ninth
+             * would need 168 registers (three warps on one scheduler).  profiles/r2_ab_microopts.txt */
+            ctx->threads = cfg->threads_per_block > 0 ? cfg->threads_per_block : 32;
+            int want_bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (cfg->threads_per_block > 0 ? 1 : 8);
+            ctx->want_bps = want_bps;
             const Variant *v = find_variant(ctx->threads, want_bps);
             if (!v)
                 return fail(ctx, GRMONTY_B200_EINVAL, "no compiled kernel variant for %d threads x %d blocks/SM",
@@ -734,7 +742,7 @@ static int begin_batch(grmonty_b200_ctx *ctx, long long count) {
 static int run_batch(grmonty_b200_ctx *ctx, long long first, long long stride, long long count,
                      const GmBiasStats &bias, const DebugOut &dbg, bool preloaded, int budget) {
     const Variant *v = ctx->kernel == 0 ? nullptr
-                                        : find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
+                                        : find_variant(ctx->threads, ctx->want_bps);
     /* the device-global copy of the arguments is written on the batch's own stream, ahead of the kernels that read it
      * through A.self; the source lives in the context and is rewritten only after the batch's final synchronisation */
     TransportArgs &args = ctx->h_args;
@@ -936,7 +944,7 @@ static int read_bias_stats(grmonty_b200_ctx *ctx, GmBiasStats *b) {
  * generations -- runs on the device and continues across windows. */
 static int run_range_pipelined(grmonty_b200_ctx *ctx, long long first, long long last) {
     const long long world = ctx->cfg.world, rank = ctx->cfg.rank;
-    const Variant *v = find_variant(ctx->threads, ctx->cfg.blocks_per_sm > 0 ? ctx->cfg.blocks_per_sm : 1);
+    const Variant *v = find_variant(ctx->threads, ctx->want_bps);
     /* ---- the generations of this call (same partition as the round-1 scheduler and the oracle) ---- */
     struct Gen {
         long long f0, count, pos_end;

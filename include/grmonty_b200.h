@@ -117,7 +117,7 @@ typedef struct grmonty_b200_config {
                                doubling with budget 256 gives +5.8 % scattered / +2.5 % recorded counts,
                                div 6 with budget 384 gives +0.6 % / +0.1 %. */
     /* Transport kernel.  0 (default) or 1: the fused per-lane loop (threads_per_block x blocks_per_sm as compiled in
-     * csrc/gm_api.cu; default 256 x 1).  2: the state-compacting wavefront kernel (csrc/gm_wavefront.cuh) -- photons
+     * csrc/gm_api.cu; default 32 x 8: one warp per block, eight blocks per SM).  2: the state-compacting wavefront kernel (csrc/gm_wavefront.cuh) -- photons
      * resident in shared memory, `slots_per_thread` of them per thread (default 2), the block runs push / interact /
      * service / scatter phases chosen by lane counts; threads_per_block 128 ... 512 (default 384).  The wavefront
      * kernel is the slower of the two on B200 (profiles/r2_wavefront_vs_fused.txt) and is kept as a selectable
