@@ -161,8 +161,8 @@ template <typename T> static cudaError_t upload(grmonty_b200_ctx *ctx, T **dst, 
     return cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
 }
 
-/* dynamic shared memory of the transport kernel: 13 snapshot rows per thread */
-static size_t transport_smem_bytes(int threads) { return (size_t)13 * threads * sizeof(double); }
+/* dynamic shared memory of the transport kernel: 13 snapshot rows + 6 pending-record rows per thread */
+static size_t transport_smem_bytes(int threads) { return (size_t)kTransportSmemRows * threads * sizeof(double); }
 
 /* ---- kernel dispatch over the compiled (block, min-blocks) variants ------------------------------------- */
 typedef void (*TransportFn)(const TransportArgs);

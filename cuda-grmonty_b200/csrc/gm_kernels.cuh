@@ -298,17 +298,45 @@ __device__ __noinline__ void cost_call(const TransportArgs *Ag, unsigned int slo
 #endif
 constexpr int kItersPerSync = GM_ITERS_PER_SYNC;
 
+/* Record stage compaction.  A photon that ends is recorded (12 RED.F64 + counters, after 7 loads of its cold record
+ * fields and a logarithm) and its lifetime is booked for the issue order: ~3 us of a warp's time when ONE lane does
+ * it while 31 wait -- 5.7 % of the transport kernel's stall samples (ncu, round 2).  So the lane only leaves what the
+ * record needs in shared memory (5 doubles, slot, n_step) and takes its next photon; when kRecordBatch lanes of the
+ * warp have one pending -- or the warp has nothing else to do, or a lane ends a second photon first -- they record
+ * together: one call, the loads in parallel, and __match_any_sync combines the lanes that hit the same bin. */
+#ifndef GM_RECORD_BATCH
+#define GM_RECORD_BATCH 12
+#endif
+constexpr int kRecordBatch = GM_RECORD_BATCH; /* 0: record at once (round 1) */
+/* (Measured and rejected, profiles/r2_ab_microopts.txt: the same deferral for the publication of a photon parked for
+ * the scattering stage -- one fence and one fetch-add per warp for several lanes -- costs 7 % at configs[1] and 20 % at
+ * configs[0]: scattered photons are on the critical path of their lineage, recorded ones are not.) */
+constexpr int kTransportSmemRows = 13 + 6; /* snapshot rows + pending-record rows per thread */
+
 template <int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const TransportArgs A) {
-    /* Control words shared by the block.  The warps of a block run the loop in lockstep (one barrier per
-     * iteration): they then execute the same code region at the same time, which matters because the loop body
-     * (~60 KB of SASS) does not fit the instruction cache -- with free-running warps ncu showed 72% of all
-     * stall cycles as "no instruction". */
+    /* Control words shared by the block.  (Default geometry since round 2: one warp per block, eight blocks per SM;
+     * with larger blocks the warps of a block re-align at the barrier of every outer iteration -- see DESIGN.md,
+     * "Block lockstep".) */
     __shared__ unsigned long long s_base; /* first scatter-queue position claimed for the block */
     __shared__ int s_count;               /* number of scatter-queue entries claimed (0: no service) */
     __shared__ int s_quit;
     const int lane = threadIdx.x & 31;
     double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
+    double *pend = gm_smem + (size_t)13 * BLOCK + threadIdx.x; /* 6 rows: x2 x3 w tau_abs tau_scatt (slot, n_step) */
+    int pending = 0; /* bit 0: lifetime to be booked, bit 1: record to be made (data in `pend`) */
+    /* the lanes that have something pending do it together */
+    auto flush_pending = [&]() {
+        if (pending) {
+            const int2 sn = *reinterpret_cast<const int2 *>(pend + 5 * BLOCK);
+            if (pending & 1)
+                cost_call(A.self, (unsigned int)sn.x, sn.y);
+            if (pending & 2)
+                record_call(A.self, (unsigned int)sn.x, pend[0], pend[BLOCK], pend[2 * BLOCK], pend[3 * BLOCK],
+                            pend[4 * BLOCK]);
+            pending = 0;
+        }
+    };
     Live L;
     bool has = false;
     long long ticket = -1; /* position in the ready queue this lane is entitled to (monotone queue, no wrap) */
@@ -408,11 +436,23 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                 bool record;
                 const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
                 if (r == STEP_FINISHED) {
-                    cost_call(A.self, L.slot, L.n_step);
-                    if (record) {
-                        record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
-                        L.status |= 1;
+                    if (kRecordBatch > 0) {
+                        if (pending)
+                            flush_pending(); /* rare: a second photon ended before the first was recorded */
+                        pend[0] = L.x[2];
+                        pend[BLOCK] = L.x[3];
+                        pend[2 * BLOCK] = L.w;
+                        pend[3 * BLOCK] = L.tau_abs;
+                        pend[4 * BLOCK] = L.tau_scatt;
+                        *reinterpret_cast<int2 *>(pend + 5 * BLOCK) = make_int2((int)L.slot, L.n_step);
+                        pending = 1 | (record ? 2 : 0);
+                    } else {
+                        cost_call(A.self, L.slot, L.n_step);
+                        if (record)
+                            record_call(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt);
                     }
+                    if (record)
+                        L.status |= 1;
                     if (A.D.final_state && L.slot < A.D.n) {
                         double *o = A.D.final_state + (size_t)L.slot * 12;
 #pragma unroll
@@ -440,8 +480,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                     ++n_done; /* done as far as this generation is concerned */
                 }
             }
+            if (kRecordBatch > 0 && __popc(__ballot_sync(0xffffffffu, pending != 0)) >= kRecordBatch)
+                flush_pending();
         }
         /* ---- publish finished counts; is the whole block out of work? ---- */
+        if (kRecordBatch > 0 && !__ballot_sync(0xffffffffu, has))
+            flush_pending(); /* nothing else to do in this warp */
         {
             int s = n_done;
 #pragma unroll
