@@ -312,6 +312,26 @@ constexpr int kRecordBatch = GM_RECORD_BATCH; /* 0: record at once (round 1) */
  * the scattering stage -- one fence and one fetch-add per warp for several lanes -- costs 7 % at configs[1] and 20 % at
  * configs[0]: scattered photons are on the critical path of their lineage, recorded ones are not.) */
 constexpr int kTransportSmemRows = 13 + 6; /* snapshot rows + pending-record rows per thread */
+/* Per-photon debug output (end state and status bits of the test exports' batches, TransportArgs::D) is compiled into
+ * the TEST library only: in the product it is ~60 instructions of the loop body that never run -- and the loop body
+ * sits at the edge of the instruction cache, where every KB shows (profiles/r2_ab_microopts.txt). */
+/* The per-lane loop-iteration counters behind grmonty_b200_stats::n_live_iterations / n_slot_iterations (lane
+ * occupancy) likewise: two registers and two instructions per iteration, 1 % of the run time; the test library and
+ * the tools that read them (GRMONTY_B200_LIB=...libgrmonty_b200_test.so) have them, the product reports 0. */
+#ifndef GM_OCC_COUNTERS
+#ifdef GRMONTY_B200_TEST_EXPORTS
+#define GM_OCC_COUNTERS 1
+#else
+#define GM_OCC_COUNTERS 0
+#endif
+#endif
+#ifndef GM_DEBUG_OUT
+#ifdef GRMONTY_B200_TEST_EXPORTS
+#define GM_DEBUG_OUT 1
+#else
+#define GM_DEBUG_OUT 0
+#endif
+#endif
 
 template <int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const TransportArgs A) {
@@ -418,8 +438,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                             bad = bad || isnan(L.x[i]) || isnan(L.k[i]);
                         if (bad) {
                             ++n_done; /* invalid photon (reference :895-900): dropped */
+#if GM_DEBUG_OUT
                             if (A.D.status && slot < A.D.n)
                                 atomicOr(A.D.status + slot, 4);
+#endif
                         } else {
                             has = true;
                         }
@@ -430,9 +452,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
             if (!live_mask)
                 break; /* nothing to do in this warp: go to the barrier */
             /* one flattened iteration for every live lane */
+#if GM_OCC_COUNTERS
             ++wk.slot_iters;
+#endif
             if (has) {
+#if GM_OCC_COUNTERS
                 ++wk.live_iters;
+#endif
                 bool record;
                 const StepResult r = advance(A, L, live_mask, snap, BLOCK, wk, record);
                 if (r == STEP_FINISHED) {
@@ -453,6 +479,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                     }
                     if (record)
                         L.status |= 1;
+#if GM_DEBUG_OUT
                     if (A.D.final_state && L.slot < A.D.n) {
                         double *o = A.D.final_state + (size_t)L.slot * 12;
 #pragma unroll
@@ -467,6 +494,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) transport_kernel(const Tran
                         atomicOr(A.D.status + L.slot, L.status);
                         A.pool.rng[L.slot] = make_uint4(L.rng.id0, L.rng.id1, L.rng.id2, L.rng.ctr);
                     }
+#endif
                     has = false;
                     ++n_done;
                 } else if (r == STEP_SCATTER) {

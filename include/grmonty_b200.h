@@ -153,7 +153,9 @@ typedef struct grmonty_b200_stats {
     uint64_t n_kernel_launches;
     uint64_t queue_high_water;
     uint64_t n_live_iterations; /* loop iterations executed by a lane that held a live photon ... */
-    uint64_t n_slot_iterations; /* ... out of all loop iterations of all lanes: lane occupancy */
+    uint64_t n_slot_iterations; /* ... out of all loop iterations of all lanes: lane occupancy.  Counted by the test
+                                   library and the optional kernels only; the product's default kernel reports 0 (the
+                                   counters cost 1 % of the run time) */
     double kernel_ms;          /* device time of all kernels of the last run (CUDA events) */
     double transport_ms;       /* of which: the persistent transport kernel */
 } grmonty_b200_stats;

@@ -3,6 +3,6 @@ set -u
 out=gpurun_out
 for round in 1 2; do
  for pn in 1e6 1e5; do
-  timeout 900 python tools/gpu_sweep.py $pn gpurun_ab/lib_pb0.so,gpurun_ab/lib_pb4.so,gpurun_ab/lib_pb8.so,gpurun_ab/lib_pb16.so f0x0 2>&1 | sed 's/"wall_ms": [0-9.]*, //; s/"rate".*"recorded"/"recorded"/' | cut -c1-170 | tee -a $out/r2_parkbatch.txt
+  timeout 900 python tools/gpu_sweep.py $pn gpurun_ab/lib_dbg1.so,gpurun_ab/lib_dbg0.so,gpurun_ab/lib_occ0.so f0x0 2>&1 | sed 's/"wall_ms": [0-9.]*, //; s/"rate".*"recorded"/"recorded"/' | cut -c1-170 | tee -a $out/r2_footprint.txt
  done
 done
