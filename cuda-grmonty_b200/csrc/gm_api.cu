@@ -5,6 +5,12 @@
  * (reference cuda_grmonty/super_photon.cuh:29-61, super_photon.cu:447-1037) with a context object,
  * on-device photon generation and one persistent kernel per generation.  No CPU fallback exists: every
  * entry point needs a CUDA device and fails with GRMONTY_B200_ECUDA otherwise.
+ *
+ * Two generation schedulers live here: run_batch / grmonty_b200_run_range (one launch per generation, statistics of
+ * all earlier generations; the default) and run_range_pipelined (one persistent launch per window of generations,
+ * generation clock on the device, csrc/gm_pipeline.cuh; grmonty_b200_config::gen_overlap = 1 / 3).  Three kernels:
+ * transport_kernel (fused per-lane loop, the default), wavefront_kernel (csrc/gm_wavefront.cuh, config kernel = 2),
+ * pipeline_kernel.  DESIGN.md section 3 has the measurements behind the defaults.
  */
 #include <cuda_profiler_api.h>
 #include <cuda_runtime.h>

@@ -3,7 +3,9 @@
  *
  *   zone_kernel       per-zone emission data: photon count, dn_max, fluid state, tetrad   (once per context)
  *   birth_kernel      make_super_photon for one generation of primaries -> photon queue   (per generation)
- *   transport_kernel  persistent wavefront: pop / track / scatter / record                (per generation)
+ *   transport_kernel  persistent loop: pop / track / scatter stage / deferred record stage (per generation)
+ *                     (default geometry one warp per block, eight blocks per SM; gm_wavefront.cuh and gm_pipeline.cuh
+ *                     hold the two optional kernels built on the same device functions)
  *
  * Reference functions restated: init_zone harm_model.cpp:1337-1389, get_zone :673-704,
  * sample_zone_photon :706-782, linear_interp_weight :784-792, run_simulation CPU loop :366-404.

@@ -22,9 +22,17 @@
  *     sees >= 32 parked photons processes them with all 32 lanes active, keeping its own live photons in
  *     registers meanwhile.  (ncu on the inline version: 10.8 of 32 threads active per instruction.)
  *   - push_photon's recursive halving is flattened: one loop iteration = one push attempt for every lane.
+ *   - Record stage compaction (round 2): a photon's end is not handled inline by its one lane either.  The
+ *     lane leaves what the record needs in shared memory and takes its next photon; the warp makes the
+ *     records of 12 lanes together (gm_kernels.cuh, kRecordBatch).  Recorded photons are off the critical
+ *     path of their lineage, so the deferral costs nothing; parked (scattering) photons are on it, and the
+ *     same deferral for their publication was measured to lose.
  *   - Spectrum bins / counters use global atomics (RED.F64) aggregated per warp by bin.
  *   - Scattering-bias statistics are frozen per generation (GmBiasStats): results do not depend on the
  *     order in which the hardware happens to finish photons.
+ *   - The device functions here are shared by the three kernels (fused loop, wavefront, pipelined
+ *     scheduler) through template switches (DEFER_PARK, PIPE): per-photon results are identical by
+ *     construction, and tests/test_gpu_invariance.py checks it.
  */
 #pragma once
 #include "gm_geometry.cuh"
