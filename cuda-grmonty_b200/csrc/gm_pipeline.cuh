@@ -173,6 +173,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) pipeline_kernel(const Trans
     __shared__ volatile unsigned long long s_prim_lim;
     const int lane = threadIdx.x & 31;
     double *snap = gm_smem + threadIdx.x; /* 13 rows of BLOCK doubles */
+    /* Record stage compaction as in transport_kernel (gm_kernels.cuh): a lane whose photon escaped leaves what the
+     * record needs here (x2 x3 w tau_abs tau_scatt, slot / generation tag) and takes its next photon; the warp makes
+     * the records of kRecordBatch lanes together -- and at the end of every outer iteration at the latest, because
+     * here the photon counts as DONE in its generation only once its record is made (the generation's statistics are
+     * folded into the run totals when done == alloc). */
+    double *pend = gm_smem + (size_t)13 * BLOCK + threadIdx.x;
+    bool pending = false;
     GenCtl *const C = A.ctl;
     unsigned long long *const line = C->line;
     Live L;
@@ -357,10 +364,26 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) pipeline_kernel(const Trans
                 bool record;
                 const StepResult r = advance<true>(A, L, live_mask, snap, BLOCK, wk, record, s_bias);
                 if (r == STEP_FINISHED) {
-                    if (record)
-                        record_call_pipe(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt, (L.status >> 4) & 3);
+                    if (record && kRecordBatch > 0) {
+                        if (pending) { /* rare: a second photon escaped before the first was recorded */
+                            const int2 st = *reinterpret_cast<const int2 *>(pend + 5 * BLOCK);
+                            record_call_pipe(A.self, (unsigned int)st.x, pend[0], pend[BLOCK], pend[2 * BLOCK],
+                                             pend[3 * BLOCK], pend[4 * BLOCK], st.y);
+                            done_pk += 1ull << (16 * st.y);
+                        }
+                        pend[0] = L.x[2];
+                        pend[BLOCK] = L.x[3];
+                        pend[2 * BLOCK] = L.w;
+                        pend[3 * BLOCK] = L.tau_abs;
+                        pend[4 * BLOCK] = L.tau_scatt;
+                        *reinterpret_cast<int2 *>(pend + 5 * BLOCK) = make_int2((int)L.slot, (L.status >> 4) & 3);
+                        pending = true; /* counted as done when the record is made */
+                    } else {
+                        if (record)
+                            record_call_pipe(A.self, L.slot, L.x[2], L.x[3], L.w, L.tau_abs, L.tau_scatt, (L.status >> 4) & 3);
+                        done_pk += 1ull << (16 * ((L.status >> 4) & 3));
+                    }
                     has = false;
-                    done_pk += 1ull << (16 * ((L.status >> 4) & 3));
                 } else if (r == STEP_SCATTER) {
                     has = false; /* parked for the scattering stage */
                 } else if (r == STEP_SUSPEND) {
@@ -372,10 +395,24 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) pipeline_kernel(const Trans
                     done_pk += 1ull << (16 * ((L.status >> 4) & 3)); /* left this generation */
                 }
             }
+            if (kRecordBatch > 0 && __popc(__ballot_sync(0xffffffffu, pending)) >= kRecordBatch && pending) {
+                const int2 st = *reinterpret_cast<const int2 *>(pend + 5 * BLOCK);
+                record_call_pipe(A.self, (unsigned int)st.x, pend[0], pend[BLOCK], pend[2 * BLOCK], pend[3 * BLOCK],
+                                 pend[4 * BLOCK], st.y);
+                done_pk += 1ull << (16 * st.y);
+                pending = false;
+            }
             if ((sub & (kDoneFlushEvery - 1)) == kDoneFlushEvery - 1 && __ballot_sync(0xffffffffu, done_pk != 0ull)) {
                 pipe_flush_done(C, done_pk);
                 done_pk = 0ull;
             }
+        }
+        if (pending) { /* end of the outer iteration: no record waits longer than this */
+            const int2 st = *reinterpret_cast<const int2 *>(pend + 5 * BLOCK);
+            record_call_pipe(A.self, (unsigned int)st.x, pend[0], pend[BLOCK], pend[2 * BLOCK], pend[3 * BLOCK],
+                             pend[4 * BLOCK], st.y);
+            done_pk += 1ull << (16 * st.y);
+            pending = false;
         }
         if (__ballot_sync(0xffffffffu, done_pk != 0ull)) {
             pipe_flush_done(C, done_pk);
