@@ -207,14 +207,13 @@ def ncu_traffic():
                    key=lambda f: (int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)), os.path.getmtime(f)))
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for f in reversed(files):
-        tot, n = 0.0, 0
+        got = {}
         for ln in open(f):
             m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.eE+-]+)\s+(\w+)", ln)
-            if m and m.group(3) in scale:
-                tot += float(m.group(2)) * scale[m.group(3)]
-                n += 1
-        if n == 2:
-            return tot, os.path.relpath(f, ROOT)
+            if m and m.group(3) in scale and m.group(1) not in got:   # the file's FIRST capture is the default kernel's
+                got[m.group(1)] = float(m.group(2)) * scale[m.group(3)]
+        if len(got) == 2:
+            return got["read"] + got["write"], os.path.relpath(f, ROOT)
     return None, "no ncu summary under profiles/"
 
 

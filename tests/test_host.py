@@ -309,3 +309,31 @@ def test_dump_cache_with_concurrent_readers(tmp_path):
     m.set_dump_cache(True)
     m.read_file(p)
     assert m.read_from_cache()
+
+
+def test_config_struct_matches_the_header(tmp_path):
+    """the ctypes mirror of grmonty_b200_config / grmonty_b200_stats must have the size and ABI version a C compiler
+    gives the structs of include/grmonty_b200.h (create() rejects a mismatch, but only on a GPU box)"""
+    import ctypes as C
+    import subprocess
+    import cuda_grmonty_b200 as gm
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "grmonty_b200.h"\n'
+                   'int main(void) { printf("%d %zu %zu\\n", GRMONTY_B200_ABI_VERSION, sizeof(grmonty_b200_config), '
+                   'sizeof(grmonty_b200_stats)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    ver, cfg_size, stats_size = (int(v) for v in subprocess.check_output([str(exe)], text=True).split())
+    assert ver == gm.ABI_VERSION
+    assert cfg_size == C.sizeof(gm.Config)
+    assert stats_size == C.sizeof(gm.Stats)
+
+
+def test_bench_reads_the_roofline_traffic_from_the_committed_ncu_summary():
+    """roofline.traffic is the dram__bytes_read + dram__bytes_write of the newest committed transport-kernel capture"""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, source = bench.ncu_traffic()
+    assert traffic and traffic > 1e8
+    assert source.startswith("profiles/r2_transport_ncu")
