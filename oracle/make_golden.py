@@ -300,7 +300,7 @@ if __name__ == "__main__":
         gen_samplers()
     elif what == "spectrum":
         gen_spectrum()
-    elif what in ("spectrum_1e6", "spectrum_1e6_more", "spectrum_1e6_more2"):
+    elif what in ("spectrum_1e6", "spectrum_1e6_more", "spectrum_1e6_more2", "spectrum_1e6_more3"):
         pass  # handled at the end of the file
     elif what == "spectrum_4e20":  # configs[3]: Compton-dominated regime, 8 seeds at photon_n = 2e4
         gen_spectrum(photon_n=20000, seeds=8, mass_units=(4e20,))
@@ -461,3 +461,6 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "functions_gr
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6_more2":
     # six further seeds (514..519): 20 complete reference runs at the bench's photon_n in total
     gen_spectrum_big(seeds=6, first_seed=14, name="spectrum_192_4e19_1e6_more2.npz")
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spectrum_1e6_more3":
+    # seven further seeds (520..526): 27 complete reference runs at the bench's photon_n in total
+    gen_spectrum_big(seeds=7, first_seed=20, name="spectrum_192_4e19_1e6_more3.npz")
