@@ -331,9 +331,16 @@ def gen_spectrum_big(photon_n=1000000, seeds=6, mu=4e19, first_seed=0, name="spe
                "--seed", str(500 + s), "--hotcross_cache", rh.HOTCROSS_CACHE, "--spectrum_bin", sb]
         procs.append((subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True), sb))
     metas, specs = [], []
-    for p, sb in procs:
+    for i, (p, sb) in enumerate(procs):
         o, _ = p.communicate()
-        metas.append(json.loads(o.strip().splitlines()[-1]))
+        line = next((ln for ln in reversed(o.splitlines()) if ln.startswith("{")), None)
+        if p.returncode != 0 or line is None or not os.path.exists(sb):
+            # the reference has undefined behaviour on some photon paths: a run that dies is
+            # dropped and reported, the ensemble is made of the runs that completed
+            print(f"seed {500 + first_seed + i}: reference process ended with rc={p.returncode}, no result: dropped",
+                  file=sys.stderr)
+            continue
+        metas.append(json.loads(line))
         specs.append(np.fromfile(sb).reshape(6, 200, 13)[:, :, [0, 1, 2, 3]])
     np.savez_compressed(os.path.join(GOLD, name), photon_n=np.array(photon_n), first_seed=np.array(500 + first_seed),
                         mass_unit=np.array(mu), created=np.array([m["created"] for m in metas]),
