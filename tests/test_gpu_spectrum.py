@@ -157,13 +157,14 @@ def conditional_residual(g_tau, g_val, r_tau, r_val, n_boot=2000):
 
 
 def test_bench_workload_photon_n_1e6_vs_reference():
-    """configs[1] (the bench workload, photon_n = 1e6): 32 CUDA runs against all 20 complete runs of the reference CLI
-    (31 - 40 minutes each on one core; tests/golden/spectrum_192_4e19_1e6.npz + ..._1e6_more.npz + ..._1e6_more2.npz,
-    written by `oracle/make_golden.py spectrum_1e6` / `spectrum_1e6_more` / `spectrum_1e6_more2`).
+    """configs[1] (the bench workload, photon_n = 1e6): 32 CUDA runs against all 26 complete runs of the reference CLI
+    (31 - 40 minutes each on one core; tests/golden/spectrum_192_4e19_1e6.npz + ..._1e6_more.npz + ..._more2.npz + ..._more3.npz,
+    written by `oracle/make_golden.py spectrum_1e6` / `spectrum_1e6_more` / `..._more2` / `..._more3`; a 27th run,
+    seed 526, died of the reference's own undefined behaviour and is not part of the ensemble).
 
     Luminosity and the spectrum are bias-independent observables and get hard bars.  The recorded / scattered COUNTS
     are not: the reference's scattering bias is ~ 1 / (running maximum of tau_scatt) (harm_model.cpp:1296,1391-1404),
-    so a run whose maximum jumped early ends with fewer, heavier scattered superphotons -- one of the 20 reference runs
+    so a run whose maximum jumped early ends with fewer, heavier scattered superphotons -- one of the 26 reference runs
     ends 32 % below the others for exactly that reason, and the per-run spread of the scattered count is 10 %.  The
     CUDA path keeps the same statistic and has the same tail.  Comparing ensemble means would therefore be decided by
     whether such a run is in the sample; the counts are compared at equal max_tau_scatt instead (median residual of the
@@ -172,9 +173,10 @@ def test_bench_workload_photon_n_1e6_vs_reference():
     import cuda_grmonty_b200 as gm
     from tools import make_harm_dump
     parts = [dict(np.load(os.path.join(ROOT, "tests", "golden", f))) for f in
-             ("spectrum_192_4e19_1e6.npz", "spectrum_192_4e19_1e6_more.npz", "spectrum_192_4e19_1e6_more2.npz")]
+             ("spectrum_192_4e19_1e6.npz", "spectrum_192_4e19_1e6_more.npz", "spectrum_192_4e19_1e6_more2.npz",
+              "spectrum_192_4e19_1e6_more3.npz")]
     ref = {k: np.concatenate([p[k] for p in parts]) for k in ("created", "recorded", "scattered", "max_tau_scatt", "spec")}
-    assert len(ref["recorded"]) == 20
+    assert len(ref["recorded"]) == 26
     dump = os.path.join(tempfile.mkdtemp(), "dump192.txt")
     make_harm_dump.write_dump(dump, *make_harm_dump.make_dump(n0=192, n1=192))
     hm = gm.HarmModel(int(parts[0]["photon_n"]), float(parts[0]["mass_unit"]))
@@ -213,9 +215,9 @@ def test_bench_workload_photon_n_1e6_vs_reference():
     report("configs1_photon_n_1e6", rep | {"n_gpu_seeds": len(runs), "n_ref_seeds": int(len(r_lum))})
     assert abs(rep["luminosity"]["rel_diff_of_means"]) < 0.01 and rep["luminosity"]["std_err"] < 0.005
     for name in ("recorded", "scattered"):
-        assert rep[name]["std_err_conditional"] < 0.007, (name, rep[name])   # bootstrap estimate, 20 reference runs
+        assert rep[name]["std_err_conditional"] < 0.007, (name, rep[name])   # bootstrap estimate, 26 reference runs
         assert abs(rep[name]["ref_minus_cuda_at_equal_max_tau"]) < 0.01, (name, rep[name])
         # the unconditional means are heavy-tailed (see above): reported, and held to the bar within their own error
         assert abs(rep[name]["rel_diff_of_means"]) < 0.01 + 2 * rep[name]["std_err"], (name, rep[name])
-    assert rep["spectrum"]["chi2_per_bin"] < 1.6          # variances from 32 + 20 samples
+    assert rep["spectrum"]["chi2_per_bin"] < 1.6          # variances from 32 + 26 samples
     assert l1 < 0.02

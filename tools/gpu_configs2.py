@@ -52,7 +52,8 @@ if world > 1:
 if rank == 0:
     spec = res["spectrum"]
     parts = [dict(np.load(os.path.join(ROOT, "tests", "golden", f))) for f in
-             ("spectrum_192_4e19_1e6.npz", "spectrum_192_4e19_1e6_more.npz", "spectrum_192_4e19_1e6_more2.npz")]
+             ("spectrum_192_4e19_1e6.npz", "spectrum_192_4e19_1e6_more.npz", "spectrum_192_4e19_1e6_more2.npz",
+              "spectrum_192_4e19_1e6_more3.npz")]
     ref_lum = np.concatenate([q["spec"][..., 1].sum(axis=(1, 2)) for q in parts])
     lum = float(spec[:, :, 1].sum())
     total = ctx.total_primaries()
