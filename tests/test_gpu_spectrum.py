@@ -160,7 +160,7 @@ def test_bench_workload_photon_n_1e6_vs_reference():
     """configs[1] (the bench workload, photon_n = 1e6): 32 CUDA runs against all 26 complete runs of the reference CLI
     (31 - 40 minutes each on one core; tests/golden/spectrum_192_4e19_1e6.npz + ..._1e6_more.npz + ..._more2.npz + ..._more3.npz,
     written by `oracle/make_golden.py spectrum_1e6` / `spectrum_1e6_more` / `..._more2` / `..._more3`; a 27th run,
-    seed 526, died of the reference's own undefined behaviour and is not part of the ensemble).
+    seed 526, ended with SIGSEGV inside the reference binary after ~35 minutes and is not part of the ensemble).
 
     Luminosity and the spectrum are bias-independent observables and get hard bars.  The recorded / scattered COUNTS
     are not: the reference's scattering bias is ~ 1 / (running maximum of tau_scatt) (harm_model.cpp:1296,1391-1404),
